@@ -1,0 +1,245 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE'S OWN KERNELS (unmodified, imported from
+/root/reference) under Numba's CUDA simulator in the build container.  TEST INFRASTRUCTURE.
+
+    python -m oracle.make_golden            # ~2-3 minutes, writes tests/golden/ref_*.npz
+
+The reference has no tests or golden vectors of its own; these fixtures are what
+pins the oracle (tests/test_oracle_golden.py) and, through it, the CUDA engine.  Simulator caveats
+(SURVEY.md 8c): update_useq_numba is launched [1,1] (race 9-R1), costs_d is snapshotted between
+kernels (9-Q1), sampled-grid VALUES are only compared for bin values that are multiples of 1/4
+(NEP-50 vs compiled typing, 8c-iv).  Sizes are tiny: the simulator runs ~40 threads/s.
+"""
+import os
+import sys
+import io
+import contextlib
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _quiet(fn, *a, **k):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        return fn(*a, **k)
+
+
+def random_pmf(rng, B, H, W, zero_frac=0.3):
+    """int (B,H,W) PMF in percent summing to 100 per cell, with some empty bins."""
+    cuts = np.sort(rng.integers(0, 101, (B - 1, H, W)), axis=0)
+    pmf = np.empty((B, H, W), dtype=np.int64)
+    pmf[0] = cuts[0]
+    pmf[1:B - 1] = cuts[1:] - cuts[:-1]
+    pmf[B - 1] = 100 - cuts[B - 2]
+    # move the mass of some bins into the last bin to create zero-probability bins
+    kill = rng.random((B - 1, H, W)) < zero_frac
+    moved = np.where(kill, pmf[:B - 1], 0)
+    pmf[:B - 1] -= moved
+    pmf[B - 1] += moved.sum(axis=0)
+    assert (pmf.sum(axis=0) == 100).all() and (pmf >= 0).all()
+    return pmf
+
+
+def base_params(x0, xgoal, cvar_alpha=0.5):
+    return dict(dt=0.1, x0=np.asarray(x0, dtype=float), xgoal=np.asarray(xgoal, dtype=float),
+                goal_tolerance=0.5, v_post_rollout=0.01, cvar_alpha=cvar_alpha, alpha_dyn=1.0,
+                dist_weight=1.0, lambda_weight=1.0, num_opt=1,
+                u_std=np.array([2.0, 3.0]), vrange=np.array([0.0, 3.0]), wrange=np.array([-np.pi, np.pi]),
+                obs_penalty=1e5, unknown_penalty=1e2)
+
+
+def main():
+    from oracle.ref_loader import load_reference
+    Config, TDM_Numba, MPPI_Numba, cuda = load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    f32 = np.float32
+
+    # ---------------------------------------------------------------- 1. RNG + noise (mppi.py:118,1354-1370)
+    cfg = _quiet(Config, T=0.8, dt=0.1, num_grid_samples=1, num_control_rollouts=100, seed=1,
+                 max_map_dim=(30, 30), use_det_dynamics=True)
+    pl = _quiet(MPPI_Numba, cfg)
+    st0 = pl.rng_states_d.copy_to_host()
+    u_std_d = cuda.to_device(np.array([2.0, 3.0], dtype=f32))
+    MPPI_Numba.sample_noise_numba[100, 8](pl.rng_states_d, u_std_d, pl.noise_samples_d)
+    n1 = pl.noise_samples_d.copy_to_host().copy()
+    MPPI_Numba.sample_noise_numba[100, 8](pl.rng_states_d, u_std_d, pl.noise_samples_d)
+    n2 = pl.noise_samples_d.copy_to_host().copy()
+    st2 = pl.rng_states_d.copy_to_host()
+    np.savez_compressed(os.path.join(OUT, "ref_noise.npz"), seed=1, N=100, T=8, u_std=[2.0, 3.0],
+                        states0=np.stack([st0["s0"], st0["s1"]], 1), noise1=n1, noise2=n2,
+                        states2=np.stack([st2["s0"], st2["s1"]], 1))
+    print("ref_noise done")
+
+    # ---------------------------------------------------------------- 2. PMF setters + grid sampling (terrain.py)
+    rng = np.random.default_rng(7)
+    B, H, W = 5, 14, 11
+    bin_values = np.array([0.0, 0.25, 0.5, 0.75, 1.0])
+    pmf_lin = random_pmf(rng, B, H, W)
+    pmf_ang = random_pmf(rng, B, H, W)
+    obstacle = (rng.random((H, W)) < 0.08).astype(np.int8)
+    unknown = (rng.random((H, W)) < 0.08).astype(np.int8)
+    res = 0.5
+    tdm_dict = dict(res=res, xlimits=np.array([1.0, 1.0 + W * res]), ylimits=np.array([-2.0, -2.0 + H * res]),
+                    bin_values=bin_values, bin_values_bounds=np.array([0.0, 1.0]), det_dynamics_cvar_alpha=0.3)
+    out = dict(pmf_lin=pmf_lin, pmf_ang=pmf_ang, obstacle=obstacle, unknown=unknown, res=res,
+               xlimits=tdm_dict["xlimits"], ylimits=tdm_dict["ylimits"], bin_values=bin_values,
+               bounds=[0.0, 1.0], max_speed_padding=5.0, dt=0.1, max_map_dim=[20, 18], seed=1,
+               thread_dim=[4, 3], M=3)
+    for mode, flags in (("tdm", dict(use_tdm=True)), ("det", dict(use_det_dynamics=True)),
+                        ("spd", dict(use_nom_dynamics_with_speed_map=True))):
+        for alpha in (0.3, 1.0):
+            cfg = _quiet(Config, T=1.0, dt=0.1, num_grid_samples=3, num_control_rollouts=100, seed=1,
+                         max_map_dim=(20, 18), tdm_sample_thread_dim=(4, 3), max_speed_padding=5.0, **flags)
+            tdm = _quiet(TDM_Numba, cfg)
+            d = dict(tdm_dict)
+            d["det_dynamics_cvar_alpha"] = alpha
+            _quiet(tdm.set_TDM_from_PMF_grid, pmf_lin, d, obstacle, unknown)
+            key = "%s_a%02d" % (mode, int(alpha * 10))
+            out[key + "_pmf_padded"] = tdm.pmf_grid_d.copy_to_host()
+            out[key + "_pxl"] = np.asarray(tdm.padded_xlimits)
+            out[key + "_pyl"] = np.asarray(tdm.padded_ylimits)
+            out[key + "_pad"] = tdm.pad_cells
+            out[key + "_obs_padded"] = tdm.obstacle_map_d.copy_to_host()
+            out[key + "_unk_padded"] = tdm.unknown_map_d.copy_to_host()
+            if mode == "spd":
+                out[key + "_risk"] = tdm.risk_traction_map_d.copy_to_host()
+            Hp, Wp = out[key + "_pmf_padded"].shape[1:]
+            # zero the (uninitialised) sample buffer so that unwritten cells are comparable
+            tdm.sample_grid_batch_d.copy_to_device(np.zeros(tdm.sample_grid_batch_d.shape, dtype=np.int8))
+            st = tdm.rng_states_d.copy_to_host()
+            out[key + "_states0"] = np.stack([st["s0"], st["s1"]], 1)
+            g1 = _quiet(tdm.sample_grids, 1.0).copy_to_host().copy()
+            g2 = _quiet(tdm.sample_grids, 0.6).copy_to_host().copy()
+            st = tdm.rng_states_d.copy_to_host()
+            out[key + "_grid1"] = g1
+            out[key + "_grid2"] = g2
+            out[key + "_states2"] = np.stack([st["s0"], st["s1"]], 1)
+            print("terrain", key, "done", g1.shape)
+    np.savez_compressed(os.path.join(OUT, "ref_terrain.npz"), **out)
+
+    # ---------------------------------------------------------------- 3. rollouts (mppi.py:613-1111)
+    rng = np.random.default_rng(11)
+    M, R, C = 6, 26, 24
+    Hp, Wp = 24, 22
+    lin = rng.integers(0, 101, (M, R, C)).astype(np.int8)
+    ang = rng.integers(0, 101, (M, R, C)).astype(np.int8)
+    lin[:, :Hp, :Wp][:, [0, 1, Hp - 2, Hp - 1], :] = 0
+    lin[:, :Hp, :Wp][:, :, [0, 1, Wp - 2, Wp - 1]] = 0
+    obs = (rng.random((Hp, Wp)) < 0.05).astype(np.int8)
+    unk = (rng.random((Hp, Wp)) < 0.05).astype(np.int8)
+    risk = rng.integers(5, 101, (1, Hp, Wp)).astype(np.int8)
+    res = f32(0.25)
+    xlim = np.array([-1.0, -1.0 + Wp * 0.25], dtype=f32)
+    ylim = np.array([2.0, 2.0 + Hp * 0.25], dtype=f32)
+    N, T = 24, 12
+    noise = (rng.standard_normal((N, T, 2)) * np.array([2.0, 3.0])).astype(f32)
+    u_cur = np.stack([rng.uniform(0, 2, T), rng.uniform(-1, 1, T)], 1).astype(f32)
+    x0 = np.array([1.7, 4.9, 0.4], dtype=f32)
+    xgoal_near = np.array([2.6, 5.6], dtype=f32)       # some rollouts reach it (early break)
+    xgoal_far = np.array([30.0, 30.0], dtype=f32)
+    common = dict(lin=lin, ang=ang, obs=obs, unk=unk, risk=risk, res=res, xlim=xlim, ylim=ylim,
+                  noise=noise, u_cur=u_cur, x0=x0, xgoal_near=xgoal_near, xgoal_far=xgoal_far,
+                  lin_bounds=[0.0, 1.0], ang_bounds=[0.0, 1.0], vrange=[0.0, 3.0], wrange=[-np.pi, np.pi],
+                  u_std=[2.0, 3.0], v_post=0.01, obs_cost=1e5, unk_cost=1e2, goal_tol=0.5, lam=1.0,
+                  dt=0.1, dist_weight=1.0)
+    dev = cuda.to_device
+
+    def launch_sto(goal, alpha, grids_l, grids_a, block):
+        costs_d = cuda.device_array((N,), dtype=f32)
+        MPPI_Numba.rollout_numba[N, block, 0, 4 * block](
+            dev(grids_l), dev(grids_a), dev(np.array([0, 1], f32)), dev(np.array([0, 1], f32)), dev(obs), dev(unk),
+            res, dev(xlim), dev(ylim), dev(np.array([0, 3], f32)), dev(np.array([-np.pi, np.pi], f32)), dev(goal),
+            f32(0.01), f32(1e5), f32(1e2), f32(0.5), f32(1.0), dev(np.array([2, 3], f32)), f32(alpha), dev(x0),
+            f32(0.1), 1.0, dev(noise), dev(u_cur), costs_d)
+        return costs_d.copy_to_host()
+
+    def launch_det(goal, speed_map):
+        costs_d = cuda.device_array((N,), dtype=f32)
+        args = [dev(lin[:1]), dev(ang[:1])]
+        if speed_map:
+            args.append(dev(risk))
+        args += [dev(np.array([0, 1], f32)), dev(np.array([0, 1], f32)), dev(obs), dev(unk),
+                 res, dev(xlim), dev(ylim), dev(np.array([0, 3], f32)), dev(np.array([-np.pi, np.pi], f32)), dev(goal),
+                 f32(0.01), f32(1e5), f32(1e2), f32(0.5), f32(1.0), dev(np.array([2, 3], f32)), dev(x0),
+                 f32(0.1), 1.0, dev(noise), dev(u_cur), costs_d]
+        k = MPPI_Numba.rollout_det_dyn_w_speed_map_numba if speed_map else MPPI_Numba.rollout_det_dyn_numba
+        k[N, 1](*args)
+        return costs_d.copy_to_host()
+
+    for gname, goal in (("near", xgoal_near), ("far", xgoal_far)):
+        # per-(n,m) costs from the reference itself: one-thread blocks on map m with alpha = 1
+        cnm = np.stack([launch_sto(goal, 1.0, lin[m:m + 1], ang[m:m + 1], 1) for m in range(M)], 1)
+        common["sto_cnm_" + gname] = cnm
+        for alpha in (0.5, 0.9, 1.0):
+            common["sto_cvar%02d_%s" % (int(alpha * 10), gname)] = launch_sto(goal, alpha, lin, ang, M)
+        common["det_" + gname] = launch_det(goal, False)
+        common["spd_" + gname] = launch_det(goal, True)
+        print("rollouts", gname, "done")
+    np.savez_compressed(os.path.join(OUT, "ref_rollout.npz"), **common)
+
+    # ---------------------------------------------------------------- 4. update (mppi.py:1113-1191), launched [1,1]
+    rng = np.random.default_rng(13)
+    Nu, Tu = 150, 9
+    costs = (rng.uniform(20, 30, Nu)).astype(f32)
+    noise_u = (rng.standard_normal((Nu, Tu, 2)) * np.array([2.0, 3.0])).astype(f32)
+    u0 = np.stack([rng.uniform(0, 2.9, Tu), rng.uniform(-3, 3, Tu)], 1).astype(f32)
+    upd = dict(costs=costs, noise=noise_u, u0=u0, vrange=[0.0, 3.0], wrange=[-np.pi, np.pi])
+    for lam in (1.0, 0.3):
+        c_d, w_d, u_d = dev(costs.copy()), cuda.device_array((Nu,), dtype=f32), dev(u0.copy())
+        MPPI_Numba.update_useq_numba[1, 1](f32(lam), c_d, dev(noise_u), w_d,
+                                          dev(np.array([0, 3], f32)), dev(np.array([-np.pi, np.pi], f32)), u_d)
+        upd["u_lam%02d" % int(lam * 10)] = u_d.copy_to_host()
+        upd["w_lam%02d" % int(lam * 10)] = w_d.copy_to_host()
+    np.savez_compressed(os.path.join(OUT, "ref_update.npz"), **upd)
+    print("update done")
+
+    # ---------------------------------------------------------------- 5. whole solve() through the public API
+    rng = np.random.default_rng(17)
+    B, H, W = 5, 12, 12
+    pmf_l = random_pmf(rng, B, H, W, zero_frac=0.2)
+    pmf_a = random_pmf(rng, B, H, W, zero_frac=0.2)
+    obstacle = (rng.random((H, W)) < 0.05).astype(np.int8)
+    unknown = (rng.random((H, W)) < 0.05).astype(np.int8)
+    res = 0.5
+    solve = dict(pmf_lin=pmf_l, pmf_ang=pmf_a, obstacle=obstacle, unknown=unknown, res=res,
+                 bin_values=bin_values, max_map_dim=[24, 24], N=100, M=4, T_s=0.6, dt=0.1, seed=1,
+                 thread_dim=[4, 4], max_speed_padding=5.0)
+    for mode, flags in (("tdm", dict(use_tdm=True)), ("det", dict(use_det_dynamics=True)),
+                        ("spd", dict(use_nom_dynamics_with_speed_map=True))):
+        cfg = _quiet(Config, T=0.6, dt=0.1, num_grid_samples=4, num_control_rollouts=100, seed=1,
+                     max_map_dim=(24, 24), tdm_sample_thread_dim=(4, 4), max_speed_padding=5.0, **flags)
+        lt, at = _quiet(TDM_Numba, cfg), _quiet(TDM_Numba, cfg)
+        d = dict(res=res, xlimits=np.array([0.0, W * res]), ylimits=np.array([0.0, H * res]),
+                 bin_values=bin_values, bin_values_bounds=np.array([0.0, 1.0]), det_dynamics_cvar_alpha=0.4)
+        _quiet(lt.set_TDM_from_PMF_grid, pmf_l, d, obstacle, unknown)
+        _quiet(at.set_TDM_from_PMF_grid, pmf_a, d, obstacle, unknown)
+        for t_ in (lt, at):
+            t_.sample_grid_batch_d.copy_to_device(np.zeros(t_.sample_grid_batch_d.shape, dtype=np.int8))
+        pl = _quiet(MPPI_Numba, cfg)
+        p = base_params([2.3, 3.1, 0.3], [5.0, 4.5], cvar_alpha=0.5)
+        pl.setup(p, lt, at)
+        # the reference's update kernel is racy in the simulator with 32 threads:
+        # run it with one thread by wrapping the launch configuration.
+        orig = MPPI_Numba.update_useq_numba
+
+        class _One:
+            def __getitem__(self, cfg_):
+                return orig[1, 1]
+        pl.update_useq_numba = _One()
+        u1 = _quiet(pl.solve).copy()
+        solve[mode + "_u1"] = u1
+        solve[mode + "_noise1"] = pl.noise_samples_d.copy_to_host().copy()
+        solve[mode + "_lin_grid1"] = lt.sample_grid_batch_d.copy_to_host().copy()
+        solve[mode + "_ang_grid1"] = at.sample_grid_batch_d.copy_to_host().copy()
+        pl.shift_and_update(np.array([2.4, 3.15, 0.35]), u1, num_shifts=1)
+        u2 = _quiet(pl.solve).copy()
+        solve[mode + "_u2"] = u2
+        solve[mode + "_weights2"] = pl.weights_d.copy_to_host().copy()
+        print("solve", mode, "done")
+    np.savez_compressed(os.path.join(OUT, "ref_solve.npz"), **solve)
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, os.path.dirname(HERE))
+    main()
