@@ -1,0 +1,741 @@
+// api.cu -- the C-ABI of include/b200mppi.h: handles, device buffers, and the per-solve launch
+// sequence that replaces the bodies of MPPI_Numba.solve_* (mppi_numba/mppi.py:237-451) and
+// TDM_Numba.sample_grids (terrain.py:610-622).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200mppi.h"
+#include "kernels.h"
+
+using namespace b200;
+
+// --------------------------------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return fail(B200MPPI_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+  } while (0)
+#define CHECK_LAUNCH() CU(cudaGetLastError())
+
+extern "C" const char* b200mppi_last_error(void) { return g_err.c_str(); }
+extern "C" int b200mppi_version(void) { return B200MPPI_VERSION; }
+extern "C" int b200mppi_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// --------------------------------------------------------------------------------------------- TDM
+struct b200mppi_tdm {
+  b200mppi_config cfg{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool det_dyn = false;
+  int num_maps = 1;           // M or 1
+  int pitch = 0;              // bytes per sample-grid row
+  int8_t* grid = nullptr;     // (num_maps, Rmax, pitch)
+  uint64_t* states = nullptr; // (num_gen, 2)
+  int64_t num_gen = 0;
+  // map
+  bool pmf_set = false, masks_set = false, risk_set = false;
+  int B = 0, bpad = 0, rows = 0, cols = 0;
+  int8_t* pmf = nullptr; int8_t* cum = nullptr; int8_t* qvals = nullptr;
+  size_t pmf_cap = 0, cum_cap = 0;
+  float bounds[2] = {0, 1};
+  float res = 1, pxl[2] = {0, 0}, pyl[2] = {0, 0};
+  int8_t* obstacle = nullptr; int8_t* unknown = nullptr; int8_t* risk = nullptr;
+  size_t mask_cap = 0, risk_cap = 0;
+  int mask_rows = 0, mask_cols = 0;
+  int64_t launches = 0;
+};
+
+static int tdm_sample_on(b200mppi_tdm* t, double alpha_dyn, cudaStream_t st) {
+  if (!t->pmf_set) return fail(B200MPPI_ESTATE, "sample_grids: PMF grid not set");
+  SampleGridsArgs a{};
+  a.grid = t->grid; a.cum = t->cum; a.states = t->states; a.qvals = t->qvals;
+  a.num_bins = t->B; a.bpad = t->bpad; a.rows = t->rows; a.cols = t->cols;
+  a.grid_rows = t->cfg.max_map_rows; a.pitch = t->pitch;
+  a.tx = t->cfg.tdm_thread_x; a.ty = t->cfg.tdm_thread_y; a.num_maps = t->num_maps;
+  a.alpha_dyn = alpha_dyn;
+  launch_sample_grids(a, st);
+  t->launches++;
+  CHECK_LAUNCH();
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_tdm_create(const b200mppi_config* cfg, b200mppi_tdm** out) {
+  if (!cfg || !out) return fail(B200MPPI_EINVAL, "tdm_create: null argument");
+  if (cfg->max_map_rows < 1 || cfg->max_map_cols < 1 || cfg->tdm_thread_x < 1 || cfg->tdm_thread_y < 1 ||
+      cfg->num_grid_samples < 1)
+    return fail(B200MPPI_EINVAL, "tdm_create: bad sizes");
+  if (b200mppi_device_count() < 1) return fail(B200MPPI_ECUDA, "tdm_create: no CUDA device (no CPU fallback)");
+  CU(cudaSetDevice(cfg->device));
+  b200mppi_tdm* t = new b200mppi_tdm();
+  t->cfg = *cfg;
+  t->det_dyn = cfg->mode != B200MPPI_MODE_TDM;
+  t->num_maps = t->det_dyn ? 1 : cfg->num_grid_samples;
+  t->pitch = round_up(cfg->max_map_cols, 16);
+  CU(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+  t->own_stream = true;
+  const size_t gbytes = (size_t)t->num_maps * cfg->max_map_rows * t->pitch;
+  CU(cudaMalloc(&t->grid, gbytes));
+  CU(cudaMemsetAsync(t->grid, 0, gbytes, t->stream));
+  t->num_gen = (int64_t)cfg->tdm_thread_x * cfg->tdm_thread_y * t->num_maps;
+  std::vector<uint64_t> h((size_t)t->num_gen * 2);
+  create_xoroshiro_states(h.data(), 0, t->num_gen, cfg->seed);
+  CU(cudaMalloc(&t->states, h.size() * sizeof(uint64_t)));
+  CU(cudaMemcpyAsync(t->states, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, t->stream));
+  CU(cudaStreamSynchronize(t->stream));
+  *out = t;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_tdm_destroy(b200mppi_tdm* t) {
+  if (!t) return B200MPPI_OK;
+  cudaSetDevice(t->cfg.device);
+  cudaFree(t->grid); cudaFree(t->states); cudaFree(t->pmf); cudaFree(t->cum); cudaFree(t->qvals);
+  cudaFree(t->obstacle); cudaFree(t->unknown); cudaFree(t->risk);
+  if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
+  delete t;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_tdm_set_stream(b200mppi_tdm* t, void* s) {
+  if (!t) return fail(B200MPPI_EINVAL, "null tdm");
+  if (t->own_stream && t->stream) { cudaStreamSynchronize(t->stream); cudaStreamDestroy(t->stream); }
+  t->stream = (cudaStream_t)s;
+  t->own_stream = false;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_tdm_set_pmf(b200mppi_tdm* t, const int8_t* pmf, int32_t B, int32_t rows, int32_t cols,
+                                    const float* bin_values, const float bounds[2], float res,
+                                    const float pxl[2], const float pyl[2]) {
+  if (!t || !pmf || !bin_values || !bounds || !pxl || !pyl) return fail(B200MPPI_EINVAL, "set_pmf: null argument");
+  if (B < 1 || B > 127 || rows < 1 || cols < 1) return fail(B200MPPI_EINVAL, "set_pmf: bad shape");
+  if (rows > t->cfg.max_map_rows || cols > t->cfg.max_map_cols)
+    return fail(B200MPPI_EINVAL, "set_pmf: padded PMF larger than max_map_dim (crop on the host first, terrain.py:562-583)");
+  CU(cudaSetDevice(t->cfg.device));
+  const int bpad = round_up(B, 4);
+  const size_t pbytes = (size_t)B * rows * cols, cbytes = (size_t)bpad * rows * cols;
+  if (pbytes > t->pmf_cap) { cudaFree(t->pmf); t->pmf = nullptr; CU(cudaMalloc(&t->pmf, pbytes)); t->pmf_cap = pbytes; }
+  if (cbytes > t->cum_cap) { cudaFree(t->cum); t->cum = nullptr; CU(cudaMalloc(&t->cum, cbytes)); t->cum_cap = cbytes; }
+  if (!t->qvals) CU(cudaMalloc(&t->qvals, 128));
+  CU(cudaMemcpyAsync(t->pmf, pmf, pbytes, cudaMemcpyHostToDevice, t->stream));
+  // quantised bin values, terrain.py:689 as compiled: int8(100.*(f32-f32)/f64(f32 range)), truncation
+  int8_t q[128];
+  std::memset(q, 0, sizeof(q));
+  const float range = bounds[1] - bounds[0];
+  for (int b = 0; b < B; ++b) {
+    const float d = bin_values[b] - bounds[0];
+    const double v = ((double)d * 100.0) / (double)range;
+    q[b] = (int8_t)(int16_t)std::trunc(v);
+  }
+  CU(cudaMemcpyAsync(t->qvals, q, 128, cudaMemcpyHostToDevice, t->stream));
+  launch_build_cum(t->pmf, t->cum, B, bpad, rows, cols, t->stream);
+  t->launches++;
+  CHECK_LAUNCH();
+  CU(cudaStreamSynchronize(t->stream));
+  t->B = B; t->bpad = bpad; t->rows = rows; t->cols = cols;
+  t->bounds[0] = bounds[0]; t->bounds[1] = bounds[1];
+  t->res = res; t->pxl[0] = pxl[0]; t->pxl[1] = pxl[1]; t->pyl[0] = pyl[0]; t->pyl[1] = pyl[1];
+  t->pmf_set = true;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_tdm_set_bin_quantisation(b200mppi_tdm* t, const int8_t* qvals, int32_t n) {
+  if (!t || !qvals) return fail(B200MPPI_EINVAL, "set_bin_quantisation: null argument");
+  if (!t->pmf_set || n != t->B) return fail(B200MPPI_EINVAL, "set_bin_quantisation: call after set_pmf with num_bins values");
+  CU(cudaSetDevice(t->cfg.device));
+  CU(cudaMemcpyAsync(t->qvals, qvals, (size_t)n, cudaMemcpyHostToDevice, t->stream));
+  CU(cudaStreamSynchronize(t->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_tdm_sample_grid_view(b200mppi_tdm* t, void** ptr, int32_t* pitch) {
+  if (!t) return fail(B200MPPI_EINVAL, "null tdm");
+  if (ptr) *ptr = t->grid;
+  if (pitch) *pitch = t->pitch;
+  return B200MPPI_OK;
+}
+
+static int upload_plane(b200mppi_tdm* t, int8_t** dst, size_t* cap, const int8_t* src, size_t bytes) {
+  if (bytes > *cap) { cudaFree(*dst); *dst = nullptr; CU(cudaMalloc(dst, bytes)); *cap = bytes; }
+  if (src) CU(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, t->stream));
+  else CU(cudaMemsetAsync(*dst, 0, bytes, t->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_tdm_set_masks(b200mppi_tdm* t, const int8_t* obs, const int8_t* unk, int32_t rows,
+                                      int32_t cols) {
+  if (!t) return fail(B200MPPI_EINVAL, "null tdm");
+  if (rows < 1 || cols < 1) return fail(B200MPPI_EINVAL, "set_masks: bad shape");
+  CU(cudaSetDevice(t->cfg.device));
+  const size_t bytes = (size_t)rows * cols;
+  size_t cap2 = t->mask_cap;
+  int rc = upload_plane(t, &t->obstacle, &t->mask_cap, obs, bytes);
+  if (rc) return rc;
+  rc = upload_plane(t, &t->unknown, &cap2, unk, bytes);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(t->stream));
+  t->mask_rows = rows; t->mask_cols = cols; t->masks_set = true;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_tdm_set_risk_map(b200mppi_tdm* t, const int8_t* risk, int32_t rows, int32_t cols) {
+  if (!t || !risk) return fail(B200MPPI_EINVAL, "set_risk_map: null argument");
+  CU(cudaSetDevice(t->cfg.device));
+  int rc = upload_plane(t, &t->risk, &t->risk_cap, risk, (size_t)rows * cols);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(t->stream));
+  t->risk_set = true;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_tdm_sample_grids(b200mppi_tdm* t, double alpha_dyn) {
+  if (!t) return fail(B200MPPI_EINVAL, "null tdm");
+  CU(cudaSetDevice(t->cfg.device));
+  int rc = tdm_sample_on(t, alpha_dyn, t->stream);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(t->stream));
+  return B200MPPI_OK;
+}
+
+static size_t tdm_grid_bytes(const b200mppi_tdm* t) {
+  return (size_t)t->num_maps * t->cfg.max_map_rows * t->cfg.max_map_cols;
+}
+
+extern "C" int b200mppi_tdm_get_sample_grids(b200mppi_tdm* t, int8_t* out, size_t bytes) {
+  if (!t || !out) return fail(B200MPPI_EINVAL, "null argument");
+  if (bytes != tdm_grid_bytes(t)) return fail(B200MPPI_EINVAL, "get_sample_grids: size mismatch");
+  CU(cudaSetDevice(t->cfg.device));
+  CU(cudaMemcpy2DAsync(out, t->cfg.max_map_cols, t->grid, t->pitch, t->cfg.max_map_cols,
+                       (size_t)t->num_maps * t->cfg.max_map_rows, cudaMemcpyDeviceToHost, t->stream));
+  CU(cudaStreamSynchronize(t->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_tdm_set_sample_grids(b200mppi_tdm* t, const int8_t* in, size_t bytes) {
+  if (!t || !in) return fail(B200MPPI_EINVAL, "null argument");
+  if (bytes != tdm_grid_bytes(t)) return fail(B200MPPI_EINVAL, "set_sample_grids: size mismatch");
+  CU(cudaSetDevice(t->cfg.device));
+  CU(cudaMemcpy2DAsync(t->grid, t->pitch, in, t->cfg.max_map_cols, t->cfg.max_map_cols,
+                       (size_t)t->num_maps * t->cfg.max_map_rows, cudaMemcpyHostToDevice, t->stream));
+  CU(cudaStreamSynchronize(t->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_tdm_num_generators(b200mppi_tdm* t, int64_t* out) {
+  if (!t || !out) return fail(B200MPPI_EINVAL, "null argument");
+  *out = t->num_gen;
+  return B200MPPI_OK;
+}
+extern "C" int b200mppi_tdm_get_rng_states(b200mppi_tdm* t, uint64_t* out, size_t bytes) {
+  if (!t || !out || bytes != (size_t)t->num_gen * 16) return fail(B200MPPI_EINVAL, "get_rng_states: bad argument");
+  CU(cudaSetDevice(t->cfg.device));
+  CU(cudaMemcpyAsync(out, t->states, bytes, cudaMemcpyDeviceToHost, t->stream));
+  CU(cudaStreamSynchronize(t->stream));
+  return B200MPPI_OK;
+}
+extern "C" int b200mppi_tdm_set_rng_states(b200mppi_tdm* t, const uint64_t* in, size_t bytes) {
+  if (!t || !in || bytes != (size_t)t->num_gen * 16) return fail(B200MPPI_EINVAL, "set_rng_states: bad argument");
+  CU(cudaSetDevice(t->cfg.device));
+  CU(cudaMemcpyAsync(t->states, in, bytes, cudaMemcpyHostToDevice, t->stream));
+  CU(cudaStreamSynchronize(t->stream));
+  return B200MPPI_OK;
+}
+
+// --------------------------------------------------------------------------------------------- planner
+struct b200mppi_planner {
+  b200mppi_config cfg{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int n_begin = 0, n_local = 0, T = 0, M = 1;
+  float* noise = nullptr; float* u_cur = nullptr; float* u_prev = nullptr;
+  float* costs = nullptr; float* weights = nullptr; float* costs_nm = nullptr; float* w_raw = nullptr;
+  float* cta_partials = nullptr; float* rank_partial = nullptr; float* state_rollout = nullptr;
+  uint64_t* states = nullptr;
+  float* h_u = nullptr;        // pinned staging for the T x 2 result
+  int num_ctas = 1, rows_per_cta = 1;
+  b200mppi_tdm* lin = nullptr; b200mppi_tdm* ang = nullptr;
+  b200mppi_params prm{};
+  bool params_set = false;
+  bool profiling = false;
+  cudaEvent_t ev[8] = {};
+  float last_ms[B200MPPI_T_COUNT] = {};
+  int64_t launches = 0;
+};
+
+static int planner_check_ready(b200mppi_planner* p) {
+  if (!p->lin || !p->ang) return fail(B200MPPI_ESTATE, "planner: TDMs not set");
+  if (!p->params_set) return fail(B200MPPI_ESTATE, "planner: params not set");
+  if (!p->lin->pmf_set || !p->ang->pmf_set) return fail(B200MPPI_ESTATE, "planner: TDM PMF not initialised");
+  if (!p->lin->masks_set) return fail(B200MPPI_ESTATE, "planner: obstacle/unknown maps not set on lin TDM");
+  if (p->cfg.mode == B200MPPI_MODE_SPEED_MAP && !p->lin->risk_set)
+    return fail(B200MPPI_ESTATE, "planner: risk traction map not set on lin TDM");
+  if (p->lin->rows != p->ang->rows || p->lin->cols != p->ang->cols)
+    return fail(B200MPPI_EINVAL, "planner: lin/ang TDM shapes differ");
+  if (p->lin->mask_rows != p->lin->rows || p->lin->mask_cols != p->lin->cols)
+    return fail(B200MPPI_EINVAL, "planner: mask shape differs from padded PMF shape");
+  if (p->cfg.mode == B200MPPI_MODE_TDM && p->M > 1024)
+    return fail(B200MPPI_EINVAL, "planner: num_grid_samples > 1024 is not supported (reference's oversized kernel is out of scope)");
+  return B200MPPI_OK;
+}
+
+static void fill_rollout_params(b200mppi_planner* p, RolloutParams& r) {
+  const b200mppi_tdm* l = p->lin; const b200mppi_tdm* a = p->ang;
+  r.g.res = l->res; r.g.inv_res = 1.0f / l->res;
+  r.g.xlo = l->pxl[0]; r.g.ylo = l->pyl[0];
+  r.g.rows = l->rows; r.g.cols = l->cols;
+  r.g.grid_rows = l->cfg.max_map_rows; r.g.grid_cols = l->cfg.max_map_cols; r.g.grid_pitch = l->pitch;
+  const b200mppi_params& q = p->prm;
+  r.dt = q.dt;
+  for (int i = 0; i < 3; ++i) r.x0[i] = q.x0[i];
+  r.xgoal[0] = q.xgoal[0]; r.xgoal[1] = q.xgoal[1];
+  r.tol2 = q.goal_tolerance * q.goal_tolerance;
+  r.v_post = q.v_post_rollout; r.lambda = q.lambda_weight;
+  r.u_std[0] = q.u_std[0]; r.u_std[1] = q.u_std[1];
+  r.vrange[0] = q.vrange[0]; r.vrange[1] = q.vrange[1];
+  r.wrange[0] = q.wrange[0]; r.wrange[1] = q.wrange[1];
+  r.obs_cost = q.obs_penalty; r.unk_cost = q.unknown_penalty; r.dist_weight = q.dist_weight;
+  r.lin_lo = l->bounds[0]; r.ang_lo = a->bounds[0];
+  r.lin_ratio = 0.01 * (double)(float)(l->bounds[1] - l->bounds[0]);
+  r.ang_ratio = 0.01 * (double)(float)(a->bounds[1] - a->bounds[0]);
+  r.T = p->T; r.N = p->n_local; r.M = p->M;
+}
+
+static void fill_update_args(b200mppi_planner* p, UpdateArgs& u, const float* costs) {
+  u.costs = costs ? costs : p->costs; u.noise = p->noise; u.w_raw = p->w_raw;
+  u.cta_partials = p->cta_partials; u.rank_partial = p->rank_partial; u.u_cur = p->u_cur;
+  u.weights = p->weights; u.N = p->n_local; u.T = p->T; u.num_ctas = p->num_ctas;
+  u.rows_per_cta = p->rows_per_cta; u.lambda = p->prm.lambda_weight;
+  u.vrange[0] = p->prm.vrange[0]; u.vrange[1] = p->prm.vrange[1];
+  u.wrange[0] = p->prm.wrange[0]; u.wrange[1] = p->prm.wrange[1];
+}
+
+extern "C" int b200mppi_planner_create(const b200mppi_config* cfg, b200mppi_planner** out) {
+  if (!cfg || !out) return fail(B200MPPI_EINVAL, "planner_create: null argument");
+  if (cfg->num_steps < 1 || cfg->num_steps > 1024 || cfg->num_control_rollouts < 1 || cfg->world_size < 1 ||
+      cfg->rank < 0 || cfg->rank >= cfg->world_size || cfg->num_grid_samples < 1)
+    return fail(B200MPPI_EINVAL, "planner_create: bad sizes (1 <= num_steps <= 1024)");
+  if (b200mppi_device_count() < 1) return fail(B200MPPI_ECUDA, "planner_create: no CUDA device (no CPU fallback)");
+  CU(cudaSetDevice(cfg->device));
+  b200mppi_planner* p = new b200mppi_planner();
+  p->cfg = *cfg;
+  const int64_t N = cfg->num_control_rollouts;
+  p->n_begin = (int)(N * cfg->rank / cfg->world_size);
+  p->n_local = (int)(N * (cfg->rank + 1) / cfg->world_size) - p->n_begin;
+  if (p->n_local < 1) { delete p; return fail(B200MPPI_EINVAL, "planner_create: empty shard"); }
+  p->T = cfg->num_steps;
+  p->M = cfg->mode == B200MPPI_MODE_TDM ? cfg->num_grid_samples : 1;
+  CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  p->own_stream = true;
+  const size_t nT = (size_t)p->n_local * p->T;
+  CU(cudaMalloc(&p->noise, nT * 2 * sizeof(float)));
+  CU(cudaMalloc(&p->u_cur, (size_t)p->T * 2 * sizeof(float)));
+  CU(cudaMalloc(&p->u_prev, (size_t)p->T * 2 * sizeof(float)));
+  CU(cudaMalloc(&p->costs, (size_t)p->n_local * sizeof(float)));
+  CU(cudaMalloc(&p->weights, (size_t)p->n_local * sizeof(float)));
+  CU(cudaMalloc(&p->w_raw, (size_t)p->n_local * sizeof(float)));
+  CU(cudaMalloc(&p->costs_nm, (size_t)p->n_local * p->M * sizeof(float)));
+  p->num_ctas = update_num_ctas(p->n_local);
+  p->rows_per_cta = (p->n_local + p->num_ctas - 1) / p->num_ctas;
+  p->num_ctas = (p->n_local + p->rows_per_cta - 1) / p->rows_per_cta;
+  CU(cudaMalloc(&p->cta_partials, (size_t)p->num_ctas * (2 * p->T + 2) * sizeof(float)));
+  CU(cudaMalloc(&p->rank_partial, (size_t)(2 * p->T + 2) * sizeof(float)));
+  const int V = cfg->num_vis_state_rollouts < 1 ? 1 : cfg->num_vis_state_rollouts;
+  CU(cudaMalloc(&p->state_rollout, (size_t)V * (p->T + 1) * 3 * sizeof(float)));
+  CU(cudaMemsetAsync(p->noise, 0, nT * 2 * sizeof(float), p->stream));
+  CU(cudaMemsetAsync(p->u_cur, 0, (size_t)p->T * 2 * sizeof(float), p->stream));
+  CU(cudaMemsetAsync(p->u_prev, 0, (size_t)p->T * 2 * sizeof(float), p->stream));
+  CU(cudaMemsetAsync(p->costs, 0, (size_t)p->n_local * sizeof(float), p->stream));
+  CU(cudaMemsetAsync(p->weights, 0, (size_t)p->n_local * sizeof(float), p->stream));
+  CU(cudaMemsetAsync(p->state_rollout, 0, (size_t)V * (p->T + 1) * 3 * sizeof(float), p->stream));
+  CU(cudaMallocHost(&p->h_u, (size_t)p->T * 2 * sizeof(float)));
+  // generators n_global*T + t of this shard (mppi.py:118,1367)
+  std::vector<uint64_t> h(nT * 2);
+  create_xoroshiro_states(h.data(), (int64_t)p->n_begin * p->T, (int64_t)nT, cfg->seed);
+  CU(cudaMalloc(&p->states, h.size() * sizeof(uint64_t)));
+  CU(cudaMemcpyAsync(p->states, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
+  for (auto& e : p->ev) CU(cudaEventCreate(&e));
+  CU(cudaStreamSynchronize(p->stream));
+  *out = p;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_destroy(b200mppi_planner* p) {
+  if (!p) return B200MPPI_OK;
+  cudaSetDevice(p->cfg.device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  cudaFree(p->noise); cudaFree(p->u_cur); cudaFree(p->u_prev); cudaFree(p->costs); cudaFree(p->weights);
+  cudaFree(p->w_raw); cudaFree(p->costs_nm); cudaFree(p->cta_partials); cudaFree(p->rank_partial);
+  cudaFree(p->state_rollout); cudaFree(p->states);
+  if (p->h_u) cudaFreeHost(p->h_u);
+  for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+  if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_set_stream(b200mppi_planner* p, void* s) {
+  if (!p) return fail(B200MPPI_EINVAL, "null planner");
+  if (p->own_stream && p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
+  p->stream = (cudaStream_t)s;
+  p->own_stream = false;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_set_tdms(b200mppi_planner* p, b200mppi_tdm* lin, b200mppi_tdm* ang) {
+  if (!p || !lin || !ang) return fail(B200MPPI_EINVAL, "set_tdms: null argument");
+  if (lin->cfg.device != p->cfg.device || ang->cfg.device != p->cfg.device)
+    return fail(B200MPPI_EINVAL, "set_tdms: TDMs live on another device");
+  if (lin->num_maps != ang->num_maps || lin->cfg.max_map_rows != ang->cfg.max_map_rows ||
+      lin->cfg.max_map_cols != ang->cfg.max_map_cols)
+    return fail(B200MPPI_EINVAL, "set_tdms: lin/ang allocation shapes differ");
+  if (p->cfg.mode == B200MPPI_MODE_TDM && lin->num_maps < p->M)
+    return fail(B200MPPI_EINVAL, "set_tdms: TDM holds fewer sampled maps than the planner's num_grid_samples");
+  p->lin = lin; p->ang = ang;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_set_params(b200mppi_planner* p, const b200mppi_params* q) {
+  if (!p || !q) return fail(B200MPPI_EINVAL, "set_params: null argument");
+  if (!(q->dt > 0) || q->num_opt < 0) return fail(B200MPPI_EINVAL, "set_params: bad dt/num_opt");
+  p->prm = *q;
+  p->params_set = true;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_set_u(b200mppi_planner* p, const float* u) {
+  if (!p || !u) return fail(B200MPPI_EINVAL, "set_u: null argument");
+  CU(cudaSetDevice(p->cfg.device));
+  std::memcpy(p->h_u, u, (size_t)p->T * 2 * sizeof(float));
+  CU(cudaMemcpyAsync(p->u_cur, p->h_u, (size_t)p->T * 2 * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_get_u(b200mppi_planner* p, float* u) {
+  if (!p || !u) return fail(B200MPPI_EINVAL, "get_u: null argument");
+  CU(cudaSetDevice(p->cfg.device));
+  CU(cudaMemcpyAsync(p->h_u, p->u_cur, (size_t)p->T * 2 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  std::memcpy(u, p->h_u, (size_t)p->T * 2 * sizeof(float));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_shift_u(b200mppi_planner* p, int32_t shifts) {
+  if (!p) return fail(B200MPPI_EINVAL, "null planner");
+  CU(cudaSetDevice(p->cfg.device));
+  launch_shift_u(p->u_cur, p->T, shifts, p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
+  return B200MPPI_OK;
+}
+
+// ---- stages
+static int stage_noise(b200mppi_planner* p) {
+  launch_sample_noise(p->states, p->noise, p->n_local, p->T, p->prm.u_std[0], p->prm.u_std[1], p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
+  return B200MPPI_OK;
+}
+
+static int stage_rollout(b200mppi_planner* p) {
+  RolloutArgs a{};
+  fill_rollout_params(p, a.p);
+  a.mode = p->cfg.mode;
+  a.lin_grid = p->lin->grid; a.ang_grid = p->ang->grid;
+  a.obstacle = p->lin->obstacle; a.unknown = p->lin->unknown; a.risk = p->lin->risk;
+  a.noise = p->noise; a.u_cur = p->u_cur; a.costs_nm = p->costs_nm; a.costs = p->costs;
+  launch_rollout(a, p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
+  if (p->profiling) cudaEventRecord(p->ev[3], p->stream);
+  if (p->cfg.mode == B200MPPI_MODE_TDM) {
+    launch_cvar(p->costs_nm, p->costs, p->n_local, p->M, p->prm.cvar_alpha, p->stream);
+    p->launches++;
+    CHECK_LAUNCH();
+  }
+  return B200MPPI_OK;
+}
+
+static int stage_update_partial(b200mppi_planner* p, const float* costs) {
+  UpdateArgs u{};
+  fill_update_args(p, u, costs);
+  launch_update_partial(u, p->stream);
+  p->launches += 2;
+  CHECK_LAUNCH();
+  return B200MPPI_OK;
+}
+
+static int stage_update_finish(b200mppi_planner* p, const float* gathered, int count) {
+  UpdateArgs u{};
+  fill_update_args(p, u, nullptr);
+  launch_update_finish(u, gathered, count, p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
+  if (p->cfg.mode != B200MPPI_MODE_TDM)   // self.u_prev_d = self.u_cur_d (alias, mppi.py:292,362)
+    CU(cudaMemcpyAsync(p->u_prev, p->u_cur, (size_t)p->T * 2 * sizeof(float), cudaMemcpyDeviceToDevice, p->stream));
+  return B200MPPI_OK;
+}
+
+static int stage_sample_tdms(b200mppi_planner* p) {
+  // det / speed-map solves call sample_grids() with the default alpha_dyn = 1.0 (mppi.py:248-249,322-323)
+  const double alpha = p->cfg.mode == B200MPPI_MODE_TDM ? p->prm.alpha_dyn : 1.0;
+  int rc = tdm_sample_on(p->lin, alpha, p->stream);
+  if (rc) return rc;
+  rc = tdm_sample_on(p->ang, alpha, p->stream);
+  if (rc) return rc;
+  p->launches += 2;
+  return B200MPPI_OK;
+}
+
+static void collect_timings(b200mppi_planner* p) {
+  // ev: 0 start, 1 after sampling, 2 after noise, 3 after rollout, 4 after cvar, 5 after update (last iteration)
+  if (!p->profiling) return;
+  float ms = 0;
+  auto dt = [&](int a, int b) { ms = 0; cudaEventElapsedTime(&ms, p->ev[a], p->ev[b]); return ms; };
+  p->last_ms[B200MPPI_T_SAMPLE_GRIDS] = dt(0, 1);
+  p->last_ms[B200MPPI_T_NOISE] = dt(1, 2);
+  p->last_ms[B200MPPI_T_ROLLOUT] = dt(2, 3);
+  p->last_ms[B200MPPI_T_CVAR] = dt(3, 4);
+  p->last_ms[B200MPPI_T_UPDATE] = dt(4, 5);
+  p->last_ms[B200MPPI_T_TOTAL] = dt(0, 5);
+}
+
+extern "C" int b200mppi_planner_solve(b200mppi_planner* p, float* u_out) {
+  if (!p) return fail(B200MPPI_EINVAL, "null planner");
+  if (p->cfg.world_size != 1) return fail(B200MPPI_ESTATE, "solve: world_size > 1, use solve_local/solve_finish");
+  int rc = planner_check_ready(p);
+  if (rc) return rc;
+  CU(cudaSetDevice(p->cfg.device));
+  if (p->profiling) cudaEventRecord(p->ev[0], p->stream);
+  rc = stage_sample_tdms(p);
+  if (rc) return rc;
+  if (p->profiling) cudaEventRecord(p->ev[1], p->stream);
+  for (int k = 0; k < p->prm.num_opt; ++k) {
+    const bool last = (k == p->prm.num_opt - 1);
+    if (p->profiling && !last) cudaEventRecord(p->ev[1], p->stream);
+    if ((rc = stage_noise(p))) return rc;
+    if (p->profiling) cudaEventRecord(p->ev[2], p->stream);
+    if ((rc = stage_rollout(p))) return rc;
+    if (p->profiling) cudaEventRecord(p->ev[4], p->stream);
+    if ((rc = stage_update_partial(p, nullptr))) return rc;
+    if ((rc = stage_update_finish(p, p->rank_partial, 1))) return rc;
+    if (p->profiling) cudaEventRecord(p->ev[5], p->stream);
+  }
+  CU(cudaMemcpyAsync(p->h_u, p->u_cur, (size_t)p->T * 2 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  if (u_out) std::memcpy(u_out, p->h_u, (size_t)p->T * 2 * sizeof(float));
+  if (p->prm.num_opt > 0) collect_timings(p);
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_solve_local(b200mppi_planner* p, int32_t first_iteration) {
+  if (!p) return fail(B200MPPI_EINVAL, "null planner");
+  int rc = planner_check_ready(p);
+  if (rc) return rc;
+  CU(cudaSetDevice(p->cfg.device));
+  if (p->profiling) cudaEventRecord(p->ev[0], p->stream);
+  if (first_iteration && (rc = stage_sample_tdms(p))) return rc;
+  if (p->profiling) cudaEventRecord(p->ev[1], p->stream);
+  if ((rc = stage_noise(p))) return rc;
+  if (p->profiling) cudaEventRecord(p->ev[2], p->stream);
+  if ((rc = stage_rollout(p))) return rc;
+  if (p->profiling) cudaEventRecord(p->ev[4], p->stream);
+  if ((rc = stage_update_partial(p, nullptr))) return rc;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_solve_finish(b200mppi_planner* p, const float* gathered_dev, float* u_out) {
+  if (!p || !gathered_dev) return fail(B200MPPI_EINVAL, "solve_finish: null argument");
+  if (p->cfg.world_size > 512) return fail(B200MPPI_EINVAL, "solve_finish: world_size > 512");
+  CU(cudaSetDevice(p->cfg.device));
+  int rc = stage_update_finish(p, gathered_dev, p->cfg.world_size);
+  if (rc) return rc;
+  if (p->profiling) cudaEventRecord(p->ev[5], p->stream);
+  if (u_out) {
+    CU(cudaMemcpyAsync(p->h_u, p->u_cur, (size_t)p->T * 2 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    std::memcpy(u_out, p->h_u, (size_t)p->T * 2 * sizeof(float));
+    collect_timings(p);
+  }
+  return B200MPPI_OK;
+}
+
+// Host combine of gathered (beta, S, V[2T]) partials: same math as update_apply_kernel.
+extern "C" int b200mppi_combine_partials_host(const float* g, int32_t ws, int32_t T, float lambda,
+                                              const float* u_in, const float vr[2], const float wr[2],
+                                              float* u_out) {
+  if (!g || !u_in || !u_out || !vr || !wr || ws < 1 || T < 1) return fail(B200MPPI_EINVAL, "combine: bad argument");
+  const int stride = 2 * T + 2;
+  float beta = INFINITY;
+  for (int r = 0; r < ws; ++r) beta = std::fmin(beta, g[(size_t)r * stride]);
+  std::vector<float> sc(ws);
+  float W = 0.0f;
+  for (int r = 0; r < ws; ++r) {
+    const float b = g[(size_t)r * stride];
+    sc[r] = std::isinf(b) ? 0.0f : (float)std::exp((-1.0 / (double)lambda) * (double)(b - beta));
+    W = std::fmaf(g[(size_t)r * stride + 1], sc[r], W);
+  }
+  for (int j = 0; j < 2 * T; ++j) {
+    float v = 0.0f;
+    for (int r = 0; r < ws; ++r) v = std::fmaf(g[(size_t)r * stride + 2 + j], sc[r], v);
+    const float u = u_in[j] + v / W;
+    const float lo = (j & 1) ? wr[0] : vr[0], hi = (j & 1) ? wr[1] : vr[1];
+    u_out[j] = std::fmax(lo, std::fmin(hi, u));
+  }
+  return B200MPPI_OK;
+}
+
+// ---- stage-level entry points
+extern "C" int b200mppi_planner_sample_noise(b200mppi_planner* p) {
+  if (!p) return fail(B200MPPI_EINVAL, "null planner");
+  if (!p->params_set) return fail(B200MPPI_ESTATE, "sample_noise: params not set");
+  CU(cudaSetDevice(p->cfg.device));
+  int rc = stage_noise(p);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_rollout(b200mppi_planner* p) {
+  if (!p) return fail(B200MPPI_EINVAL, "null planner");
+  int rc = planner_check_ready(p);
+  if (rc) return rc;
+  CU(cudaSetDevice(p->cfg.device));
+  if ((rc = stage_rollout(p))) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_cvar(b200mppi_planner* p) {
+  if (!p) return fail(B200MPPI_EINVAL, "null planner");
+  if (!p->params_set) return fail(B200MPPI_ESTATE, "cvar: params not set");
+  if (p->cfg.mode != B200MPPI_MODE_TDM) return fail(B200MPPI_ESTATE, "cvar: only MODE_TDM has per-(n,m) costs");
+  if (p->M > 1024) return fail(B200MPPI_EINVAL, "cvar: num_grid_samples > 1024");
+  CU(cudaSetDevice(p->cfg.device));
+  launch_cvar(p->costs_nm, p->costs, p->n_local, p->M, p->prm.cvar_alpha, p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
+  CU(cudaStreamSynchronize(p->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_update(b200mppi_planner* p, const float* costs_host) {
+  if (!p) return fail(B200MPPI_EINVAL, "null planner");
+  if (!p->params_set) return fail(B200MPPI_ESTATE, "update: params not set");
+  CU(cudaSetDevice(p->cfg.device));
+  if (costs_host)
+    CU(cudaMemcpyAsync(p->costs, costs_host, (size_t)p->n_local * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+  int rc = stage_update_partial(p, nullptr);
+  if (rc) return rc;
+  if (p->cfg.world_size == 1 && (rc = stage_update_finish(p, p->rank_partial, 1))) return rc;
+  CU(cudaStreamSynchronize(p->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_get_state_rollout(b200mppi_planner* p, float* out, size_t bytes) {
+  if (!p || !out) return fail(B200MPPI_EINVAL, "null argument");
+  int rc = planner_check_ready(p);
+  if (rc) return rc;
+  const int V = p->cfg.num_vis_state_rollouts < 1 ? 1 : p->cfg.num_vis_state_rollouts;
+  const size_t need = (size_t)V * (p->T + 1) * 3 * sizeof(float);
+  if (bytes != need) return fail(B200MPPI_EINVAL, "get_state_rollout: size mismatch");
+  if (p->cfg.mode == B200MPPI_MODE_TDM ? V > p->lin->num_maps : V > p->n_local)
+    return fail(B200MPPI_EINVAL, "get_state_rollout: more vis rollouts than maps / local rollouts");
+  CU(cudaSetDevice(p->cfg.device));
+  VisArgs a{};
+  fill_rollout_params(p, a.p);
+  a.mode = p->cfg.mode; a.V = V;
+  a.lin_grid = p->lin->grid; a.ang_grid = p->ang->grid;
+  a.noise = p->noise; a.u_cur = p->u_cur; a.u_prev = p->u_prev; a.out = p->state_rollout;
+  launch_state_rollout(a, p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
+  CU(cudaMemcpyAsync(out, p->state_rollout, need, cudaMemcpyDeviceToHost, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_buffer(b200mppi_planner* p, int32_t id, void** ptr, size_t* bytes) {
+  if (!p) return fail(B200MPPI_EINVAL, "null planner");
+  void* d = nullptr; size_t b = 0;
+  const size_t nl = p->n_local, T = p->T;
+  const int V = p->cfg.num_vis_state_rollouts < 1 ? 1 : p->cfg.num_vis_state_rollouts;
+  switch (id) {
+    case B200MPPI_BUF_NOISE: d = p->noise; b = nl * T * 2 * sizeof(float); break;
+    case B200MPPI_BUF_U_CUR: d = p->u_cur; b = T * 2 * sizeof(float); break;
+    case B200MPPI_BUF_U_PREV: d = p->u_prev; b = T * 2 * sizeof(float); break;
+    case B200MPPI_BUF_COSTS: d = p->costs; b = nl * sizeof(float); break;
+    case B200MPPI_BUF_WEIGHTS: d = p->weights; b = nl * sizeof(float); break;
+    case B200MPPI_BUF_COSTS_NM: d = p->costs_nm; b = nl * p->M * sizeof(float); break;
+    case B200MPPI_BUF_RNG: d = p->states; b = nl * T * 16; break;
+    case B200MPPI_BUF_PARTIAL: d = p->rank_partial; b = (2 * T + 2) * sizeof(float); break;
+    case B200MPPI_BUF_STATE_ROLLOUT: d = p->state_rollout; b = (size_t)V * (T + 1) * 3 * sizeof(float); break;
+    default: return fail(B200MPPI_EINVAL, "buffer: unknown id");
+  }
+  if (ptr) *ptr = d;
+  if (bytes) *bytes = b;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_copy_out(b200mppi_planner* p, int32_t id, void* dst, size_t bytes) {
+  void* d; size_t b;
+  int rc = b200mppi_planner_buffer(p, id, &d, &b);
+  if (rc) return rc;
+  if (!dst || bytes != b) return fail(B200MPPI_EINVAL, "copy_out: size mismatch");
+  CU(cudaSetDevice(p->cfg.device));
+  CU(cudaMemcpyAsync(dst, d, b, cudaMemcpyDeviceToHost, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_copy_in(b200mppi_planner* p, int32_t id, const void* src, size_t bytes) {
+  void* d; size_t b;
+  int rc = b200mppi_planner_buffer(p, id, &d, &b);
+  if (rc) return rc;
+  if (!src || bytes != b) return fail(B200MPPI_EINVAL, "copy_in: size mismatch");
+  CU(cudaSetDevice(p->cfg.device));
+  CU(cudaMemcpyAsync(d, src, b, cudaMemcpyHostToDevice, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_set_noise(b200mppi_planner* p, const float* noise, size_t bytes) {
+  return b200mppi_planner_copy_in(p, B200MPPI_BUF_NOISE, noise, bytes);
+}
+
+extern "C" int b200mppi_planner_synchronize(b200mppi_planner* p) {
+  if (!p) return fail(B200MPPI_EINVAL, "null planner");
+  CU(cudaSetDevice(p->cfg.device));
+  CU(cudaStreamSynchronize(p->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_set_profiling(b200mppi_planner* p, int32_t enable) {
+  if (!p) return fail(B200MPPI_EINVAL, "null planner");
+  p->profiling = enable != 0;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_last_timings(b200mppi_planner* p, float* ms) {
+  if (!p || !ms) return fail(B200MPPI_EINVAL, "null argument");
+  for (int i = 0; i < B200MPPI_T_COUNT; ++i) ms[i] = p->last_ms[i];
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_launch_count(b200mppi_planner* p, int64_t* out) {
+  if (!p || !out) return fail(B200MPPI_EINVAL, "null argument");
+  *out = p->launches + (p->lin ? 0 : 0);
+  return B200MPPI_OK;
+}

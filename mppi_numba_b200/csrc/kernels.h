@@ -1,0 +1,83 @@
+// kernels.h -- host-callable launchers of the engine's CUDA kernels (internal; the public
+// surface is include/b200mppi.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace b200 {
+
+// sample_grids_numba (terrain.py:633-694), bit-exact stream layout.
+struct SampleGridsArgs {
+  int8_t* grid;            // (num_maps, grid_rows, pitch) int8
+  const int8_t* cum;       // cumulative PMF, (rows, cols, bpad) int8-as-uint8 (saturated at 127)
+  uint64_t* states;        // (num_gen, 2)
+  const int8_t* qvals;     // int8[bpad] quantised bin values (terrain.py:689)
+  int num_bins, bpad;
+  int rows, cols;          // padded PMF dims
+  int grid_rows, pitch;
+  int tx, ty, num_maps;
+  double alpha_dyn;
+  int col_sums_ok;         // every column reaches >= 100 (no "nothing written" cells)
+};
+void launch_sample_grids(const SampleGridsArgs& a, cudaStream_t st);
+// builds the (rows, cols, bpad) cumulative table from the (B, rows, cols) PMF
+void launch_build_cum(const int8_t* pmf, int8_t* cum, int num_bins, int bpad, int rows, int cols,
+                      cudaStream_t st);
+
+// sample_noise_numba (mppi.py:1354-1370): generators (n_global*T + t); writes noise (N,T,2).
+void launch_sample_noise(uint64_t* states, float* noise, int n_local, int T, float std_v,
+                         float std_w, cudaStream_t st);
+
+// rollout kernels (mppi.py:613-1111)
+struct RolloutArgs {
+  RolloutParams p;
+  int mode;
+  const int8_t* lin_grid;   // (M|1, grid_rows, pitch)
+  const int8_t* ang_grid;
+  const int8_t* obstacle;   // (rows, cols)
+  const int8_t* unknown;
+  const int8_t* risk;       // (rows, cols) or null
+  const float* noise;       // (N, T, 2)
+  const float* u_cur;       // (T, 2)
+  float* costs_nm;          // (N, M)   MODE_TDM
+  float* costs;             // (N)
+};
+void launch_rollout(const RolloutArgs& a, cudaStream_t st);
+// CVaR over M (mppi.py:718-755): costs[n] = mean of the ceil(M*alpha) largest of costs_nm[n,:]
+void launch_cvar(const float* costs_nm, float* costs, int N, int M, float cvar_alpha,
+                 cudaStream_t st);
+
+// update_useq_numba (mppi.py:1113-1191) as an online-softmax two-level reduction
+struct UpdateArgs {
+  const float* costs;     // (N)
+  const float* noise;     // (N, T, 2)
+  float* w_raw;           // (N) exp(-(c-beta_cta)/lambda)
+  float* cta_partials;    // (num_ctas, 2T+2): beta, S, V[2T]
+  float* rank_partial;    // (2T+2)
+  float* u_cur;           // (T,2) in/out
+  float* weights;         // (N) normalised
+  int N, T, num_ctas, rows_per_cta;
+  float lambda, vrange[2], wrange[2];
+};
+int update_num_ctas(int N);
+void launch_update_partial(const UpdateArgs& a, cudaStream_t st);
+// combine `count` partials (each 2T+2 floats; this rank's own partial is entry `self`) into u and weights
+void launch_update_finish(const UpdateArgs& a, const float* gathered, int count, cudaStream_t st);
+
+void launch_shift_u(float* u, int T, int shifts, cudaStream_t st);
+
+// visualisation rollouts (mppi.py:1194-1351)
+struct VisArgs {
+  RolloutParams p;
+  int mode, V;
+  const int8_t* lin_grid; const int8_t* ang_grid;
+  const float* noise; const float* u_cur; const float* u_prev;
+  float* out;   // (V, T+1, 3)
+};
+void launch_state_rollout(const VisArgs& a, cudaStream_t st);
+
+// host: numba-compatible generator states (random.py:226-241)
+void create_xoroshiro_states(uint64_t* host_out, int64_t first, int64_t count, uint64_t seed);
+
+}  // namespace b200

@@ -1,0 +1,130 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/b200mppi.h declares, fails loudly without a GPU, and the host-side API mirrors behave like
+the reference's Config / error conventions.  No compute calls (there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libmod():
+    import __graft_entry__
+    __graft_entry__.build()
+    from mppi_numba_b200 import _lib
+    return _lib
+
+
+def test_every_declared_symbol_is_exported(libmod):
+    hdr = open(os.path.join(ROOT, "include", "b200mppi.h")).read()
+    declared = set(re.findall(r"\b(b200mppi_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 35
+    raw = C.CDLL(libmod.LIB_PATH)
+    missing = [name for name in sorted(declared) if not hasattr(raw, name)]
+    assert not missing, missing
+    assert set(libmod.EXPORTS) == declared, set(libmod.EXPORTS) ^ declared
+
+
+def test_library_has_sm100a_code(libmod):
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", libmod.LIB_PATH], capture_output=True, text=True)
+    assert "sm_100a" in out.stdout
+
+
+def test_pod_layouts_match_header(libmod, tmp_path):
+    """sizeof/offsetof of the two PODs as gcc sees include/b200mppi.h == the ctypes mirrors."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text("""
+#include <stdio.h>
+#include <stddef.h>
+#include "b200mppi.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b200mppi_config), offsetof(b200mppi_config, seed),
+         offsetof(b200mppi_config, world_size), sizeof(b200mppi_params), offsetof(b200mppi_params, num_opt),
+         offsetof(b200mppi_params, alpha_dyn), offsetof(b200mppi_params, wrange));
+  return 0;
+}
+""")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    Cfg, Prm = libmod.ConfigPOD, libmod.ParamsPOD
+    assert got == [C.sizeof(Cfg), Cfg.seed.offset, Cfg.world_size.offset, C.sizeof(Prm), Prm.num_opt.offset,
+                   Prm.alpha_dyn.offset, Prm.wrange.offset]
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="GPU present")
+def test_no_cpu_fallback(libmod):
+    from mppi_numba_b200 import Config, MPPI_Numba, TDM_Numba, B200MPPIError
+    assert libmod.device_count() == 0
+    cfg = Config(T=1.0, dt=0.1, num_grid_samples=4, num_control_rollouts=100, use_tdm=True, max_map_dim=(20, 20))
+    with pytest.raises(B200MPPIError, match="no CUDA device"):
+        TDM_Numba(cfg)
+    with pytest.raises(B200MPPIError, match="no CUDA device"):
+        MPPI_Numba(cfg)
+
+
+def test_product_never_imports_oracle():
+    import ast
+    pkg = os.path.join(ROOT, "mppi_numba_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            tree = ast.parse(open(os.path.join(pkg, fn)).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                assert not any(n.split(".")[0] in ("oracle", "numba") for n in names), (fn, names)
+
+
+def test_config_clamps_and_modes(capsys):
+    from mppi_numba_b200 import Config
+    c = Config(T=6.4, dt=0.1, use_det_dynamics=True, num_control_rollouts=64, num_grid_samples=0)
+    assert c.num_steps == int(6.4 / 0.1) and c.num_control_rollouts == 100 and c.num_grid_samples == 1
+    assert c.num_vis_state_rollouts == 1 and c.mode == 1 and c.det_dyn
+    c = Config(use_tdm=True, num_control_rollouts=20000, num_grid_samples=20000, tdm_sample_thread_dim=(32, 32))
+    assert c.num_control_rollouts == 15000 and c.num_grid_samples == 15000
+    assert c.tdm_sample_thread_dim == (32, 32) and c.max_threads_per_block == 1024
+    c = Config(use_tdm=True, tdm_sample_thread_dim=(64, 32))
+    assert c.tdm_sample_thread_dim == (32, 32)
+    assert Config(use_nom_dynamics_with_speed_map=True).mode == 2
+    capsys.readouterr()
+    for bad in (dict(), dict(use_tdm=True, use_det_dynamics=True), dict(use_costmap=True)):
+        with pytest.raises(AssertionError):
+            Config(**bad)
+    with pytest.raises(AssertionError):
+        Config(T=0.05, dt=0.1, use_tdm=True)
+
+
+def test_combine_partials_host_matches_oracle_update(libmod):
+    """The N>1 exchange math: per-rank (beta, S, V[2T]) partials merged by the library's host
+    combine equal the oracle's single-process softmax update."""
+    from oracle import mppi_ref as MR
+    rng = np.random.default_rng(0)
+    N, T, ws = 240, 7, 3
+    costs = rng.uniform(50, 60, N).astype(np.float32)
+    noise = (rng.standard_normal((N, T, 2)) * [2, 3]).astype(np.float32)
+    u0 = rng.uniform(0, 1, (T, 2)).astype(np.float32)
+    lam = np.float32(0.7)
+    parts = []
+    for r in range(ws):
+        sl = slice(N * r // ws, N * (r + 1) // ws)
+        beta = costs[sl].min()
+        w = np.exp((-1.0 / float(lam)) * (costs[sl] - beta).astype(np.float64)).astype(np.float32)
+        V = np.einsum("n,ntk->tk", w.astype(np.float64), noise[sl].astype(np.float64)).astype(np.float32)
+        parts.append(np.concatenate([[beta, w.sum(dtype=np.float64)], V.ravel()]).astype(np.float32))
+    g = np.ascontiguousarray(np.stack(parts))
+    out = np.empty((T, 2), dtype=np.float32)
+    vr = np.array([0, 3], np.float32)
+    wr = np.array([-np.pi, np.pi], np.float32)
+    libmod.check(libmod.lib.b200mppi_combine_partials_host(libmod.ptr(g), ws, T, lam, libmod.ptr(u0),
+                                                          libmod.ptr(vr), libmod.ptr(wr), libmod.ptr(out)))
+    want, _ = MR.update_useq(lam, costs, noise, vr, wr, u0)
+    np.testing.assert_allclose(out, want, rtol=1e-5, atol=2e-6)
