@@ -36,7 +36,7 @@ def make_scenario(mode, N, M, T, H, W, res, B, seed=1, near_goal=False, warm_sta
     x0 = np.array([L / 2 + r5.uniform(-2, 2) * min(1.0, L / 20), L / 2 + r5.uniform(-2, 2) * min(1.0, L / 20),
                    r5.uniform(-np.pi, np.pi)])
     obstacle[int(x0[1] / res), int(x0[0] / res)] = 0
-    xgoal = x0[:2] + (np.array([3.0, 3.0]) * min(1.0, L / 20) if near_goal else 0.42 * L * np.ones(2))
+    xgoal = x0[:2] + (np.array([1.2, 1.2]) * min(1.0, L / 20) if near_goal else 0.42 * L * np.ones(2))
     if bin_values is None:
         bin_values = np.linspace(0, 1, B)
     tdm_dict = dict(res=res, xlimits=np.array([0.0, W * res]), ylimits=np.array([0.0, H * res]),
