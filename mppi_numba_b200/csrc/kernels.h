@@ -21,6 +21,19 @@ struct SampleGridsArgs {
   int col_sums_ok;         // every column reaches >= 100 (no "nothing written" cells)
 };
 void launch_sample_grids(const SampleGridsArgs& a, cudaStream_t st);
+// v2 (staged, integer-threshold, optionally lin+ang fused) sampler -- see sample.cu
+struct SampleTdm {
+  int8_t* grid; const int8_t* cum; uint64_t* states; const int8_t* qvals; int bpad;
+};
+struct SampleGridsV2Args {
+  SampleTdm t[2];
+  const uint64_t* thresholds;   // device, 136 entries
+  uint32_t est_mul;
+  int rows, cols, grid_rows, pitch, tx, ty, num_maps;
+};
+bool build_sample_thresholds(double alpha, int q_cap, uint64_t* T, uint32_t* est_mul);
+bool sample_grids_v2_fits(const SampleGridsV2Args& a, int nt);
+void launch_sample_grids_v2(const SampleGridsV2Args& a, int nt, cudaStream_t st);
 // builds the (rows, cols, bpad) cumulative table from the (B, rows, cols) PMF
 void launch_build_cum(const int8_t* pmf, int8_t* cum, int num_bins, int bpad, int rows, int cols,
                       cudaStream_t st);

@@ -8,6 +8,7 @@
 // if no bin reaches q the cell keeps its previous content.  The table of cumulative PMFs is built
 // once per set_pmf (cell-major, so one cell's bins are contiguous) instead of re-summing B strided
 // int8 loads per cell per map as the reference does.
+#include <cmath>
 #include "kernels.h"
 
 namespace b200 {
@@ -73,6 +74,199 @@ void launch_sample_grids(const SampleGridsArgs& a, cudaStream_t st) {
   const int64_t total = (int64_t)a.tx * a.ty * a.num_maps;
   const int threads = 128;
   sample_grids_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// v2 sampler (the one solve() uses whenever the PMF is well-formed): same bit-exact streams, but
+//   * a CTA owns one tile-row band of the map for GM consecutive maps: the band's cumulative-PMF rows
+//     are staged ONCE in shared memory and reused by all GM maps x ty tile columns (the reference
+//     re-reads B strided int8 per cell per map from global memory);
+//   * the threshold q = int8(ceil(f64(f32(v*2^-53))*100*alpha)) is obtained WITHOUT the five float64 /
+//     conversion (XU-pipe) instructions: q(v) is a monotone step function of the 53-bit draw v, so the
+//     host tabulates its breakpoints T[k] = min{v : q(v) >= k} with the exact float arithmetic and the
+//     kernel does an integer estimate + <= 3 table compares (the host verifies est <= q <= est+3 at
+//     every breakpoint, otherwise the generic kernel is used);
+//   * the first bin whose cumulative mass reaches q is found with a SIMD-in-register byte compare and
+//     one POPC instead of a loop;
+//   * sampled bytes are staged per row in shared memory and written with coalesced 16-byte stores;
+//   * NT = 2 samples the linear and angular maps together from ONE stream when both TDMs hold identical
+//     generator states (same seed, same history -- the reference seeds both with cfg.seed, so their
+//     streams are identical): the draw and the threshold are shared.
+constexpr int SG_GM = 8;          // maps per CTA
+
+template <int NT, int NW>
+__global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const SampleGridsV2Args a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int nw = (NW > 0) ? NW : a.t[0].bpad / 4;
+  const int bpad = nw * 4;
+  const int row_bytes = a.cols * bpad;                       // one row of the cumulative table
+  const int row_bytes_al = (row_bytes + 15) & ~15;
+  const int stage_pitch = (a.cols + 15) & ~15;
+  unsigned char* s_cum = smem;                               // [NT][row_bytes_al]
+  unsigned char* s_stage = s_cum + NT * row_bytes_al;        // [NT][GM][stage_pitch]
+  uint64_t* s_T = reinterpret_cast<uint64_t*>(s_stage + NT * SG_GM * stage_pitch);   // [136]
+  unsigned char* s_q = reinterpret_cast<unsigned char*>(s_T + 136);                  // [NT][128]
+
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int tiy = tid % a.ty, mloc = tid / a.ty;
+  const int tix = blockIdx.x;
+  const int m = blockIdx.y * SG_GM + mloc;
+  const bool active = (mloc < SG_GM) && (m < a.num_maps);
+
+  for (int i = tid; i < 136; i += nthreads) s_T[i] = a.thresholds[i];
+  for (int i = tid; i < 128; i += nthreads) {
+    s_q[i] = (unsigned char)a.t[0].qvals[i];
+    if (NT == 2) s_q[128 + i] = (unsigned char)a.t[1].qvals[i];
+  }
+
+  const int ncol = (a.cols + a.ty - 1) / a.ty;
+  const int nrow = (a.rows + a.tx - 1) / a.tx;
+  const int r0 = min(tix * nrow, a.rows), r1 = min(r0 + nrow, a.rows);
+  const int c0 = min(tiy * ncol, a.cols), c1 = min(c0 + ncol, a.cols);
+
+  const int64_t gen = (int64_t)tix * ((int64_t)a.ty * a.num_maps) + (int64_t)m * a.ty + tiy;
+  Xoro s{0, 0};
+  if (active) {
+    const ulonglong2 raw = reinterpret_cast<const ulonglong2*>(a.t[0].states)[gen];
+    s.s0 = raw.x; s.s1 = raw.y;
+  }
+  const uint32_t c32 = a.est_mul;
+
+  for (int ri = r0; ri < r1; ++ri) {
+    __syncthreads();                                          // previous row's stage fully drained
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(a.t[k].cum + (size_t)ri * row_bytes);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(s_cum + k * row_bytes_al);
+      for (int i = tid; i < row_bytes / 4; i += nthreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if (active) {
+      for (int ci = c0; ci < c1; ++ci) {
+        const uint64_t v = xoro_next(s) >> 11;
+        const uint32_t est = __umulhi((uint32_t)(v >> 21), c32) >> 25;
+        const uint32_t q = est + (v >= s_T[est + 1]) + (v >= s_T[est + 2]) + (v >= s_T[est + 3]);
+        const uint32_t qq = q * 0x01010101u;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+          const uint32_t* cw = reinterpret_cast<const uint32_t*>(s_cum + k * row_bytes_al + ci * bpad);
+          uint32_t bits = 0;
+          if (NW > 0) {
+#pragma unroll
+            for (int w = 0; w < (NW > 0 ? NW : 1); ++w) {
+              const uint32_t lt = ~((cw[w] | 0x80808080u) - qq) & 0x80808080u;   // bytes with cum < q
+              bits |= lt >> (7 - w);
+            }
+          } else {
+            for (int w = 0; w < nw; ++w) {
+              const uint32_t lt = ~((cw[w] | 0x80808080u) - qq) & 0x80808080u;
+              bits |= lt >> (7 - w);
+            }
+          }
+          const int bin = __popc(bits);                       // cum is monotone: #bins below q = first bin >= q
+          s_stage[(k * SG_GM + mloc) * stage_pitch + ci] = s_q[k * 128 + bin];
+        }
+      }
+    }
+    __syncthreads();
+    // coalesced write-back of the GM x NT staged rows: 16-byte chunks, byte tail
+    const int chunks = (a.cols + 15) / 16;
+    const int maps_here = min(SG_GM, a.num_maps - (int)blockIdx.y * SG_GM);
+    for (int idx = tid; idx < NT * maps_here * chunks; idx += nthreads) {
+      const int ch = idx % chunks;
+      const int km = idx / chunks;
+      const int k = km / maps_here, ml = km % maps_here;
+      const unsigned char* srow = s_stage + (k * SG_GM + ml) * stage_pitch + ch * 16;
+      int8_t* gbase = (NT == 2 && k == 1) ? a.t[1].grid : a.t[0].grid;
+      int8_t* grow = gbase + ((size_t)(blockIdx.y * SG_GM + ml) * a.grid_rows + ri) * a.pitch + ch * 16;
+      if (ch * 16 + 16 <= a.cols) {
+        *reinterpret_cast<uint4*>(grow) = *reinterpret_cast<const uint4*>(srow);
+      } else {
+        for (int b = 0; b < a.cols - ch * 16; ++b) grow[b] = (int8_t)srow[b];
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < NT; ++k)
+      reinterpret_cast<ulonglong2*>(a.t[k].states)[gen] = make_ulonglong2(s.s0, s.s1);
+  }
+}
+
+size_t sample_grids_v2_smem(const SampleGridsV2Args& a, int nt) {
+  const int row_bytes_al = (a.cols * a.t[0].bpad + 15) & ~15;
+  const int stage_pitch = (a.cols + 15) & ~15;
+  return (size_t)nt * row_bytes_al + (size_t)nt * SG_GM * stage_pitch + 136 * 8 + (size_t)nt * 128;
+}
+
+template <int NT>
+static void launch_v2_nt(const SampleGridsV2Args& a, cudaStream_t st) {
+  const dim3 grid(a.tx, (a.num_maps + SG_GM - 1) / SG_GM);
+  const int threads = ((a.ty * SG_GM + 31) / 32) * 32;
+  const size_t smem = sample_grids_v2_smem(a, NT);
+  const int nw = a.t[0].bpad / 4;
+  auto go = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, threads, smem, st>>>(a);
+  };
+  if (nw == 3) go(sample_grids_v2_kernel<NT, 3>);
+  else if (nw == 8) go(sample_grids_v2_kernel<NT, 8>);
+  else if (nw == 1) go(sample_grids_v2_kernel<NT, 1>);
+  else go(sample_grids_v2_kernel<NT, 0>);
+}
+
+bool sample_grids_v2_fits(const SampleGridsV2Args& a, int nt) {
+  return a.ty * SG_GM <= 1024 && a.t[0].bpad <= 32 && sample_grids_v2_smem(a, nt) <= 200 * 1024 &&
+         (nt == 1 || a.t[0].bpad == a.t[1].bpad);
+}
+
+void launch_sample_grids_v2(const SampleGridsV2Args& a, int nt, cudaStream_t st) {
+  if (nt == 2) launch_v2_nt<2>(a, st); else launch_v2_nt<1>(a, st);
+}
+
+// Host: breakpoints of q(v) = int8(ceil(f64(f32(v * 2^-53)) * 100.0 * alpha)) (terrain.py:682-683 as
+// compiled: cvt.rn.f64.u64, mul.f64 2^-53, cvt.rn.f32.f64, cvt.f64.f32, mul.f64 100, mul.f64 alpha,
+// cvt.rpi.f64, cvt.rzi.s16 -> low byte).  Returns false if q is not a monotone map into [0, q_cap]
+// or if the integer estimate used by the kernel cannot be proven tight.
+static inline int q_of_v(uint64_t v, double alpha) {
+  const float u = (float)((double)v * (1.0 / 9007199254740992.0));
+  volatile double t = (double)u * 100.0;
+  volatile double t2 = t * alpha;
+  const double c = std::ceil(t2);
+  if (!(c > -32768.0 && c < 32767.0)) return 1 << 20;
+  return (int)(int8_t)(int16_t)c;
+}
+
+bool build_sample_thresholds(double alpha, int q_cap, uint64_t* T /*[136]*/, uint32_t* est_mul) {
+  if (!(alpha >= 0.0) || !(alpha * 100.0 <= 127.0)) return false;
+  const uint64_t VMAX = (1ULL << 53) - 1;
+  const int qmax = q_of_v(VMAX, alpha);
+  if (qmax < 0 || qmax > q_cap || qmax > 127 || q_of_v(0, alpha) != 0) return false;
+  for (int k = 0; k < 136; ++k) T[k] = ~0ULL;
+  T[0] = 0;
+  for (int k = 1; k <= qmax; ++k) {                   // smallest v with q(v) >= k (q monotone in v)
+    uint64_t lo = 0, hi = VMAX;                       // q(lo) < k <= q(hi)
+    if (q_of_v(0, alpha) >= k) { T[k] = 0; continue; }
+    while (hi - lo > 1) {
+      const uint64_t mid = lo + (hi - lo) / 2;
+      if (q_of_v(mid, alpha) >= k) hi = mid; else lo = mid;
+    }
+    T[k] = hi;
+  }
+  const double c = std::floor(alpha * 100.0 * 33554432.0);          // 100*alpha * 2^25
+  if (!(c >= 0.0 && c < 4294967296.0)) return false;
+  const uint32_t c32 = (uint32_t)c;
+  auto est = [&](uint64_t v) { return (uint32_t)(((uint64_t)(uint32_t)(v >> 21) * c32) >> 57); };
+  // est is monotone; q == k on [T[k], T[k+1]).  Need est <= k and est >= k-3 on that interval.
+  for (int k = 0; k <= qmax; ++k) {
+    if (T[k] == ~0ULL) continue;
+    const uint64_t first = T[k];
+    const uint64_t last = (k < qmax) ? T[k + 1] - 1 : VMAX;
+    if (last < first) continue;                        // empty level
+    if ((int)est(last) > k || (int)est(first) + 3 < k) return false;
+  }
+  *est_mul = c32;
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -52,13 +52,16 @@ def sample_noise(states, u_std, N, T):
 def floor_div_f32(a, r):
     """Python ``//`` on float32 as Numba lowers it (numba/cpython/numbers.py real_divmod; PTX of
     rollout_det_dyn_numba): remainder via abs/div.rn/floor/mul/sub, quotient (a-mod)/r, sign fix,
-    floor, snap-to-nearest.  ``a`` float32 array, ``r`` float32 scalar != 0."""
+    floor, snap-to-nearest.  ptxas contracts the remainder's mul+sub into ONE FMA (SASS of the
+    reference kernel: FFMA.FTZ m = -floor(t)*|r| + |a|), i.e. the remainder is exact -- the same
+    result CPython's fmod-based float_divmod gives in the simulator.
+    ``a`` float32 array, ``r`` float32 scalar != 0."""
     a = a.astype(F32)
     r = F32(r)
     aa = np.abs(a)
     rr = np.abs(r)
     t = (aa / rr).astype(F32)
-    m = (aa - (np.floor(t) * rr).astype(F32)).astype(F32)
+    m = (aa.astype(F64) - np.floor(t).astype(F64) * F64(rr)).astype(F32)      # one rounding (FMA)
     m = np.where(a < 0, -m, m).astype(F32)
     q = ((a - m).astype(F32) / r).astype(F32)
     fix = (m != 0) & ((r < 0) != (m < 0))
