@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -53,7 +54,7 @@ struct b200mppi_tdm {
   float res = 1, pxl[2] = {0, 0}, pyl[2] = {0, 0};
   int8_t* obstacle = nullptr; int8_t* unknown = nullptr; int8_t* risk = nullptr;
   size_t mask_cap = 0, risk_cap = 0;
-  int mask_rows = 0, mask_cols = 0;
+  int mask_rows = 0, mask_cols = 0, mask_pitch = 0;
   int64_t launches = 0;
   // fast sampler eligibility (sample.cu v2): entries in [0,127], monotone sums <= 127
   bool pmf_valid = false;
@@ -269,10 +270,11 @@ extern "C" int b200mppi_tdm_sample_grid_view(b200mppi_tdm* t, void** ptr, int32_
   return B200MPPI_OK;
 }
 
-static int upload_plane(b200mppi_tdm* t, int8_t** dst, size_t* cap, const int8_t* src, size_t bytes) {
+static int upload_plane(b200mppi_tdm* t, int8_t** dst, size_t* cap, const int8_t* src, int rows, int cols, int pitch) {
+  const size_t bytes = (size_t)rows * pitch;
   if (bytes > *cap) { cudaFree(*dst); *dst = nullptr; CU(cudaMalloc(dst, bytes)); *cap = bytes; }
-  if (src) CU(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, t->stream));
-  else CU(cudaMemsetAsync(*dst, 0, bytes, t->stream));
+  CU(cudaMemsetAsync(*dst, 0, bytes, t->stream));
+  if (src) CU(cudaMemcpy2DAsync(*dst, pitch, src, cols, cols, rows, cudaMemcpyHostToDevice, t->stream));
   return B200MPPI_OK;
 }
 
@@ -281,21 +283,21 @@ extern "C" int b200mppi_tdm_set_masks(b200mppi_tdm* t, const int8_t* obs, const 
   if (!t) return fail(B200MPPI_EINVAL, "null tdm");
   if (rows < 1 || cols < 1) return fail(B200MPPI_EINVAL, "set_masks: bad shape");
   CU(cudaSetDevice(t->cfg.device));
-  const size_t bytes = (size_t)rows * cols;
+  const int pitch = round_up(cols, 16);
   size_t cap2 = t->mask_cap;
-  int rc = upload_plane(t, &t->obstacle, &t->mask_cap, obs, bytes);
+  int rc = upload_plane(t, &t->obstacle, &t->mask_cap, obs, rows, cols, pitch);
   if (rc) return rc;
-  rc = upload_plane(t, &t->unknown, &cap2, unk, bytes);
+  rc = upload_plane(t, &t->unknown, &cap2, unk, rows, cols, pitch);
   if (rc) return rc;
   CU(cudaStreamSynchronize(t->stream));
-  t->mask_rows = rows; t->mask_cols = cols; t->masks_set = true;
+  t->mask_rows = rows; t->mask_cols = cols; t->mask_pitch = pitch; t->masks_set = true;
   return B200MPPI_OK;
 }
 
 extern "C" int b200mppi_tdm_set_risk_map(b200mppi_tdm* t, const int8_t* risk, int32_t rows, int32_t cols) {
   if (!t || !risk) return fail(B200MPPI_EINVAL, "set_risk_map: null argument");
   CU(cudaSetDevice(t->cfg.device));
-  int rc = upload_plane(t, &t->risk, &t->risk_cap, risk, (size_t)rows * cols);
+  int rc = upload_plane(t, &t->risk, &t->risk_cap, risk, rows, cols, round_up(cols, 16));
   if (rc) return rc;
   CU(cudaStreamSynchronize(t->stream));
   t->risk_set = true;
@@ -369,6 +371,9 @@ struct b200mppi_planner {
   float* costs = nullptr; float* weights = nullptr; float* costs_nm = nullptr; float* w_raw = nullptr;
   float* cta_partials = nullptr; float* rank_partial = nullptr; float* state_rollout = nullptr;
   uint64_t* states = nullptr;
+  float* noiseT = nullptr; float* ctrl = nullptr; int npad = 0;   // windowed rollout kernel inputs
+  alignas(64) unsigned char tmaps[4][128];
+  bool use_win = true;
   float* h_u = nullptr;        // pinned staging for the T x 2 result
   int num_ctas = 1, rows_per_cta = 1;
   b200mppi_tdm* lin = nullptr; b200mppi_tdm* ang = nullptr;
@@ -402,6 +407,7 @@ static void fill_rollout_params(b200mppi_planner* p, RolloutParams& r) {
   r.g.xlo = l->pxl[0]; r.g.ylo = l->pyl[0];
   r.g.rows = l->rows; r.g.cols = l->cols;
   r.g.grid_rows = l->cfg.max_map_rows; r.g.grid_cols = l->cfg.max_map_cols; r.g.grid_pitch = l->pitch;
+  r.g.mask_pitch = l->mask_pitch;
   const b200mppi_params& q = p->prm;
   r.dt = q.dt;
   for (int i = 0; i < 3; ++i) r.x0[i] = q.x0[i];
@@ -452,6 +458,10 @@ extern "C" int b200mppi_planner_create(const b200mppi_config* cfg, b200mppi_plan
   CU(cudaMalloc(&p->weights, (size_t)p->n_local * sizeof(float)));
   CU(cudaMalloc(&p->w_raw, (size_t)p->n_local * sizeof(float)));
   CU(cudaMalloc(&p->costs_nm, (size_t)p->n_local * p->M * sizeof(float)));
+  p->npad = round_up(p->n_local, 32);
+  CU(cudaMalloc(&p->noiseT, (size_t)p->T * p->npad * 2 * sizeof(float)));
+  CU(cudaMalloc(&p->ctrl, (size_t)p->npad * sizeof(float)));
+  p->use_win = getenv("B200MPPI_NO_WINDOW") == nullptr;
   p->num_ctas = update_num_ctas(p->n_local);
   p->rows_per_cta = (p->n_local + p->num_ctas - 1) / p->num_ctas;
   p->num_ctas = (p->n_local + p->rows_per_cta - 1) / p->rows_per_cta;
@@ -483,7 +493,7 @@ extern "C" int b200mppi_planner_destroy(b200mppi_planner* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   cudaFree(p->noise); cudaFree(p->u_cur); cudaFree(p->u_prev); cudaFree(p->costs); cudaFree(p->weights);
   cudaFree(p->w_raw); cudaFree(p->costs_nm); cudaFree(p->cta_partials); cudaFree(p->rank_partial);
-  cudaFree(p->state_rollout); cudaFree(p->states);
+  cudaFree(p->state_rollout); cudaFree(p->states); cudaFree(p->noiseT); cudaFree(p->ctrl);
   if (p->h_u) cudaFreeHost(p->h_u);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
@@ -562,9 +572,41 @@ static int stage_rollout(b200mppi_planner* p) {
   a.lin_grid = p->lin->grid; a.ang_grid = p->ang->grid;
   a.obstacle = p->lin->obstacle; a.unknown = p->lin->unknown; a.risk = p->lin->risk;
   a.noise = p->noise; a.u_cur = p->u_cur; a.costs_nm = p->costs_nm; a.costs = p->costs;
-  launch_rollout(a, p->stream);
-  p->launches++;
-  CHECK_LAUNCH();
+  bool done = false;
+  if (p->cfg.mode == B200MPPI_MODE_TDM && p->use_win) {
+    // stochastic mode: TMA-staged map windows (rollout_win.cu); window centred on the robot's cell
+    int WW, WH; size_t smem;
+    rollout_win_geometry(p->T, &WW, &WH, &smem);
+    const b200mppi_tdm* l = p->lin; const b200mppi_tdm* g = p->ang;
+    const bool ok = WH >= 16 &&
+        make_u8_tensor_map(p->tmaps[0], l->grid, 3, l->cfg.max_map_cols, l->cfg.max_map_rows, l->num_maps, l->pitch, WW, WH) &&
+        make_u8_tensor_map(p->tmaps[1], g->grid, 3, g->cfg.max_map_cols, g->cfg.max_map_rows, g->num_maps, g->pitch, WW, WH) &&
+        make_u8_tensor_map(p->tmaps[2], l->obstacle, 2, l->mask_cols, l->mask_rows, 1, l->mask_pitch, WW, WH) &&
+        make_u8_tensor_map(p->tmaps[3], l->unknown, 2, l->mask_cols, l->mask_rows, 1, l->mask_pitch, WW, WH);
+    if (ok) {
+      launch_prepare_rollout(p->noise, p->u_cur, p->noiseT, p->ctrl, p->n_local, p->T, p->npad, p->prm.lambda_weight,
+                             p->prm.u_std[0], p->prm.u_std[1], p->stream);
+      p->launches++;
+      CHECK_LAUNCH();
+      RolloutWinArgs w{};
+      w.p = a.p;
+      w.WW = WW; w.WH = WH;
+      const int xi0 = (int)std::floor(((double)p->prm.x0[0] - (double)l->pxl[0]) / (double)l->res);
+      const int yi0 = (int)std::floor(((double)p->prm.x0[1] - (double)l->pyl[0]) / (double)l->res);
+      w.wx0 = xi0 - WW / 2; w.wy0 = yi0 - WH / 2;
+      w.npad = p->npad;
+      w.lin_grid = l->grid; w.ang_grid = g->grid; w.obstacle = l->obstacle; w.unknown = l->unknown;
+      w.noiseT = p->noiseT; w.ctrl = p->ctrl; w.u_cur = p->u_cur; w.costs_nm = p->costs_nm;
+      CU(launch_rollout_win(w, p->tmaps[0], p->tmaps[1], p->tmaps[2], p->tmaps[3], p->stream));
+      p->launches++;
+      done = true;
+    }
+  }
+  if (!done) {
+    launch_rollout(a, p->stream);
+    p->launches++;
+    CHECK_LAUNCH();
+  }
   if (p->profiling) cudaEventRecord(p->ev[3], p->stream);
   if (p->cfg.mode == B200MPPI_MODE_TDM) {
     launch_cvar(p->costs_nm, p->costs, p->n_local, p->M, p->prm.cvar_alpha, p->stream);

@@ -57,6 +57,24 @@ struct RolloutArgs {
   float* costs;             // (N)
 };
 void launch_rollout(const RolloutArgs& a, cudaStream_t st);
+// windowed (TMA-staged) stochastic rollout kernel -- rollout_win.cu
+struct RolloutWinArgs {
+  RolloutParams p;
+  int WW, WH, wx0, wy0;     // window size / origin in cells
+  int npad;                 // row length of noiseT
+  const int8_t* lin_grid; const int8_t* ang_grid; const int8_t* obstacle; const int8_t* unknown;
+  const float* noiseT;      // [T][npad] float2
+  const float* ctrl;        // [npad]
+  const float* u_cur;
+  float* costs_nm;          // (N, M)
+};
+void launch_prepare_rollout(const float* noise, const float* u_cur, float* noiseT, float* ctrl, int N, int T,
+                            int npad, float lambda, float std_v, float std_w, cudaStream_t st);
+bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int rows, int maps, int pitch,
+                        int WW, int WH);
+void rollout_win_geometry(int T, int* WW, int* WH, size_t* smem);
+cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, const void* tm_ang, const void* tm_obs,
+                               const void* tm_unk, cudaStream_t st);
 // CVaR over M (mppi.py:718-755): costs[n] = mean of the ceil(M*alpha) largest of costs_nm[n,:]
 void launch_cvar(const float* costs_nm, float* costs, int N, int M, float cvar_alpha,
                  cudaStream_t st);

@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
     const int my = wrap_clamp(yi, p.g.rows), mx = wrap_clamp(xi, p.g.cols);
     const int ql = __ldg(lin + (size_t)gy * p.g.grid_pitch + gx);
     const int qa = __ldg(ang + (size_t)gy * p.g.grid_pitch + gx);
-    const int ob = __ldg(a.obstacle + (size_t)my * p.g.cols + mx);
-    const int un = __ldg(a.unknown + (size_t)my * p.g.cols + mx);
+    const int ob = __ldg(a.obstacle + (size_t)my * p.g.mask_pitch + mx);
+    const int un = __ldg(a.unknown + (size_t)my * p.g.mask_pitch + mx);
     const float2 e = __ldg(eps + t);
     const float v = fmaxf(c.v_lo, fminf(c.v_hi, fadd(s_u[2 * t], e.x)));
     const float w = fmaxf(c.w_lo, fminf(c.w_hi, fadd(s_u[2 * t + 1], e.y)));
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
 
     float dt_eff = c.dt;
     if (MODE == 2) {
-      const int rk = __ldg(a.risk + (size_t)my * p.g.cols + mx);
+      const int rk = __ldg(a.risk + (size_t)my * p.g.mask_pitch + mx);
       const double eff = fma(c.lin_ratio, (double)rk, c.lin_lo64);
       dt_eff = d2f(c.dt64 / (eff + 1e-6));
     }

@@ -1,0 +1,291 @@
+// rollout_win.cu -- the stochastic ("CVaR-cost") rollout kernel as it is meant to run on a B200:
+// one CTA works on ONE sampled traction map; the window of that map around the robot (linear and
+// angular traction planes of map m, plus the obstacle / unknown planes shared by all maps) is staged
+// into shared memory with four TMA tensor loads (cp.async.bulk.tensor, zero-filled outside the map),
+// after which every per-step lookup of the 1024 rollouts of the CTA is a shared-memory byte load.
+// Lanes of a warp share the map and differ in the control sequence n -- the opposite of the
+// reference (mppi_numba/mppi.py:613-755: block = n, thread = m, i.e. 32 different maps per warp-load).
+//
+// Arithmetic: identical to rollout.cu / the reference (float64 FMA state update rounded once to
+// float32, approximate sin/cos/sqrt, the reference's FMA contractions).  What differs from the
+// generic kernel is only HOW the same numbers are obtained:
+//   * lo + ratio*q and its product with dt (two float64 ops per step in the reference) come from a
+//     256-entry float64 table per map type built with the same two operations;
+//   * the cell index uses round-down magic-number arithmetic on the FP32 pipe (no FRND / F2I on the
+//     XU pipe) and falls back to the exact reference sequence near cell edges;
+//   * obstacle / unknown penalties are skipped when the mask byte is 0 (x + 0*c == x exactly);
+//   * the control-cost sum over T, identical for all M maps of a control sequence, is computed once
+//     per n by the prepare kernel (rounding differs from the reference's running sum by ~1 ulp).
+// A rollout that leaves the window reads the maps from global memory instead (same values).
+#include <cuda.h>
+
+#include "kernels.h"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// prepare: noise (N,T,2) -> transposed noiseT [T][npad] float2 (coalesced per-step loads for lanes =
+// consecutive n) and the per-n control cost  sum_t lambda*(u_v/s_v^2*e_v + u_w/s_w^2*e_w)
+// (mppi.py:708-710), accumulated in the reference's order t = 0..T-1.
+__global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __restrict__ noise,
+                                                              const float* __restrict__ u_cur,
+                                                              float2* __restrict__ noiseT,
+                                                              float* __restrict__ ctrl, int N, int T, int npad,
+                                                              float lambda, float sv2, float sw2) {
+  __shared__ float2 tile[32][33];
+  const int n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  float acc = 0.0f;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    for (int r = ty; r < 32; r += 8) {                         // rows = n, cols = t  (coalesced along t)
+      const int n = n0 + r, t = t0 + tx;
+      tile[r][tx] = (n < N && t < T) ? noise[(size_t)n * T + t] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {                         // rows = t, cols = n  (coalesced along n)
+      const int t = t0 + r;
+      if (t < T) noiseT[(size_t)t * npad + n0 + tx] = tile[tx][r];
+    }
+    if (ty == 0) {                                             // lane tx owns rollout n0+tx
+      const int tend = min(32, T - t0);
+      for (int j = 0; j < tend; ++j) {
+        const float2 e = tile[tx][j];
+        const float a = div_approx(u_cur[2 * (t0 + j)], sv2);
+        const float b = div_approx(u_cur[2 * (t0 + j) + 1], sw2);
+        acc = ffma(ffma(a, e.x, fmul(b, e.y)), lambda, acc);
+      }
+    }
+    __syncthreads();
+  }
+  if (ty == 0 && n0 + tx < N) ctrl[n0 + tx] = acc;
+}
+
+void launch_prepare_rollout(const float* noise, const float* u_cur, float* noiseT, float* ctrl, int N, int T,
+                            int npad, float lambda, float std_v, float std_w, cudaStream_t st) {
+  prepare_rollout_kernel<<<npad / 32, 256, 0, st>>>(reinterpret_cast<const float2*>(noise), u_cur,
+                                                   reinterpret_cast<float2*>(noiseT), ctrl, N, T, npad, lambda,
+                                                   std_v * std_v, std_w * std_w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA plumbing (sm_90+/sm_100a): mbarrier + cp.async.bulk.tensor
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// round-down magic: for |y| < 2^22, (y (+)rd 1.5*2^23) has floor(y) in its low mantissa bits
+__device__ __forceinline__ int cell_index_fast(float a, float r, float inv_r) {
+  const float MAGIC = 12582912.0f;
+  const float y = a * inv_r;
+  const float yk = __fadd_rd(y, MAGIC);
+  const float fl = yk - MAGIC;                    // exact
+  const float frac = y - fl;
+  const float eps = fmaf(fabsf(y), 4.8e-7f, 1e-6f);
+  if (frac > eps && frac < 1.0f - eps && fabsf(y) < 4194304.0f) return __float_as_int(yk) - 0x4B400000;
+  return cell_index_exact(a, r);
+}
+
+struct WinSmem {                 // dynamic shared memory carve-up (all offsets multiples of 128)
+  int plane;                     // bytes per plane = WW*WH
+  int off_lut, off_u, off_bar, total;
+};
+__host__ __device__ inline WinSmem win_smem_layout(int WW, int WH, int T) {
+  WinSmem s;
+  s.plane = WW * WH;
+  const int planes = (4 * s.plane + 127) & ~127;
+  s.off_lut = planes;                              // 2 x 256 doubles
+  s.off_u = s.off_lut + 2 * 256 * 8;               // 2T floats
+  s.off_bar = (s.off_u + 2 * T * 4 + 15) & ~15;
+  s.total = s.off_bar + 16;
+  return s;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWinArgs a,
+                                                                 const __grid_constant__ CUtensorMap tm_lin,
+                                                                 const __grid_constant__ CUtensorMap tm_ang,
+                                                                 const __grid_constant__ CUtensorMap tm_obs,
+                                                                 const __grid_constant__ CUtensorMap tm_unk) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const RolloutParams& p = a.p;
+  const int WW = a.WW, WH = a.WH;
+  const WinSmem L = win_smem_layout(WW, WH, p.T);
+  const int8_t* s_lin = reinterpret_cast<const int8_t*>(smem);
+  const int8_t* s_ang = s_lin + L.plane;
+  const int8_t* s_obs = s_ang + L.plane;
+  const int8_t* s_unk = s_obs + L.plane;
+  double* s_lutL = reinterpret_cast<double*>(smem + L.off_lut);
+  double* s_lutA = s_lutL + 256;
+  float* s_u = reinterpret_cast<float*>(smem + L.off_u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+
+  const int tid = threadIdx.x;
+  const int m = blockIdx.y;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(bar, 4u * (uint32_t)L.plane);
+    tma_load_3d(smem, &tm_lin, bar, a.wx0, a.wy0, m);
+    tma_load_3d(smem + L.plane, &tm_ang, bar, a.wx0, a.wy0, m);
+    tma_load_2d(smem + 2 * L.plane, &tm_obs, bar, a.wx0, a.wy0);
+    tma_load_2d(smem + 3 * L.plane, &tm_unk, bar, a.wx0, a.wy0);
+  }
+  // traction tables: (lo + ratio*q) * dt exactly as the reference evaluates it (fma.rn.f64, mul.f64)
+  const double dt64 = f2d(p.dt);
+  for (int i = tid; i < 256; i += THREADS) {
+    const double q = (double)(i - 128);
+    s_lutL[i] = fma(p.lin_ratio, q, f2d(p.lin_lo)) * dt64;
+    s_lutA[i] = fma(p.ang_ratio, q, f2d(p.ang_lo)) * dt64;
+  }
+  for (int i = tid; i < 2 * p.T; i += THREADS) s_u[i] = a.u_cur[i];
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  const float xlo = p.g.xlo, ylo = p.g.ylo, res = p.g.res, inv_res = p.g.inv_res;
+  const float v_lo = p.vrange[0], v_hi = p.vrange[1], w_lo = p.wrange[0], w_hi = p.wrange[1];
+  const float gx = p.xgoal[0], gy = p.xgoal[1];
+  const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
+  const int8_t* __restrict__ g_ang = a.ang_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
+  const float2* __restrict__ epsT = reinterpret_cast<const float2*>(a.noiseT);
+
+  for (int tile = blockIdx.x; tile * THREADS < p.N; tile += gridDim.x) {
+    const int n = tile * THREADS + tid;
+    if (n >= p.N) break;
+    float x = p.x0[0], y = p.x0[1], th = p.x0[2];
+    float cost = 0.0f, d2 = 1e9f;
+    bool reached = false;
+    for (int t = 0; t < p.T; ++t) {
+      const int xi = cell_index_fast(fsub(x, xlo), res, inv_res);
+      const int yi = cell_index_fast(fsub(y, ylo), res, inv_res);
+      const int wx = xi - a.wx0, wy = yi - a.wy0;
+      int ql, qa, ob, un;
+      if ((unsigned)wx < (unsigned)WW && (unsigned)wy < (unsigned)WH) {
+        const int off = wy * WW + wx;
+        ql = s_lin[off]; qa = s_ang[off]; ob = s_obs[off]; un = s_unk[off];
+      } else {                                              // left the staged window: same data from global
+        const int gy2 = min(max(yi < 0 ? yi + p.g.grid_rows : yi, 0), p.g.grid_rows - 1);
+        const int gx2 = min(max(xi < 0 ? xi + p.g.grid_cols : xi, 0), p.g.grid_cols - 1);
+        const int my = min(max(yi < 0 ? yi + p.g.rows : yi, 0), p.g.rows - 1);
+        const int mx = min(max(xi < 0 ? xi + p.g.cols : xi, 0), p.g.cols - 1);
+        ql = __ldg(g_lin + (size_t)gy2 * p.g.grid_pitch + gx2);
+        qa = __ldg(g_ang + (size_t)gy2 * p.g.grid_pitch + gx2);
+        ob = __ldg(a.obstacle + (size_t)my * p.g.mask_pitch + mx);
+        un = __ldg(a.unknown + (size_t)my * p.g.mask_pitch + mx);
+      }
+      const float2 e = __ldg(epsT + (size_t)t * a.npad + n);
+      const float v = fmaxf(v_lo, fminf(v_hi, fadd(s_u[2 * t], e.x)));
+      const float w = fmaxf(w_lo, fminf(w_hi, fadd(s_u[2 * t + 1], e.y)));
+      const double dv = s_lutL[ql + 128] * f2d(v);
+      const float cs = cos_approx(th);
+      const float sn = sin_approx(th);
+      x = d2f(fma(dv, f2d(cs), f2d(x)));
+      y = d2f(fma(dv, f2d(sn), f2d(y)));
+      th = d2f(fma(s_lutA[qa + 128], f2d(w), f2d(th)));
+      const float dx = fsub(gx, x), dy = fsub(gy, y);
+      d2 = ffma(dx, dx, fmul(dy, dy));
+      cost = fadd(cost, ffma(sqrt_approx(d2), p.dist_weight, p.dt));
+      if (ob) cost = ffma((float)ob, p.obs_cost, cost);
+      if (un) cost = ffma((float)un, p.unk_cost, cost);
+      if (d2 <= p.tol2) { reached = true; break; }
+    }
+    cost = fadd(cost, a.ctrl[n]);                                           // control cost (mppi.py:708-710)
+    const double num = (1.0 - (reached ? 1.0 : 0.0)) * f2d(sqrt_approx(d2));  // terminal cost (mppi.py:26-28)
+    cost = fadd(cost, d2f(num / (f2d(p.v_post) + 1e-6)));
+    a.costs_nm[(size_t)n * p.M + m] = cost;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// uint8 tensor map: rank 3 (cols, rows, maps) or rank 2 (cols, rows); box = (WW, WH[, 1])
+bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int rows, int maps, int pitch,
+                        int WW, int WH) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)maps};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)WW, (cuuint32_t)WH, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank,
+                        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+constexpr int WIN_THREADS = 1024;
+constexpr int WIN_MAX_SMEM = 232448;      // 227 KB: per-block opt-in limit on sm_100
+
+void rollout_win_geometry(int T, int* WW, int* WH, size_t* smem) {
+  // 4 byte planes + tables must fit 227 KB; inner box extent a multiple of 16 B and <= 256
+  const int ww = 240;
+  int wh = (WIN_MAX_SMEM - 2 * 256 * 8 - 2 * T * 4 - 256) / (4 * ww);
+  if (wh > 256) wh = 256;
+  wh &= ~7;                                  // plane size a multiple of 128 B (TMA destination alignment)
+  *WW = ww; *WH = wh;
+  *smem = (size_t)win_smem_layout(ww, wh, T).total;
+}
+
+int rollout_win_threads() { return WIN_THREADS; }
+
+cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, const void* tm_ang, const void* tm_obs,
+                               const void* tm_unk, cudaStream_t st) {
+  const WinSmem L = win_smem_layout(a.WW, a.WH, a.p.T);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(rollout_win_kernel<WIN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         WIN_MAX_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = (a.p.N + WIN_THREADS - 1) / WIN_THREADS;
+  int ctas_per_map = (tiles + 1) / 2;                 // each CTA reuses its staged window for ~2 tiles of n
+  if (ctas_per_map < 1) ctas_per_map = 1;
+  const dim3 grid(ctas_per_map, a.p.M);
+  rollout_win_kernel<WIN_THREADS><<<grid, WIN_THREADS, L.total, st>>>(
+      a, *reinterpret_cast<const CUtensorMap*>(tm_lin), *reinterpret_cast<const CUtensorMap*>(tm_ang),
+      *reinterpret_cast<const CUtensorMap*>(tm_obs), *reinterpret_cast<const CUtensorMap*>(tm_unk));
+  return cudaGetLastError();
+}
+
+}  // namespace b200

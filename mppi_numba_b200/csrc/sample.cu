@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
     }
     __syncthreads();
     if (active) {
-      for (int ci = c0; ci < c1; ++ci) {
-        const uint64_t v = xoro_next(s) >> 11;
+      // one cell: threshold from the 53-bit draw, then the first bin whose cumulative mass reaches it
+      auto cell = [&](int ci, uint64_t v) {
         const uint32_t est = __umulhi((uint32_t)(v >> 21), c32) >> 25;
         const uint32_t q = est + (v >= s_T[est + 1]) + (v >= s_T[est + 2]) + (v >= s_T[est + 3]);
         const uint32_t qq = q * 0x01010101u;
@@ -166,7 +166,16 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
           const int bin = __popc(bits);                       // cum is monotone: #bins below q = first bin >= q
           s_stage[(k * SG_GM + mloc) * stage_pitch + ci] = s_q[k * 128 + bin];
         }
+      };
+      int ci = c0;
+      for (; ci + 4 <= c1; ci += 4) {          // 4 draws in stream order, then 4 independent cells (ILP)
+        uint64_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = xoro_next(s) >> 11;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cell(ci + j, v[j]);
       }
+      for (; ci < c1; ++ci) cell(ci, xoro_next(s) >> 11);
     }
     __syncthreads();
     // coalesced write-back of the GM x NT staged rows: 16-byte chunks, byte tail

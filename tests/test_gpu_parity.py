@@ -262,6 +262,7 @@ def test_rollouts_vs_reference_golden(eng, golden_dir, gname):
     ("tdm", 512, 32, 48, 200, 0.1, 12, True, True),        # goal within reach: early exits
     ("det", 4096, 1, 128, 512, 0.2, 32, False, True),      # BASELINE config 4 (CVaR-dynamics alpha 0.3)
     ("spd", 1024, 1, 64, 256, 0.2, 12, True, True),        # speed-map mode
+    ("tdm", 512, 16, 128, 900, 0.05, 12, False, True),     # fine grid: rollouts LEAVE the staged window
 ])
 def test_rollout_costs_vs_oracle(eng, mode, N, M, T, H, res, B, near, warm):
     sc = make_scenario(mode, N=N, M=M, T=T, H=H, W=H, res=res, B=B, seed=4, near_goal=near, warm_start=warm,
@@ -302,6 +303,35 @@ def test_rollout_costs_vs_oracle(eng, mode, N, M, T, H, res, B, near, warm):
         assert (rc < 1e-4).mean() >= 0.99
     if near:
         assert (got < 0.5 * np.median(got)).any(), "near-goal case should contain early exits"
+
+
+def test_window_kernel_equals_generic_kernel(eng, monkeypatch):
+    """The TMA-window kernel and the generic global-memory kernel walk identical trajectories: per-(n,m)
+    costs agree to the rounding of the pre-summed control cost (~1 ulp), including rollouts that leave
+    the window (res 0.05 m, T = 128)."""
+    sc = make_scenario("tdm", N=512, M=16, T=128, H=900, W=900, res=0.05, B=12, seed=8, warm_start=True)
+    L = eng._lib
+    outs = []
+    noise = grids = None
+    for no_win in (False, True):
+        if no_win:
+            monkeypatch.setenv("B200MPPI_NO_WINDOW", "1")
+        cfg = eng.Config(**sc["cfg"])
+        lin, ang = eng.TDM_Numba(cfg), eng.TDM_Numba(cfg)
+        lin.set_TDM_from_PMF_grid(sc["pmf_lin"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+        ang.set_TDM_from_PMF_grid(sc["pmf_ang"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+        pl = eng.MPPI_Numba(cfg)
+        pl.setup(sc["params"], lin, ang)
+        pl.u_cur_d.copy_to_device(sc["u0"])
+        pl.move_mppi_task_vars_to_device()
+        lin.sample_grids(1.0)
+        ang.sample_grids(1.0)
+        L.check(L.lib.b200mppi_planner_sample_noise(pl._handle))
+        L.check(L.lib.b200mppi_planner_rollout(pl._handle))
+        outs.append(pl.costs_nm_d.copy_to_host())
+    monkeypatch.delenv("B200MPPI_NO_WINDOW")
+    r = rel_err(outs[0], outs[1])
+    assert r.max() < 2e-6, r.max()
 
 
 def test_cvar_selection_properties(eng):
