@@ -593,7 +593,11 @@ static int stage_rollout(b200mppi_planner* p) {
       w.WW = WW; w.WH = WH;
       const int xi0 = (int)std::floor(((double)p->prm.x0[0] - (double)l->pxl[0]) / (double)l->res);
       const int yi0 = (int)std::floor(((double)p->prm.x0[1] - (double)l->pyl[0]) / (double)l->res);
-      w.wx0 = xi0 - WW / 2; w.wy0 = yi0 - WH / 2;
+      // TMA: the inner (x) start coordinate must be 16-byte aligned for 1-byte elements (probed on B200:
+      // an unaligned c0 raises 'illegal instruction'); floor to a multiple of 16, also for negatives
+      const int cx = xi0 - WW / 2;
+      w.wx0 = (cx >= 0) ? (cx & ~15) : -(((-cx) + 15) & ~15);
+      w.wy0 = yi0 - WH / 2;
       w.npad = p->npad;
       w.lin_grid = l->grid; w.ang_grid = g->grid; w.obstacle = l->obstacle; w.unknown = l->unknown;
       w.noiseT = p->noiseT; w.ctrl = p->ctrl; w.u_cur = p->u_cur; w.costs_nm = p->costs_nm;
