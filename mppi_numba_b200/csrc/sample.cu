@@ -119,6 +119,15 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
     if (NT == 2) s_q[128 + i] = (unsigned char)a.t[1].qvals[i];
   }
 
+  // value tables for <= 16 bins live in registers (4 x 32-bit per TDM), looked up with PRMT
+  uint32_t qreg[NT][4];
+#pragma unroll
+  for (int k = 0; k < NT; ++k) {
+    const int8_t* qv = (NT == 2 && k == 1) ? a.t[1].qvals : a.t[0].qvals;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) qreg[k][w] = __ldg(reinterpret_cast<const uint32_t*>(qv) + w);
+  }
+
   const int ncol = (a.cols + a.ty - 1) / a.ty;
   const int nrow = (a.rows + a.tx - 1) / a.tx;
   const int r0 = min(tix * nrow, a.rows), r1 = min(r0 + nrow, a.rows);
@@ -138,12 +147,15 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
     for (int k = 0; k < NT; ++k) {
       const uint32_t* src = reinterpret_cast<const uint32_t*>(a.t[k].cum + (size_t)ri * row_bytes);
       uint32_t* dst = reinterpret_cast<uint32_t*>(s_cum + k * row_bytes_al);
+#pragma unroll 8
       for (int i = tid; i < row_bytes / 4; i += nthreads) dst[i] = __ldg(src + i);
     }
     __syncthreads();
     if (active) {
-      // one cell: threshold from the 53-bit draw, then the first bin whose cumulative mass reaches it
-      auto cell = [&](int ci, uint64_t v) {
+      // one cell: threshold from the 53-bit draw, then the first bin whose cumulative mass reaches it.
+      // Returns the sampled value byte of each TDM; the caller stores them AFTER a group of cells so that
+      // the shared-memory loads of the whole group are independent of the byte stores (ILP).
+      auto cell = [&](int ci, uint64_t v, uint32_t (&outv)[NT]) {
         const uint32_t est = __umulhi((uint32_t)(v >> 21), c32) >> 25;
         const uint32_t q = est + (v >= s_T[est + 1]) + (v >= s_T[est + 2]) + (v >= s_T[est + 3]);
         const uint32_t qq = q * 0x01010101u;
@@ -164,18 +176,37 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
             }
           }
           const int bin = __popc(bits);                       // cum is monotone: #bins below q = first bin >= q
-          s_stage[(k * SG_GM + mloc) * stage_pitch + ci] = s_q[k * 128 + bin];
+          if (NW > 0 && NW <= 4) {                            // value table in registers: byte-permute lookup
+            const uint32_t lo8 = __byte_perm(qreg[k][0], qreg[k][1], bin & 7);
+            const uint32_t hi8 = __byte_perm(qreg[k][2], qreg[k][3], bin & 7);
+            outv[k] = ((bin & 8) ? hi8 : lo8) & 0xffu;
+          } else {
+            outv[k] = s_q[k * 128 + bin];
+          }
         }
       };
+      unsigned char* st0 = s_stage + mloc * stage_pitch;
+      unsigned char* st1 = s_stage + (SG_GM + mloc) * stage_pitch;
       int ci = c0;
       for (; ci + 4 <= c1; ci += 4) {          // 4 draws in stream order, then 4 independent cells (ILP)
         uint64_t v[4];
+        uint32_t o[4][NT];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = xoro_next(s) >> 11;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cell(ci + j, v[j]);
+        for (int j = 0; j < 4; ++j) cell(ci + j, v[j], o[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          st0[ci + j] = (unsigned char)o[j][0];
+          if (NT == 2) st1[ci + j] = (unsigned char)o[j][NT - 1];
+        }
       }
-      for (; ci < c1; ++ci) cell(ci, xoro_next(s) >> 11);
+      for (; ci < c1; ++ci) {
+        uint32_t o[NT];
+        cell(ci, xoro_next(s) >> 11, o);
+        st0[ci] = (unsigned char)o[0];
+        if (NT == 2) st1[ci] = (unsigned char)o[NT - 1];
+      }
     }
     __syncthreads();
     // coalesced write-back of the GM x NT staged rows: 16-byte chunks, byte tail
