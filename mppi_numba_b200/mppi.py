@@ -240,7 +240,7 @@ class MPPI_Numba(object):
         for tdm in (self.lin_tdm, self.ang_tdm):
             check(lib.b200mppi_tdm_set_stream(tdm._handle, C.c_void_p(self._stream.cuda_stream)))
         self._partial_t = torch.as_tensor(self.partial_d, device=dev)          # zero-copy view
-        self._gathered = torch.empty((self.world_size, 2 * self.num_steps + 2), dtype=torch.float32, device=dev)
+        self._gathered = torch.empty((self.world_size * (2 * self.num_steps + 2),), dtype=torch.float32, device=dev)
 
     def _solve_sharded(self, u_out):
         import torch
