@@ -578,7 +578,7 @@ static int stage_rollout(b200mppi_planner* p) {
     int WW, WH; size_t smem;
     rollout_win_geometry(p->T, &WW, &WH, &smem);
     const b200mppi_tdm* l = p->lin; const b200mppi_tdm* g = p->ang;
-    const bool ok = WH >= 16 &&
+    const bool ok = smem <= 232448 &&
         make_u8_tensor_map(p->tmaps[0], l->grid, 3, l->cfg.max_map_cols, l->cfg.max_map_rows, l->num_maps, l->pitch, WW, WH) &&
         make_u8_tensor_map(p->tmaps[1], g->grid, 3, g->cfg.max_map_cols, g->cfg.max_map_rows, g->num_maps, g->pitch, WW, WH) &&
         make_u8_tensor_map(p->tmaps[2], l->obstacle, 2, l->mask_cols, l->mask_rows, 1, l->mask_pitch, WW, WH) &&

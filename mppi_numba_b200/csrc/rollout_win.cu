@@ -96,16 +96,30 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
       ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
-// round-down magic: for |y| < 2^22, (y (+)rd 1.5*2^23) has floor(y) in its low mantissa bits
-__device__ __forceinline__ int cell_index_fast(float a, float r, float inv_r) {
-  const float MAGIC = 12582912.0f;
-  const float y = a * inv_r;
-  const float yk = __fadd_rd(y, MAGIC);
-  const float fl = yk - MAGIC;                    // exact
-  const float frac = y - fl;
-  const float eps = fmaf(fabsf(y), 4.8e-7f, 1e-6f);
-  if (frac > eps && frac < 1.0f - eps && fabsf(y) < 4194304.0f) return __float_as_int(yk) - 0x4B400000;
-  return cell_index_exact(a, r);
+// explicit shared-space loads (a generic pointer into dynamic smem makes the compiler rebuild the
+// shared-window base with S2UR/ULEA every iteration)
+__device__ __forceinline__ int lds_s8(uint32_t addr, int imm_plane) {
+  int v;
+  asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr + (uint32_t)imm_plane));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+  float2 v;
+  asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+// widening / narrowing without the .ftz flush (the reference flushes f32 denormals here; positions,
+// headings and clipped controls are never denormal, zero converts exactly either way)
+__device__ __forceinline__ double widen(float a) {
+  double r; asm("cvt.f64.f32 %0, %1;" : "=d"(r) : "f"(a)); return r;
+}
+__device__ __forceinline__ float narrow(double a) {
+  float r; asm("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(a)); return r;
 }
 
 struct WinSmem {                 // dynamic shared memory carve-up (all offsets multiples of 128)
@@ -123,7 +137,9 @@ __host__ __device__ inline WinSmem win_smem_layout(int WW, int WH, int T) {
   return s;
 }
 
-template <int THREADS>
+constexpr int WIN_WW = 240;       // window width in cells (inner TMA box extent: 240 B, multiple of 16)
+
+template <int THREADS, int WH>
 __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWinArgs a,
                                                                  const __grid_constant__ CUtensorMap tm_lin,
                                                                  const __grid_constant__ CUtensorMap tm_ang,
@@ -131,12 +147,9 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
                                                                  const __grid_constant__ CUtensorMap tm_unk) {
   extern __shared__ __align__(128) unsigned char smem[];
   const RolloutParams& p = a.p;
-  const int WW = a.WW, WH = a.WH;
+  constexpr int WW = WIN_WW;
+  constexpr int PLANE = WW * WH;
   const WinSmem L = win_smem_layout(WW, WH, p.T);
-  const int8_t* s_lin = reinterpret_cast<const int8_t*>(smem);
-  const int8_t* s_ang = s_lin + L.plane;
-  const int8_t* s_obs = s_ang + L.plane;
-  const int8_t* s_unk = s_obs + L.plane;
   double* s_lutL = reinterpret_cast<double*>(smem + L.off_lut);
   double* s_lutA = s_lutL + 256;
   float* s_u = reinterpret_cast<float*>(smem + L.off_u);
@@ -148,11 +161,11 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(bar, 4u * (uint32_t)L.plane);
+    mbar_expect_tx(bar, 4u * (uint32_t)PLANE);
     tma_load_3d(smem, &tm_lin, bar, a.wx0, a.wy0, m);
-    tma_load_3d(smem + L.plane, &tm_ang, bar, a.wx0, a.wy0, m);
-    tma_load_2d(smem + 2 * L.plane, &tm_obs, bar, a.wx0, a.wy0);
-    tma_load_2d(smem + 3 * L.plane, &tm_unk, bar, a.wx0, a.wy0);
+    tma_load_3d(smem + PLANE, &tm_ang, bar, a.wx0, a.wy0, m);
+    tma_load_2d(smem + 2 * PLANE, &tm_obs, bar, a.wx0, a.wy0);
+    tma_load_2d(smem + 3 * PLANE, &tm_unk, bar, a.wx0, a.wy0);
   }
   // traction tables: (lo + ratio*q) * dt exactly as the reference evaluates it (fma.rn.f64, mul.f64)
   const double dt64 = f2d(p.dt);
@@ -165,28 +178,51 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   __syncthreads();
   mbar_wait(bar, 0);
 
+  uint32_t sb_win = smem_u32(smem);
+  uint32_t sb_lutL = smem_u32(s_lutL) + 128 * 8;     // index by the signed int8 value directly
+  uint32_t sb_lutA = smem_u32(s_lutA) + 128 * 8;
+  uint32_t sb_u = smem_u32(s_u);
+  // keep the shared-window addresses in registers (opaque to the optimiser, which would otherwise
+  // re-derive them from SR_CgaCtaId with S2UR/ULEA inside the loop)
+  asm volatile("" : "+r"(sb_win), "+r"(sb_lutL), "+r"(sb_lutA), "+r"(sb_u));
   const float xlo = p.g.xlo, ylo = p.g.ylo, res = p.g.res, inv_res = p.g.inv_res;
   const float v_lo = p.vrange[0], v_hi = p.vrange[1], w_lo = p.wrange[0], w_hi = p.wrange[1];
   const float gx = p.xgoal[0], gy = p.xgoal[1];
+  const float MAGIC = 12582912.0f;                          // 1.5 * 2^23
   const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
   const int8_t* __restrict__ g_ang = a.ang_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
-  const float2* __restrict__ epsT = reinterpret_cast<const float2*>(a.noiseT);
 
   for (int tile = blockIdx.x; tile * THREADS < p.N; tile += gridDim.x) {
     const int n = tile * THREADS + tid;
     if (n >= p.N) break;
+    const float2* __restrict__ ep = reinterpret_cast<const float2*>(a.noiseT) + n;
     float x = p.x0[0], y = p.x0[1], th = p.x0[2];
     float cost = 0.0f, d2 = 1e9f;
     bool reached = false;
-    for (int t = 0; t < p.T; ++t) {
-      const int xi = cell_index_fast(fsub(x, xlo), res, inv_res);
-      const int yi = cell_index_fast(fsub(y, ylo), res, inv_res);
+    uint32_t ua = sb_u;
+    for (int t = 0; t < p.T; ++t, ep += a.npad, ua += 8) {
+      // ---- cell index of both axes: floor(a/res) by round-down magic-number addition on the FP32 pipe;
+      //      |frac - 0.5| < 0.5 - 5 ulp(y) proves it equals the reference's exact sequence, else run that
+      const float ax = fsub(x, xlo), ay = fsub(y, ylo);
+      const float yx = ax * inv_res, yy = ay * inv_res;
+      const float kx = __fadd_rd(yx, MAGIC), ky = __fadd_rd(yy, MAGIC);
+      const float hx = (yx - 0.5f) - (kx - MAGIC);
+      const float hy = (yy - 0.5f) - (ky - MAGIC);
+      const float lx = fmaf(fabsf(yx), -6.0e-7f, 0.499999f);
+      const float ly = fmaf(fabsf(yy), -6.0e-7f, 0.499999f);
+      int xi = __float_as_int(kx) - 0x4B400000;
+      int yi = __float_as_int(ky) - 0x4B400000;
+      if (!(fabsf(hx) < lx && fabsf(hy) < ly)) {
+        xi = cell_index_exact(ax, res);
+        yi = cell_index_exact(ay, res);
+      }
+      // ---- traction / mask lookup: staged window, global memory only for rollouts that left it
       const int wx = xi - a.wx0, wy = yi - a.wy0;
       int ql, qa, ob, un;
       if ((unsigned)wx < (unsigned)WW && (unsigned)wy < (unsigned)WH) {
-        const int off = wy * WW + wx;
-        ql = s_lin[off]; qa = s_ang[off]; ob = s_obs[off]; un = s_unk[off];
-      } else {                                              // left the staged window: same data from global
+        const uint32_t ad = sb_win + (uint32_t)(wy * WW + wx);
+        ql = lds_s8(ad, 0); qa = lds_s8(ad, PLANE); ob = lds_s8(ad, 2 * PLANE); un = lds_s8(ad, 3 * PLANE);
+      } else {
         const int gy2 = min(max(yi < 0 ? yi + p.g.grid_rows : yi, 0), p.g.grid_rows - 1);
         const int gx2 = min(max(xi < 0 ? xi + p.g.grid_cols : xi, 0), p.g.grid_cols - 1);
         const int my = min(max(yi < 0 ? yi + p.g.rows : yi, 0), p.g.rows - 1);
@@ -196,24 +232,30 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
         ob = __ldg(a.obstacle + (size_t)my * p.g.mask_pitch + mx);
         un = __ldg(a.unknown + (size_t)my * p.g.mask_pitch + mx);
       }
-      const float2 e = __ldg(epsT + (size_t)t * a.npad + n);
-      const float v = fmaxf(v_lo, fminf(v_hi, fadd(s_u[2 * t], e.x)));
-      const float w = fmaxf(w_lo, fminf(w_hi, fadd(s_u[2 * t + 1], e.y)));
-      const double dv = s_lutL[ql + 128] * f2d(v);
+      // ---- noisy clipped control (mppi.py:686-689)
+      const float2 e = __ldg(ep);
+      const float2 u = lds_f32x2(ua);
+      const float v = fmaxf(v_lo, fminf(v_hi, fadd(u.x, e.x)));
+      const float w = fmaxf(w_lo, fminf(w_hi, fadd(u.y, e.y)));
+      // ---- unicycle step (mppi.py:692-694): float64 FMA, one rounding to float32 per component
+      const double dv = lds_f64(sb_lutL + (uint32_t)(ql * 8)) * widen(v);
       const float cs = cos_approx(th);
       const float sn = sin_approx(th);
-      x = d2f(fma(dv, f2d(cs), f2d(x)));
-      y = d2f(fma(dv, f2d(sn), f2d(y)));
-      th = d2f(fma(s_lutA[qa + 128], f2d(w), f2d(th)));
+      x = narrow(fma(dv, widen(cs), widen(x)));
+      y = narrow(fma(dv, widen(sn), widen(y)));
+      th = narrow(fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), widen(w), widen(th)));
+      // ---- stage cost (mppi.py:696-701)
       const float dx = fsub(gx, x), dy = fsub(gy, y);
       d2 = ffma(dx, dx, fmul(dy, dy));
       cost = fadd(cost, ffma(sqrt_approx(d2), p.dist_weight, p.dt));
-      if (ob) cost = ffma((float)ob, p.obs_cost, cost);
-      if (un) cost = ffma((float)un, p.unk_cost, cost);
+      if (ob | un) {
+        cost = ffma((float)ob, p.obs_cost, cost);
+        cost = ffma((float)un, p.unk_cost, cost);
+      }
       if (d2 <= p.tol2) { reached = true; break; }
     }
     cost = fadd(cost, a.ctrl[n]);                                           // control cost (mppi.py:708-710)
-    const double num = (1.0 - (reached ? 1.0 : 0.0)) * f2d(sqrt_approx(d2));  // terminal cost (mppi.py:26-28)
+    const double num = (reached ? 0.0 : 1.0) * f2d(sqrt_approx(d2));         // terminal cost (mppi.py:26-28)
     cost = fadd(cost, d2f(num / (f2d(p.v_post) + 1e-6)));
     a.costs_nm[(size_t)n * p.M + m] = cost;
   }
@@ -257,13 +299,11 @@ constexpr int WIN_THREADS = 1024;
 constexpr int WIN_MAX_SMEM = 232448;      // 227 KB: per-block opt-in limit on sm_100
 
 void rollout_win_geometry(int T, int* WW, int* WH, size_t* smem) {
-  // 4 byte planes + tables must fit 227 KB; inner box extent a multiple of 16 B and <= 256
-  const int ww = 240;
-  int wh = (WIN_MAX_SMEM - 2 * 256 * 8 - 2 * T * 4 - 256) / (4 * ww);
-  if (wh > 256) wh = 256;
-  wh &= ~7;                                  // plane size a multiple of 128 B (TMA destination alignment)
-  *WW = ww; *WH = wh;
-  *smem = (size_t)win_smem_layout(ww, wh, T).total;
+  // 4 byte planes + tables must fit 227 KB; inner box extent a multiple of 16 B and <= 256; plane size a
+  // multiple of 128 B (TMA destination alignment).  Two compiled heights: 232 rows (T <= 700), 224 rows.
+  const int wh = (win_smem_layout(WIN_WW, 232, T).total <= WIN_MAX_SMEM) ? 232 : 224;
+  *WW = WIN_WW; *WH = wh;
+  *smem = (size_t)win_smem_layout(WIN_WW, wh, T).total;
 }
 
 int rollout_win_threads() { return WIN_THREADS; }
@@ -273,18 +313,25 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
   const WinSmem L = win_smem_layout(a.WW, a.WH, a.p.T);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rollout_win_kernel<WIN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         WIN_MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(rollout_win_kernel<WIN_THREADS, 232>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_MAX_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(rollout_win_kernel<WIN_THREADS, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               WIN_MAX_SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  if (a.WW != WIN_WW || (a.WH != 232 && a.WH != 224) || L.total > WIN_MAX_SMEM) return cudaErrorInvalidValue;
   const int tiles = (a.p.N + WIN_THREADS - 1) / WIN_THREADS;
   int ctas_per_map = (tiles + 1) / 2;                 // each CTA reuses its staged window for ~2 tiles of n
   if (ctas_per_map < 1) ctas_per_map = 1;
   const dim3 grid(ctas_per_map, a.p.M);
-  rollout_win_kernel<WIN_THREADS><<<grid, WIN_THREADS, L.total, st>>>(
-      a, *reinterpret_cast<const CUtensorMap*>(tm_lin), *reinterpret_cast<const CUtensorMap*>(tm_ang),
-      *reinterpret_cast<const CUtensorMap*>(tm_obs), *reinterpret_cast<const CUtensorMap*>(tm_unk));
+  const CUtensorMap& t0 = *reinterpret_cast<const CUtensorMap*>(tm_lin);
+  const CUtensorMap& t1 = *reinterpret_cast<const CUtensorMap*>(tm_ang);
+  const CUtensorMap& t2 = *reinterpret_cast<const CUtensorMap*>(tm_obs);
+  const CUtensorMap& t3 = *reinterpret_cast<const CUtensorMap*>(tm_unk);
+  if (a.WH == 232) rollout_win_kernel<WIN_THREADS, 232><<<grid, WIN_THREADS, L.total, st>>>(a, t0, t1, t2, t3);
+  else rollout_win_kernel<WIN_THREADS, 224><<<grid, WIN_THREADS, L.total, st>>>(a, t0, t1, t2, t3);
   return cudaGetLastError();
 }
 
