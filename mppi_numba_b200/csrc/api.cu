@@ -585,7 +585,7 @@ static int stage_rollout(b200mppi_planner* p) {
         make_u8_tensor_map(p->tmaps[3], l->unknown, 2, l->mask_cols, l->mask_rows, 1, l->mask_pitch, WW, WH);
     if (ok) {
       launch_prepare_rollout(p->noise, p->u_cur, p->noiseT, p->ctrl, p->n_local, p->T, p->npad, p->prm.lambda_weight,
-                             p->prm.u_std[0], p->prm.u_std[1], p->stream);
+                             p->prm.u_std[0], p->prm.u_std[1], p->prm.vrange, p->prm.wrange, p->stream);
       p->launches++;
       CHECK_LAUNCH();
       RolloutWinArgs w{};

@@ -63,13 +63,14 @@ struct RolloutWinArgs {
   int WW, WH, wx0, wy0;     // window size / origin in cells
   int npad;                 // row length of noiseT
   const int8_t* lin_grid; const int8_t* ang_grid; const int8_t* obstacle; const int8_t* unknown;
-  const float* noiseT;      // [T][npad] float2
+  const float* noiseT;      // [T][npad] float2: clipped noisy controls (v, w)
   const float* ctrl;        // [npad]
   const float* u_cur;
   float* costs_nm;          // (N, M)
 };
 void launch_prepare_rollout(const float* noise, const float* u_cur, float* noiseT, float* ctrl, int N, int T,
-                            int npad, float lambda, float std_v, float std_w, cudaStream_t st);
+                            int npad, float lambda, float std_v, float std_w, const float vrange[2],
+                            const float wrange[2], cudaStream_t st);
 bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int rows, int maps, int pitch,
                         int WW, int WH);
 void rollout_win_geometry(int T, int* WW, int* WH, size_t* smem);

@@ -24,14 +24,17 @@
 namespace b200 {
 
 // ---------------------------------------------------------------------------------------------
-// prepare: noise (N,T,2) -> transposed noiseT [T][npad] float2 (coalesced per-step loads for lanes =
-// consecutive n) and the per-n control cost  sum_t lambda*(u_v/s_v^2*e_v + u_w/s_w^2*e_w)
+// prepare: noise (N,T,2) -> transposed CLIPPED NOISY CONTROLS ctlT [T][npad] float2
+//   (v, w) = (clip(u_v[t] + e_v, vrange), clip(u_w[t] + e_w, wrange))           (mppi.py:686-689)
+// -- identical for all M maps of a control sequence, so computed once here (coalesced per-step loads
+// for lanes = consecutive n) -- and the per-n control cost sum_t lambda*(u_v/s_v^2*e_v + u_w/s_w^2*e_w)
 // (mppi.py:708-710), accumulated in the reference's order t = 0..T-1.
 __global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __restrict__ noise,
                                                               const float* __restrict__ u_cur,
                                                               float2* __restrict__ noiseT,
                                                               float* __restrict__ ctrl, int N, int T, int npad,
-                                                              float lambda, float sv2, float sw2) {
+                                                              float lambda, float sv2, float sw2, float v_lo,
+                                                              float v_hi, float w_lo, float w_hi) {
   __shared__ float2 tile[32][33];
   const int n0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
@@ -44,7 +47,13 @@ __global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __re
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {                         // rows = t, cols = n  (coalesced along n)
       const int t = t0 + r;
-      if (t < T) noiseT[(size_t)t * npad + n0 + tx] = tile[tx][r];
+      if (t < T) {
+        const float2 e = tile[tx][r];
+        float2 c;
+        c.x = fmaxf(v_lo, fminf(v_hi, fadd(u_cur[2 * t], e.x)));
+        c.y = fmaxf(w_lo, fminf(w_hi, fadd(u_cur[2 * t + 1], e.y)));
+        noiseT[(size_t)t * npad + n0 + tx] = c;
+      }
     }
     if (ty == 0) {                                             // lane tx owns rollout n0+tx
       const int tend = min(32, T - t0);
@@ -61,10 +70,12 @@ __global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __re
 }
 
 void launch_prepare_rollout(const float* noise, const float* u_cur, float* noiseT, float* ctrl, int N, int T,
-                            int npad, float lambda, float std_v, float std_w, cudaStream_t st) {
+                            int npad, float lambda, float std_v, float std_w, const float vrange[2],
+                            const float wrange[2], cudaStream_t st) {
   prepare_rollout_kernel<<<npad / 32, 256, 0, st>>>(reinterpret_cast<const float2*>(noise), u_cur,
                                                    reinterpret_cast<float2*>(noiseT), ctrl, N, T, npad, lambda,
-                                                   std_v * std_v, std_w * std_w);
+                                                   std_v * std_v, std_w * std_w, vrange[0], vrange[1], wrange[0],
+                                                   wrange[1]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -120,6 +131,16 @@ __device__ __forceinline__ double widen(float a) {
 }
 __device__ __forceinline__ float narrow(double a) {
   float r; asm("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(a)); return r;
+}
+// float64 value rounded to float32 precision (round-to-nearest-even at bit 29), kept as float64:
+// == widen(narrow(a)) for every |a| in the float32 normal range, but on the integer pipe instead of a
+// second XU-pipe conversion (f64 conversions issue at half the MUFU rate on sm_100).
+__device__ __forceinline__ double round_to_f32_precision(double a) {
+  const uint32_t lo = (uint32_t)__double2loint(a), hi = (uint32_t)__double2hiint(a);
+  const uint32_t inc = 0x0FFFFFFFu + ((lo >> 29) & 1u);
+  const uint32_t lo2 = lo + inc;
+  const uint32_t hi2 = hi + (lo2 < lo ? 1u : 0u);
+  return __hiloint2double((int)hi2, (int)(lo2 & 0xE0000000u));
 }
 
 struct WinSmem {                 // dynamic shared memory carve-up (all offsets multiples of 128)
@@ -186,7 +207,6 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   // re-derive them from SR_CgaCtaId with S2UR/ULEA inside the loop)
   asm volatile("" : "+r"(sb_win), "+r"(sb_lutL), "+r"(sb_lutA), "+r"(sb_u));
   const float xlo = p.g.xlo, ylo = p.g.ylo, res = p.g.res, inv_res = p.g.inv_res;
-  const float v_lo = p.vrange[0], v_hi = p.vrange[1], w_lo = p.wrange[0], w_hi = p.wrange[1];
   const float gx = p.xgoal[0], gy = p.xgoal[1];
   const float MAGIC = 12582912.0f;                          // 1.5 * 2^23
   const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
@@ -197,10 +217,10 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     if (n >= p.N) break;
     const float2* __restrict__ ep = reinterpret_cast<const float2*>(a.noiseT) + n;
     float x = p.x0[0], y = p.x0[1], th = p.x0[2];
+    double x64 = widen(x), y64 = widen(y), th64 = widen(th);   // same values, float64 registers
     float cost = 0.0f, d2 = 1e9f;
     bool reached = false;
-    uint32_t ua = sb_u;
-    for (int t = 0; t < p.T; ++t, ep += a.npad, ua += 8) {
+    for (int t = 0; t < p.T; ++t, ep += a.npad) {
       // ---- cell index of both axes: floor(a/res) by round-down magic-number addition on the FP32 pipe;
       //      |frac - 0.5| < 0.5 - 5 ulp(y) proves it equals the reference's exact sequence, else run that
       const float ax = fsub(x, xlo), ay = fsub(y, ylo);
@@ -232,18 +252,18 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
         ob = __ldg(a.obstacle + (size_t)my * p.g.mask_pitch + mx);
         un = __ldg(a.unknown + (size_t)my * p.g.mask_pitch + mx);
       }
-      // ---- noisy clipped control (mppi.py:686-689)
-      const float2 e = __ldg(ep);
-      const float2 u = lds_f32x2(ua);
-      const float v = fmaxf(v_lo, fminf(v_hi, fadd(u.x, e.x)));
-      const float w = fmaxf(w_lo, fminf(w_hi, fadd(u.y, e.y)));
-      // ---- unicycle step (mppi.py:692-694): float64 FMA, one rounding to float32 per component
-      const double dv = lds_f64(sb_lutL + (uint32_t)(ql * 8)) * widen(v);
+      // ---- noisy clipped control (mppi.py:686-689), precomputed per (n, t) by the prepare kernel
+      const float2 c = __ldg(ep);
+      // ---- unicycle step (mppi.py:692-694): float64 FMA, one rounding to float32 per component.  The
+      //      float64 copies hold the float32-rounded state, so the reference's f2d(x) costs nothing.
+      const double dv = lds_f64(sb_lutL + (uint32_t)(ql * 8)) * widen(c.x);
       const float cs = cos_approx(th);
       const float sn = sin_approx(th);
-      x = narrow(fma(dv, widen(cs), widen(x)));
-      y = narrow(fma(dv, widen(sn), widen(y)));
-      th = narrow(fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), widen(w), widen(th)));
+      const double rx = fma(dv, widen(cs), x64);
+      const double ry = fma(dv, widen(sn), y64);
+      const double rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), widen(c.y), th64);
+      x = narrow(rx); y = narrow(ry); th = narrow(rt);
+      x64 = round_to_f32_precision(rx); y64 = round_to_f32_precision(ry); th64 = round_to_f32_precision(rt);
       // ---- stage cost (mppi.py:696-701)
       const float dx = fsub(gx, x), dy = fsub(gy, y);
       d2 = ffma(dx, dx, fmul(dy, dy));
