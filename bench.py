@@ -181,9 +181,9 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------- algorithmic bytes
-def algorithmic_bytes(sc, cfg, n_local):
-    """Compulsory HBM bytes per solve and per kernel, counting each operand once."""
-    N, M, T = n_local, (sc["M"] if sc["mode"] == "tdm" else 1), sc["T"]
+def algorithmic_bytes(sc, cfg, n_local, m_local):
+    """Compulsory HBM bytes per solve and per kernel on ONE rank, each operand once."""
+    N, M, T = n_local, m_local, sc["T"]
     B = sc["pmf_lin"].shape[0]
     Hp, Wp = cfg.max_map_dim
     p = sc["params"]
@@ -250,7 +250,8 @@ def run_b200(args, sc):
     import contextlib
     with contextlib.redirect_stdout(io.StringIO()):
         cfg = E.Config(**sc["cfg"])
-        lin, ang = E.TDM_Numba(cfg, device=local), E.TDM_Numba(cfg, device=local)
+        lin = E.TDM_Numba(cfg, device=local, rank=rank, world_size=world)
+        ang = E.TDM_Numba(cfg, device=local, rank=rank, world_size=world)
         lin.set_TDM_from_PMF_grid(sc["pmf_lin"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
         ang.set_TDM_from_PMF_grid(sc["pmf_ang"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
         pl = E.MPPI_Numba(cfg, device=local, rank=rank, world_size=world, process_group=pg)
@@ -327,7 +328,7 @@ def run_b200(args, sc):
             acc.setdefault(k, []).append(v)
     pl.set_profiling(False)
     stage_ms = {k: float(np.mean(v)) for k, v in acc.items()}
-    ab = algorithmic_bytes(sc, cfg, pl.n_local)
+    ab = algorithmic_bytes(sc, cfg, pl.n_local, pl.m_local)
     peak, peak_src = measured_peaks()
     dom = max(("sample_grids", "rollout", "noise", "cvar", "update"), key=lambda k: stage_ms.get(k, 0.0))
     dom_ms = stage_ms[dom] / (2.0 if dom == "sample_grids" else 1.0)     # two launches (lin, ang)
@@ -347,7 +348,7 @@ def run_b200(args, sc):
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
                "config": {"workload": workload_name(args, sc), "global_rollouts": N, "maps": M, "horizon": T,
-                          "parallelism": "N-sharded x%d, 1 all-gather of %d floats per solve" % (world, 2 * T + 2),
+                          "parallelism": ("maps sharded x%d (M/G maps per rank, all N rollouts), all-to-all of N*M/G costs + all-gather of %d floats per solve" if sc["mode"] == "tdm" else "N-sharded x%d, 1 all-gather of %d floats per solve") % (world, 2 * T + 2),
                           "l2": "per-step working set (2 x %d MB sampled maps) exceeds the 126 MB L2; no explicit flush"
                                 % (M * cfg.max_map_dim[0] * cfg.max_map_dim[1] // 2 ** 20)},
                "clocks": clk,

@@ -157,6 +157,18 @@ int b200mppi_planner_shift_u(b200mppi_planner* pl, int32_t num_shifts);
  * sample both TDMs, then num_opt x (noise, rollout, CVaR, update); returns u_cur (T,2) in u_out. */
 int b200mppi_planner_solve(b200mppi_planner* pl, float* u_out);
 
+/* Multi-GPU, MODE_TDM (the M sampled maps are sharded: rank r owns maps [r*M/ws, (r+1)*M/ws), samples
+ * only those -- bit-identical to the same maps of a single-rank run -- and rolls out ALL N control
+ * sequences on them):
+ *   solve_local  : [first_iteration: sample this rank's maps] noise, rollouts -> B200MPPI_BUF_COSTS_NM
+ *                  (N, M/ws) float32 = the send buffer of an all-to-all (block d -> rank d: rows
+ *                  [d*N/ws, (d+1)*N/ws)).
+ *   solve_reduce : CVaR over all M maps for this rank's N/ws control sequences from the received buffer
+ *                  (world_size, N/ws, M/ws) float32, then this rank's softmax partial (2T+2 float32).
+ *   solve_finish : as below.
+ * Multi-GPU, deterministic modes (one map): the N control sequences are sharded, no solve_reduce. */
+int b200mppi_planner_solve_reduce(b200mppi_planner* pl, const float* exchanged_costs_dev);
+
 /* Multi-GPU (world_size > 1): one optimisation iteration split around the single exchange.
  *   solve_local : [first_iteration: sample both TDMs] noise, rollout, CVaR, and this rank's softmax
  *                 partial  (beta_r = min cost, S_r = sum exp(-(c-beta_r)/lambda), V_r[2T] = sum w*eps)
@@ -186,7 +198,7 @@ int b200mppi_planner_update(b200mppi_planner* pl, const float* costs);
 int b200mppi_planner_get_state_rollout(b200mppi_planner* pl, float* out, size_t bytes);
 
 enum {
-  B200MPPI_BUF_NOISE = 0,     /* float32 (N_local, T, 2)   noise_samples_d            */
+  B200MPPI_BUF_NOISE = 0,     /* float32 (N_roll, T, 2)    noise_samples_d (N_roll = N when maps are sharded) */
   B200MPPI_BUF_U_CUR = 1,     /* float32 (T, 2)            u_cur_d                    */
   B200MPPI_BUF_COSTS = 2,     /* float32 (N_local)         costs_d (NOT clobbered)    */
   B200MPPI_BUF_WEIGHTS = 3,   /* float32 (N_local)         weights_d (normalised)     */

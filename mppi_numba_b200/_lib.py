@@ -76,6 +76,7 @@ def _load():
         "b200mppi_planner_shift_u": (C.c_int, [P, I32]),
         "b200mppi_planner_solve": (C.c_int, [P, P]),
         "b200mppi_planner_solve_local": (C.c_int, [P, I32]),
+        "b200mppi_planner_solve_reduce": (C.c_int, [P, P]),
         "b200mppi_planner_solve_finish": (C.c_int, [P, P, P]),
         "b200mppi_combine_partials_host": (C.c_int, [P, I32, I32, F, P, P, P, P]),
         "b200mppi_planner_sample_noise": (C.c_int, [P]),

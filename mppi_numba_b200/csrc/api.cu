@@ -164,7 +164,17 @@ extern "C" int b200mppi_tdm_create(const b200mppi_config* cfg, b200mppi_tdm** ou
   b200mppi_tdm* t = new b200mppi_tdm();
   t->cfg = *cfg;
   t->det_dyn = cfg->mode != B200MPPI_MODE_TDM;
-  t->num_maps = t->det_dyn ? 1 : cfg->num_grid_samples;
+  // MODE_TDM with world_size > 1: the M sampled maps are sharded over the ranks (rank r owns maps
+  // [r*M/ws, (r+1)*M/ws)); generator (tid_x, m, tid_y) keeps its GLOBAL index, so the union of the ranks'
+  // maps is bit-identical to a single-rank run
+  const int ws = cfg->world_size < 1 ? 1 : cfg->world_size;
+  if (!t->det_dyn && ws > 1 && cfg->num_grid_samples % ws != 0) {
+    delete t;
+    return fail(B200MPPI_EINVAL, "tdm_create: num_grid_samples must be divisible by world_size");
+  }
+  t->num_maps = t->det_dyn ? 1 : cfg->num_grid_samples / ws;
+  const int m_total = t->det_dyn ? 1 : cfg->num_grid_samples;
+  const int m_begin = t->det_dyn ? 0 : cfg->rank * t->num_maps;
   t->pitch = round_up(cfg->max_map_cols, 16);
   CU(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
   t->own_stream = true;
@@ -172,9 +182,23 @@ extern "C" int b200mppi_tdm_create(const b200mppi_config* cfg, b200mppi_tdm** ou
   CU(cudaMalloc(&t->grid, gbytes));
   CU(cudaMemsetAsync(t->grid, 0, gbytes, t->stream));
   t->num_gen = (int64_t)cfg->tdm_thread_x * cfg->tdm_thread_y * t->num_maps;
-  t->sig = mix_sig(mix_sig(cfg->seed, (uint64_t)t->num_gen), 0x71);
+  t->sig = mix_sig(mix_sig(mix_sig(cfg->seed, (uint64_t)t->num_gen), 0x71), (uint64_t)m_begin);
   std::vector<uint64_t> h((size_t)t->num_gen * 2);
-  create_xoroshiro_states(h.data(), 0, t->num_gen, cfg->seed);
+  {
+    // global generator index tid_x*(ty*M) + m*ty + tid_y (terrain.py:657-658); local storage uses the
+    // same formula with the local map count
+    const int64_t all = (int64_t)cfg->tdm_thread_x * cfg->tdm_thread_y * m_total;
+    std::vector<uint64_t> g((size_t)all * 2);
+    create_xoroshiro_states(g.data(), 0, all, cfg->seed);
+    const int ty = cfg->tdm_thread_y;
+    for (int ix = 0; ix < cfg->tdm_thread_x; ++ix)
+      for (int ml = 0; ml < t->num_maps; ++ml)
+        for (int iy = 0; iy < ty; ++iy) {
+          const int64_t src = (int64_t)ix * ((int64_t)ty * m_total) + (int64_t)(m_begin + ml) * ty + iy;
+          const int64_t dst = (int64_t)ix * ((int64_t)ty * t->num_maps) + (int64_t)ml * ty + iy;
+          h[2 * dst] = g[2 * src]; h[2 * dst + 1] = g[2 * src + 1];
+        }
+  }
   CU(cudaMalloc(&t->states, h.size() * sizeof(uint64_t)));
   CU(cudaMemcpyAsync(t->states, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, t->stream));
   CU(cudaStreamSynchronize(t->stream));
@@ -367,6 +391,11 @@ struct b200mppi_planner {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int n_begin = 0, n_local = 0, T = 0, M = 1;
+  // MODE_TDM with world_size > 1 shards the MAPS: every rank rolls out all N control sequences on its
+  // M/ws maps (n_roll = N), exchanges per-(n,m) costs (all-to-all), and reduces its N/ws slice (n_red)
+  bool shard_maps = false;
+  int M_total = 1, n_roll = 0, n_red = 0, n_red_begin = 0;
+  float* costs_x = nullptr;    // (ws, N/ws, M_local): per-(n,m) costs of this rank's n-slice after the exchange
   float* noise = nullptr; float* u_cur = nullptr; float* u_prev = nullptr;
   float* costs = nullptr; float* weights = nullptr; float* costs_nm = nullptr; float* w_raw = nullptr;
   float* cta_partials = nullptr; float* rank_partial = nullptr; float* state_rollout = nullptr;
@@ -396,7 +425,7 @@ static int planner_check_ready(b200mppi_planner* p) {
     return fail(B200MPPI_EINVAL, "planner: lin/ang TDM shapes differ");
   if (p->lin->mask_rows != p->lin->rows || p->lin->mask_cols != p->lin->cols)
     return fail(B200MPPI_EINVAL, "planner: mask shape differs from padded PMF shape");
-  if (p->cfg.mode == B200MPPI_MODE_TDM && p->M > 1024)
+  if (p->cfg.mode == B200MPPI_MODE_TDM && p->M_total > 1024)
     return fail(B200MPPI_EINVAL, "planner: num_grid_samples > 1024 is not supported (reference's oversized kernel is out of scope)");
   return B200MPPI_OK;
 }
@@ -425,9 +454,11 @@ static void fill_rollout_params(b200mppi_planner* p, RolloutParams& r) {
 }
 
 static void fill_update_args(b200mppi_planner* p, UpdateArgs& u, const float* costs) {
-  u.costs = costs ? costs : p->costs; u.noise = p->noise; u.w_raw = p->w_raw;
+  u.costs = costs ? costs : p->costs;
+  u.noise = p->noise + (size_t)p->n_red_begin * p->T * 2;      // this rank's slice of the control sequences
+  u.w_raw = p->w_raw;
   u.cta_partials = p->cta_partials; u.rank_partial = p->rank_partial; u.u_cur = p->u_cur;
-  u.weights = p->weights; u.N = p->n_local; u.T = p->T; u.num_ctas = p->num_ctas;
+  u.weights = p->weights; u.N = p->n_red; u.T = p->T; u.num_ctas = p->num_ctas;
   u.rows_per_cta = p->rows_per_cta; u.lambda = p->prm.lambda_weight;
   u.vrange[0] = p->prm.vrange[0]; u.vrange[1] = p->prm.vrange[1];
   u.wrange[0] = p->prm.wrange[0]; u.wrange[1] = p->prm.wrange[1];
@@ -447,24 +478,35 @@ extern "C" int b200mppi_planner_create(const b200mppi_config* cfg, b200mppi_plan
   p->n_local = (int)(N * (cfg->rank + 1) / cfg->world_size) - p->n_begin;
   if (p->n_local < 1) { delete p; return fail(B200MPPI_EINVAL, "planner_create: empty shard"); }
   p->T = cfg->num_steps;
-  p->M = cfg->mode == B200MPPI_MODE_TDM ? cfg->num_grid_samples : 1;
+  p->M_total = cfg->mode == B200MPPI_MODE_TDM ? cfg->num_grid_samples : 1;
+  p->shard_maps = cfg->mode == B200MPPI_MODE_TDM && cfg->world_size > 1;
+  if (p->shard_maps && (p->M_total % cfg->world_size != 0 || N % cfg->world_size != 0)) {
+    delete p;
+    return fail(B200MPPI_EINVAL, "planner_create: MODE_TDM sharding needs num_grid_samples and num_control_rollouts divisible by world_size");
+  }
+  p->M = p->shard_maps ? p->M_total / cfg->world_size : p->M_total;
+  p->n_roll = p->shard_maps ? (int)N : p->n_local;          // rollouts simulated by this rank
+  p->n_red = p->n_local;                                    // rollouts reduced (CVaR, softmax) by this rank
+  p->n_red_begin = p->shard_maps ? p->n_begin : 0;          // offset of that slice inside the noise buffer
+  p->n_local = p->n_roll;                                   // buffers below are sized by the simulated count
   CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   p->own_stream = true;
   const size_t nT = (size_t)p->n_local * p->T;
   CU(cudaMalloc(&p->noise, nT * 2 * sizeof(float)));
   CU(cudaMalloc(&p->u_cur, (size_t)p->T * 2 * sizeof(float)));
   CU(cudaMalloc(&p->u_prev, (size_t)p->T * 2 * sizeof(float)));
-  CU(cudaMalloc(&p->costs, (size_t)p->n_local * sizeof(float)));
-  CU(cudaMalloc(&p->weights, (size_t)p->n_local * sizeof(float)));
-  CU(cudaMalloc(&p->w_raw, (size_t)p->n_local * sizeof(float)));
+  CU(cudaMalloc(&p->costs, (size_t)p->n_red * sizeof(float)));
+  CU(cudaMalloc(&p->weights, (size_t)p->n_red * sizeof(float)));
+  CU(cudaMalloc(&p->w_raw, (size_t)p->n_red * sizeof(float)));
   CU(cudaMalloc(&p->costs_nm, (size_t)p->n_local * p->M * sizeof(float)));
+  if (p->shard_maps) CU(cudaMalloc(&p->costs_x, (size_t)p->n_local * p->M * sizeof(float)));
   p->npad = round_up(p->n_local, 32);
   CU(cudaMalloc(&p->noiseT, (size_t)p->T * p->npad * 2 * sizeof(float)));
   CU(cudaMalloc(&p->ctrl, (size_t)p->npad * sizeof(float)));
   p->use_win = getenv("B200MPPI_NO_WINDOW") == nullptr;
-  p->num_ctas = update_num_ctas(p->n_local);
-  p->rows_per_cta = (p->n_local + p->num_ctas - 1) / p->num_ctas;
-  p->num_ctas = (p->n_local + p->rows_per_cta - 1) / p->rows_per_cta;
+  p->num_ctas = update_num_ctas(p->n_red);
+  p->rows_per_cta = (p->n_red + p->num_ctas - 1) / p->num_ctas;
+  p->num_ctas = (p->n_red + p->rows_per_cta - 1) / p->rows_per_cta;
   CU(cudaMalloc(&p->cta_partials, (size_t)p->num_ctas * (2 * p->T + 2) * sizeof(float)));
   CU(cudaMalloc(&p->rank_partial, (size_t)(2 * p->T + 2) * sizeof(float)));
   const int V = cfg->num_vis_state_rollouts < 1 ? 1 : cfg->num_vis_state_rollouts;
@@ -472,13 +514,13 @@ extern "C" int b200mppi_planner_create(const b200mppi_config* cfg, b200mppi_plan
   CU(cudaMemsetAsync(p->noise, 0, nT * 2 * sizeof(float), p->stream));
   CU(cudaMemsetAsync(p->u_cur, 0, (size_t)p->T * 2 * sizeof(float), p->stream));
   CU(cudaMemsetAsync(p->u_prev, 0, (size_t)p->T * 2 * sizeof(float), p->stream));
-  CU(cudaMemsetAsync(p->costs, 0, (size_t)p->n_local * sizeof(float), p->stream));
-  CU(cudaMemsetAsync(p->weights, 0, (size_t)p->n_local * sizeof(float), p->stream));
+  CU(cudaMemsetAsync(p->costs, 0, (size_t)p->n_red * sizeof(float), p->stream));
+  CU(cudaMemsetAsync(p->weights, 0, (size_t)p->n_red * sizeof(float), p->stream));
   CU(cudaMemsetAsync(p->state_rollout, 0, (size_t)V * (p->T + 1) * 3 * sizeof(float), p->stream));
   CU(cudaMallocHost(&p->h_u, (size_t)p->T * 2 * sizeof(float)));
   // generators n_global*T + t of this shard (mppi.py:118,1367)
   std::vector<uint64_t> h(nT * 2);
-  create_xoroshiro_states(h.data(), (int64_t)p->n_begin * p->T, (int64_t)nT, cfg->seed);
+  create_xoroshiro_states(h.data(), p->shard_maps ? 0 : (int64_t)p->n_begin * p->T, (int64_t)nT, cfg->seed);
   CU(cudaMalloc(&p->states, h.size() * sizeof(uint64_t)));
   CU(cudaMemcpyAsync(p->states, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
   for (auto& e : p->ev) CU(cudaEventCreate(&e));
@@ -493,7 +535,7 @@ extern "C" int b200mppi_planner_destroy(b200mppi_planner* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   cudaFree(p->noise); cudaFree(p->u_cur); cudaFree(p->u_prev); cudaFree(p->costs); cudaFree(p->weights);
   cudaFree(p->w_raw); cudaFree(p->costs_nm); cudaFree(p->cta_partials); cudaFree(p->rank_partial);
-  cudaFree(p->state_rollout); cudaFree(p->states); cudaFree(p->noiseT); cudaFree(p->ctrl);
+  cudaFree(p->state_rollout); cudaFree(p->states); cudaFree(p->noiseT); cudaFree(p->ctrl); cudaFree(p->costs_x);
   if (p->h_u) cudaFreeHost(p->h_u);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
@@ -612,8 +654,8 @@ static int stage_rollout(b200mppi_planner* p) {
     CHECK_LAUNCH();
   }
   if (p->profiling) cudaEventRecord(p->ev[3], p->stream);
-  if (p->cfg.mode == B200MPPI_MODE_TDM) {
-    launch_cvar(p->costs_nm, p->costs, p->n_local, p->M, p->prm.cvar_alpha, p->stream);
+  if (p->cfg.mode == B200MPPI_MODE_TDM && !p->shard_maps) {
+    launch_cvar(p->costs_nm, p->costs, p->n_local, p->M, 1, p->prm.cvar_alpha, p->stream);
     p->launches++;
     CHECK_LAUNCH();
   }
@@ -699,8 +741,21 @@ extern "C" int b200mppi_planner_solve_local(b200mppi_planner* p, int32_t first_i
   if (p->profiling) cudaEventRecord(p->ev[2], p->stream);
   if ((rc = stage_rollout(p))) return rc;
   if (p->profiling) cudaEventRecord(p->ev[4], p->stream);
+  if (p->shard_maps) return B200MPPI_OK;                     // costs_nm is the all-to-all send buffer
   if ((rc = stage_update_partial(p, nullptr))) return rc;
   return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_solve_reduce(b200mppi_planner* p, const float* exchanged_dev) {
+  if (!p || !exchanged_dev) return fail(B200MPPI_EINVAL, "solve_reduce: null argument");
+  if (!p->shard_maps) return fail(B200MPPI_ESTATE, "solve_reduce: only for MODE_TDM with world_size > 1");
+  CU(cudaSetDevice(p->cfg.device));
+  // exchanged_dev: (world_size, N/ws, M_local) -- chunk g holds rank g's maps for THIS rank's n-slice
+  launch_cvar(exchanged_dev, p->costs, p->n_red, p->M, p->cfg.world_size, p->prm.cvar_alpha, p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
+  if (p->profiling) cudaEventRecord(p->ev[4], p->stream);
+  return stage_update_partial(p, nullptr);
 }
 
 extern "C" int b200mppi_planner_solve_finish(b200mppi_planner* p, const float* gathered_dev, float* u_out) {
@@ -771,7 +826,8 @@ extern "C" int b200mppi_planner_cvar(b200mppi_planner* p) {
   if (p->cfg.mode != B200MPPI_MODE_TDM) return fail(B200MPPI_ESTATE, "cvar: only MODE_TDM has per-(n,m) costs");
   if (p->M > 1024) return fail(B200MPPI_EINVAL, "cvar: num_grid_samples > 1024");
   CU(cudaSetDevice(p->cfg.device));
-  launch_cvar(p->costs_nm, p->costs, p->n_local, p->M, p->prm.cvar_alpha, p->stream);
+  if (p->shard_maps) return fail(B200MPPI_ESTATE, "cvar: maps are sharded, use solve_reduce");
+  launch_cvar(p->costs_nm, p->costs, p->n_local, p->M, 1, p->prm.cvar_alpha, p->stream);
   p->launches++;
   CHECK_LAUNCH();
   CU(cudaStreamSynchronize(p->stream));
@@ -783,7 +839,7 @@ extern "C" int b200mppi_planner_update(b200mppi_planner* p, const float* costs_h
   if (!p->params_set) return fail(B200MPPI_ESTATE, "update: params not set");
   CU(cudaSetDevice(p->cfg.device));
   if (costs_host)
-    CU(cudaMemcpyAsync(p->costs, costs_host, (size_t)p->n_local * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(p->costs, costs_host, (size_t)p->n_red * sizeof(float), cudaMemcpyHostToDevice, p->stream));
   int rc = stage_update_partial(p, nullptr);
   if (rc) return rc;
   if (p->cfg.world_size == 1 && (rc = stage_update_finish(p, p->rank_partial, 1))) return rc;
@@ -823,8 +879,8 @@ extern "C" int b200mppi_planner_buffer(b200mppi_planner* p, int32_t id, void** p
     case B200MPPI_BUF_NOISE: d = p->noise; b = nl * T * 2 * sizeof(float); break;
     case B200MPPI_BUF_U_CUR: d = p->u_cur; b = T * 2 * sizeof(float); break;
     case B200MPPI_BUF_U_PREV: d = p->u_prev; b = T * 2 * sizeof(float); break;
-    case B200MPPI_BUF_COSTS: d = p->costs; b = nl * sizeof(float); break;
-    case B200MPPI_BUF_WEIGHTS: d = p->weights; b = nl * sizeof(float); break;
+    case B200MPPI_BUF_COSTS: d = p->costs; b = (size_t)p->n_red * sizeof(float); break;
+    case B200MPPI_BUF_WEIGHTS: d = p->weights; b = (size_t)p->n_red * sizeof(float); break;
     case B200MPPI_BUF_COSTS_NM: d = p->costs_nm; b = nl * p->M * sizeof(float); break;
     case B200MPPI_BUF_RNG: d = p->states; b = nl * T * 16; break;
     case B200MPPI_BUF_PARTIAL: d = p->rank_partial; b = (2 * T + 2) * sizeof(float); break;

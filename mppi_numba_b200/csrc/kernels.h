@@ -77,7 +77,10 @@ void rollout_win_geometry(int T, int* WW, int* WH, size_t* smem);
 cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, const void* tm_ang, const void* tm_obs,
                                const void* tm_unk, cudaStream_t st);
 // CVaR over M (mppi.py:718-755): costs[n] = mean of the ceil(M*alpha) largest of costs_nm[n,:]
-void launch_cvar(const float* costs_nm, float* costs, int N, int M, float cvar_alpha,
+// costs_nm is laid out as `chunks` blocks of (N, M): value j of rollout n lives in block j / M at
+// (n, j % M) -- chunks = 1 is the plain (N, M) buffer; chunks = world_size is the all-to-all result of a
+// map-sharded solve (block g = rank g's maps).  The CVaR is over all chunks*M values.
+void launch_cvar(const float* costs_nm, float* costs, int N, int M, int chunks, float cvar_alpha,
                  cudaStream_t st);
 
 // update_useq_numba (mppi.py:1113-1191) as an online-softmax two-level reduction

@@ -167,17 +167,19 @@ __device__ __forceinline__ float key_float(uint32_t k) {   // inverse of float_k
 constexpr int CVAR_MAX_PER_LANE = 32;   // M <= 1024 (the reference's one-block limit, mppi.py:199)
 
 __global__ void __launch_bounds__(128) cvar_kernel(const float* __restrict__ costs_nm,
-                                                   float* __restrict__ costs, int N, int M, int numel) {
+                                                   float* __restrict__ costs, int N, int Mc, int chunks, int numel) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= N) return;
-  const float* row = costs_nm + (size_t)warp * M;
+  const int M = Mc * chunks;                                  // values per control sequence
+  const size_t chunk_stride = (size_t)N * Mc;
+  const float* row = costs_nm + (size_t)warp * Mc;
   float v[CVAR_MAX_PER_LANE];
   const int per = (M + 31) >> 5;
 #pragma unroll
   for (int i = 0; i < CVAR_MAX_PER_LANE; ++i) {
     const int j = i * 32 + lane;
-    v[i] = (i < per && j < M) ? row[j] : -INFINITY;
+    v[i] = (i < per && j < M) ? row[(size_t)(j / Mc) * chunk_stride + (j % Mc)] : -INFINITY;
   }
   float sum = 0.0f;
   if (numel >= M) {
@@ -210,13 +212,14 @@ __global__ void __launch_bounds__(128) cvar_kernel(const float* __restrict__ cos
   if (lane == 0) costs[warp] = (float)((double)sum / (double)numel);
 }
 
-void launch_cvar(const float* costs_nm, float* costs, int N, int M, float cvar_alpha, cudaStream_t st) {
+void launch_cvar(const float* costs_nm, float* costs, int N, int Mc, int chunks, float cvar_alpha, cudaStream_t st) {
+  const int M = Mc * chunks;
   int numel = (int)ceil((double)M * (double)cvar_alpha);    // mppi.py:744 (float32 alpha, f64 product)
   if (numel < 1) numel = 1;
   if (numel > M) numel = M;
   const int threads = 128;
   const int warps_per_block = threads / 32;
-  cvar_kernel<<<(N + warps_per_block - 1) / warps_per_block, threads, 0, st>>>(costs_nm, costs, N, M, numel);
+  cvar_kernel<<<(N + warps_per_block - 1) / warps_per_block, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -8,10 +8,11 @@ What a reference user keeps: ``MPPI_Numba(cfg)``, ``reset()``, ``setup(params, l
 ``noise_samples_d, u_cur_d, u_prev_d, costs_d, weights_d, rng_states_d, state_rollout_batch_d``
 (objects with ``.shape`` / ``.copy_to_host()``).
 
-What is new: the N control sequences can be sharded over ranks (one process per GPU,
-``torch.distributed``): every rank rolls out its slice on all M maps, and the only exchange per
-optimisation iteration is one all-gather of 2T+2 floats (softmax baseline, weight sum,
-weighted-noise sums).  ``costs_d`` is NOT clobbered by the update (the reference reuses it as
+What is new: the work can be sharded over ranks (one process per GPU, ``torch.distributed``).
+``use_tdm``: the M sampled MAPS are sharded -- each rank samples its M/G maps (bit-identical to the same
+maps of a 1-rank run), rolls out all N control sequences on them, an all-to-all hands every rank the
+per-(n,m) costs of its N/G slice for the CVaR, and one all-gather of 2T+2 floats (softmax baseline,
+weight sum, weighted-noise sums) joins the update.  One-map modes shard N and need only the all-gather.  ``costs_d`` is NOT clobbered by the update (the reference reuses it as
 scratch).
 """
 import copy
@@ -102,14 +103,22 @@ class MPPI_Numba(object):
         self._handle = h
         N = self.num_control_rollouts
         self.n_begin = N * self.rank // self.world_size
-        self.n_local = N * (self.rank + 1) // self.world_size - self.n_begin
+        n_slice = N * (self.rank + 1) // self.world_size - self.n_begin
         T, M = self.num_steps, (self.num_grid_samples if self.use_tdm else 1)
+        # use_tdm with several ranks shards the MAPS: every rank simulates all N control sequences on its
+        # M/ws maps and reduces (CVaR, softmax) its N/ws slice; the one-map modes shard N instead.
+        self.shard_maps = bool(self.use_tdm and self.world_size > 1)
+        self.n_local = N if self.shard_maps else n_slice          # rows of noise / per-(n,m) costs
+        self.n_reduce = n_slice                                   # rows of costs_d / weights_d
+        if self.shard_maps:
+            M //= self.world_size
+        self.m_local = M
         self.noise_samples_d = self._buffer(_lib.BUF_NOISE, (self.n_local, T, 2), np.float32)
         self.u_cur_d = self._buffer(_lib.BUF_U_CUR, (T, 2), np.float32)
         self._u_prev_buf = self._buffer(_lib.BUF_U_PREV, (T, 2), np.float32)
         self.u_prev_d = self._u_prev_buf
-        self.costs_d = self._buffer(_lib.BUF_COSTS, (self.n_local,), np.float32)
-        self.weights_d = self._buffer(_lib.BUF_WEIGHTS, (self.n_local,), np.float32)
+        self.costs_d = self._buffer(_lib.BUF_COSTS, (self.n_reduce,), np.float32)
+        self.weights_d = self._buffer(_lib.BUF_WEIGHTS, (self.n_reduce,), np.float32)
         self.costs_nm_d = self._buffer(_lib.BUF_COSTS_NM, (self.n_local, M), np.float32)
         self.rng_states_d = self._buffer(_lib.BUF_RNG, (self.n_local * T, 2), np.uint64)
         self.partial_d = self._buffer(_lib.BUF_PARTIAL, (2 * T + 2,), np.float32, writable=False)
@@ -241,6 +250,9 @@ class MPPI_Numba(object):
             check(lib.b200mppi_tdm_set_stream(tdm._handle, C.c_void_p(self._stream.cuda_stream)))
         self._partial_t = torch.as_tensor(self.partial_d, device=dev)          # zero-copy view
         self._gathered = torch.empty((self.world_size * (2 * self.num_steps + 2),), dtype=torch.float32, device=dev)
+        if self.shard_maps:
+            self._costs_send = torch.as_tensor(self.costs_nm_d, device=dev).reshape(-1)   # (N, M/ws), zero-copy
+            self._costs_recv = torch.empty_like(self._costs_send)                         # (ws, N/ws, M/ws)
 
     def _solve_sharded(self, u_out):
         import torch
@@ -250,6 +262,11 @@ class MPPI_Numba(object):
         with torch.cuda.stream(self._stream):
             for k in range(num_opt):
                 check(lib.b200mppi_planner_solve_local(self._handle, 1 if k == 0 else 0))
+                if self.shard_maps:
+                    # exchange 1: per-(n,m) costs, rank d receives rows [d*N/ws, (d+1)*N/ws) of every rank
+                    dist.all_to_all_single(self._costs_recv, self._costs_send, group=self.process_group)
+                    check(lib.b200mppi_planner_solve_reduce(self._handle, C.c_void_p(self._costs_recv.data_ptr())))
+                # exchange 2: the (2T+2)-float softmax partial of every rank
                 dist.all_gather_into_tensor(self._gathered, self._partial_t, group=self.process_group)
                 last = k == num_opt - 1
                 check(lib.b200mppi_planner_solve_finish(

@@ -37,8 +37,11 @@ class TDM_Numba(object):
     Workflow (unchanged): construct with a ``Config`` -> ``reset()`` -> one of the two setters ->
     hand the object to ``MPPI_Numba.setup`` -> repeat from ``reset()`` when the map changes."""
 
-    def __init__(self, cfg, device=0):
+    def __init__(self, cfg, device=0, rank=0, world_size=1):
+        """``rank`` / ``world_size``: with ``use_tdm`` and more than one rank the M sampled maps are sharded
+        (this object holds maps [rank*M/ws, (rank+1)*M/ws), bit-identical to the same maps of a 1-rank run)."""
         self.cfg = cfg
+        self.rank, self.world_size = int(rank), int(world_size)
         for name in ("T", "dt", "num_steps", "num_grid_samples", "num_control_rollouts",
                      "max_speed_padding", "tdm_sample_thread_dim", "num_vis_state_rollouts",
                      "max_map_dim", "seed", "use_tdm", "use_det_dynamics",
@@ -99,11 +102,12 @@ class TDM_Numba(object):
                              num_grid_samples=self.num_grid_samples, max_map_rows=rows, max_map_cols=cols,
                              tdm_thread_x=self.thread_dim[0], tdm_thread_y=self.thread_dim[1],
                              num_vis_state_rollouts=self.num_vis_state_rollouts, mode=self.cfg.mode,
-                             device=self.device, rank=0, world_size=1, seed=int(self.seed) & (2 ** 64 - 1))
+                             device=self.device, rank=self.rank, world_size=self.world_size,
+                             seed=int(self.seed) & (2 ** 64 - 1))
         h = C.c_void_p()
         check(lib.b200mppi_tdm_create(C.byref(pod), C.byref(h)))
         self._handle = h
-        maps = 1 if self.det_dyn else self.num_grid_samples
+        maps = 1 if self.det_dyn else self.num_grid_samples // self.world_size
         base, pitch = C.c_void_p(), C.c_int32()
         check(lib.b200mppi_tdm_sample_grid_view(h, C.byref(base), C.byref(pitch)))
         self.sample_grid_batch_d = DeviceArray(

@@ -449,6 +449,56 @@ def test_update_sharded_equals_single(eng):
             rp.close()
 
 
+def test_map_sharded_solve_equals_single_rank(eng):
+    """MODE_TDM on 2 'ranks' (both on this GPU, the all-to-all / all-gather done by hand): each rank's
+    sampled maps are bit-identical to its slice of the single-rank maps, its CVaR costs are bit-identical
+    to the single-rank costs of its control sequences, and every rank ends with the single-rank u."""
+    import torch
+    L = eng._lib
+    ws = 2
+    sc = make_scenario("tdm", N=256, M=16, T=32, H=120, W=120, res=0.2, B=8, seed=10, warm_start=True)
+
+    def build(rank, world):
+        cfg = eng.Config(**sc["cfg"])
+        lin = eng.TDM_Numba(cfg, rank=rank, world_size=world)
+        ang = eng.TDM_Numba(cfg, rank=rank, world_size=world)
+        lin.set_TDM_from_PMF_grid(sc["pmf_lin"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+        ang.set_TDM_from_PMF_grid(sc["pmf_ang"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+        pl = eng.MPPI_Numba(cfg, rank=rank, world_size=world)
+        pl.setup(sc["params"], lin, ang)
+        pl.u_cur_d.copy_to_device(sc["u0"])
+        pl.move_mppi_task_vars_to_device()
+        return pl, lin, ang
+    single, slin, sang = build(0, 1)
+    u_single = single.solve()
+    maps_single = slin.sample_grid_batch_d.copy_to_host()
+    costs_single = single.costs_d.copy_to_host()
+    ranks = [build(r, ws) for r in range(ws)]
+    N, M = sc["N"], sc["M"]
+    sends = []
+    for r, (pl, lin, ang) in enumerate(ranks):
+        assert lin.sample_grid_batch_d.shape[0] == M // ws and pl.costs_nm_d.shape == (N, M // ws)
+        L.check(L.lib.b200mppi_planner_solve_local(pl._handle, 1))
+        L.check(L.lib.b200mppi_planner_synchronize(pl._handle))
+        assert (lin.sample_grid_batch_d.copy_to_host() == maps_single[r * M // ws:(r + 1) * M // ws]).all()
+        assert (pl.noise_samples_d.copy_to_host() == single.noise_samples_d.copy_to_host()).all()
+        sends.append(pl.costs_nm_d.copy_to_host())
+    parts, keep = [], []
+    for d, (pl, lin, ang) in enumerate(ranks):
+        recv = np.ascontiguousarray(np.stack([sends[g][d * N // ws:(d + 1) * N // ws] for g in range(ws)]))
+        t = torch.from_numpy(recv).cuda()
+        keep.append(t)
+        L.check(L.lib.b200mppi_planner_solve_reduce(pl._handle, C.c_void_p(t.data_ptr())))
+        L.check(L.lib.b200mppi_planner_synchronize(pl._handle))
+        assert (pl.costs_d.copy_to_host() == costs_single[d * N // ws:(d + 1) * N // ws]).all()
+        parts.append(pl.partial_d.copy_to_host())
+    gathered = torch.from_numpy(np.ascontiguousarray(np.stack(parts))).cuda()
+    for pl, lin, ang in ranks:
+        u = np.empty_like(u_single)
+        L.check(L.lib.b200mppi_planner_solve_finish(pl._handle, C.c_void_p(gathered.data_ptr()), L.ptr(u)))
+        np.testing.assert_allclose(u, u_single, rtol=1e-5, atol=2e-6)
+
+
 # ----------------------------------------------------------------------------- 5. whole solve through the public API
 @pytest.mark.parametrize("mode", ["tdm", "det", "spd"])
 def test_solve_vs_reference_golden(eng, golden_dir, mode):
