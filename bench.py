@@ -220,7 +220,7 @@ def run_reference(args, sc):
            "cpu_baseline": {"value": v, "unit": "state-steps/s", "cores": cores, "kind": "port", "sample": desc},
            "e2e": {"value": v, "unit": "state-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
 
 
 def workload_name(args, sc):
@@ -361,10 +361,13 @@ def run_b200(args, sc):
         v, cores, desc, _ = run_cpu_baseline(sc, n_s, m_s)
         out["cpu_baseline"] = {"value": v, "unit": "state-steps/s", "cores": cores, "kind": "port", "sample": desc}
     if rank == 0:
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+_emit = print
 
 
 def lin_launches(tdm):
@@ -372,6 +375,16 @@ def lin_launches(tdm):
 
 
 def main():
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, the engine's allocation
+    # notices) also write to fd 1, so everything is routed to stderr and only the final line goes to the
+    # real stdout.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
+    global _emit
+
+    def _emit(line):
+        os.write(real_stdout, (line + "\n").encode())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

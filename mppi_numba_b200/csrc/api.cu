@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200mppi.h"
@@ -43,7 +44,10 @@ struct b200mppi_tdm {
   int num_maps = 1;           // M or 1
   int pitch = 0;              // bytes per sample-grid row
   int8_t* grid = nullptr;     // (num_maps, Rmax, pitch)
-  uint64_t* states = nullptr; // (num_gen, 2)
+  uint64_t* states = nullptr; // (num_gen, 2)  current generator states
+  uint64_t* states_alt = nullptr;   // double buffer for the segmented sampler
+  uint64_t* jump_d = nullptr;       // jump-ahead matrices of the current tile geometry
+  int jump_segs = 0, jump_seg_rows = 0, jump_rows = 0, jump_cols = 0;
   int64_t num_gen = 0;
   // map
   bool pmf_set = false, masks_set = false, risk_set = false;
@@ -92,13 +96,51 @@ static void tdm_advance_sig(b200mppi_tdm* t) {
   t->sig = mix_sig(mix_sig(t->sig, ((uint64_t)t->rows << 32) | (uint32_t)t->cols), 0x5a);
 }
 
+// Row segments per generator tile: enough CTAs to fill the GPU (the stream of a generator is sequential,
+// so parallelism beyond M*tx*ty generators comes from GF(2) jump-ahead), at most 8.
+static int tdm_prepare_jump(b200mppi_tdm* t, cudaStream_t st) {
+  const int tx = t->cfg.tdm_thread_x, ty = t->cfg.tdm_thread_y;
+  const int nrow = (t->rows + tx - 1) / tx, ncol = (t->cols + ty - 1) / ty;
+  const int groups = (t->num_maps + 7) / 8;
+  int segs = (4 * 148 + tx * groups - 1) / (tx * groups);
+  if (const char* e = getenv("B200MPPI_SAMPLE_SEGS")) segs = atoi(e);      // tuning / test hook
+  if (segs > 8) segs = 8;
+  if (segs > nrow) segs = nrow;
+  if (segs < 1) segs = 1;
+  const int seg_rows = (nrow + segs - 1) / segs;
+  if (t->jump_d && t->jump_segs == segs && t->jump_seg_rows == seg_rows && t->jump_rows == t->rows &&
+      t->jump_cols == t->cols)
+    return B200MPPI_OK;
+  if (!t->jump_d) CU(cudaMalloc(&t->jump_d, (size_t)7 * 2 * 256 * sizeof(uint64_t)));
+  if (segs > 1) {
+    // width classes: 0 = full tile column (ncol cells), 1 = the last, narrower column
+    int last_w = t->cols - (ty - 1) * ncol;
+    for (int iy = ty - 1; iy >= 0 && last_w <= 0; --iy) last_w = t->cols - iy * ncol;   // first non-empty from the right
+    if (last_w > ncol) last_w = ncol;
+    if (last_w < 0) last_w = 0;
+    std::vector<int64_t> ks;
+    for (int sgm = 1; sgm < segs; ++sgm) {
+      ks.push_back((int64_t)sgm * seg_rows * ncol);
+      ks.push_back((int64_t)sgm * seg_rows * last_w);
+    }
+    std::vector<uint64_t> h(ks.size() * 256);
+    build_jump_matrices(ks.data(), (int)ks.size(), h.data());
+    CU(cudaMemcpyAsync(t->jump_d, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));            // h is a temporary
+  }
+  t->jump_segs = segs; t->jump_seg_rows = seg_rows; t->jump_rows = t->rows; t->jump_cols = t->cols;
+  return B200MPPI_OK;
+}
+
 static void fill_v2(const b200mppi_tdm* t, SampleGridsV2Args& a, int slot) {
   a.t[slot].grid = t->grid; a.t[slot].cum = t->cum; a.t[slot].states = t->states;
+  a.t[slot].states_out = t->states_alt;
   a.t[slot].qvals = t->qvals; a.t[slot].bpad = t->bpad;
   if (slot == 0) {
-    a.thresholds = t->thr_d; a.est_mul = t->est_mul;
+    a.thresholds = t->thr_d; a.est_mul = t->est_mul; a.jump = t->jump_d;
     a.rows = t->rows; a.cols = t->cols; a.grid_rows = t->cfg.max_map_rows; a.pitch = t->pitch;
     a.tx = t->cfg.tdm_thread_x; a.ty = t->cfg.tdm_thread_y; a.num_maps = t->num_maps;
+    a.segs = t->jump_segs; a.seg_rows = t->jump_seg_rows;
   }
 }
 
@@ -107,10 +149,12 @@ static int tdm_sample_on(b200mppi_tdm* t, double alpha_dyn, cudaStream_t st) {
   if (!t->pmf_set) return fail(B200MPPI_ESTATE, "sample_grids: PMF grid not set");
   int rc = tdm_prepare_thresholds(t, alpha_dyn, st);
   if (rc) return rc;
+  if ((rc = tdm_prepare_jump(t, st))) return rc;
   SampleGridsV2Args v2{};
   fill_v2(t, v2, 0);
   if (t->thr_ok && sample_grids_v2_fits(v2, 1)) {
     launch_sample_grids_v2(v2, 1, st);
+    std::swap(t->states, t->states_alt);       // the kernel wrote the advanced states to the other buffer
   } else {
     SampleGridsArgs a{};
     a.grid = t->grid; a.cum = t->cum; a.states = t->states; a.qvals = t->qvals;
@@ -137,11 +181,14 @@ static int tdm_sample_pair_on(b200mppi_tdm* l, b200mppi_tdm* g, double alpha_dyn
                            l->num_maps == g->num_maps && l->pitch == g->pitch &&
                            l->cfg.tdm_thread_x == g->cfg.tdm_thread_x && l->cfg.tdm_thread_y == g->cfg.tdm_thread_y &&
                            l->cfg.max_map_rows == g->cfg.max_map_rows;
+  if ((rc = tdm_prepare_jump(l, st))) return rc;
   SampleGridsV2Args v2{};
   fill_v2(l, v2, 0);
   fill_v2(g, v2, 1);
   if (same_stream && l->thr_ok && g->thr_ok && sample_grids_v2_fits(v2, 2)) {
     launch_sample_grids_v2(v2, 2, st);
+    std::swap(l->states, l->states_alt);
+    std::swap(g->states, g->states_alt);
     tdm_advance_sig(l);
     tdm_advance_sig(g);
     *launches += 1;
@@ -200,6 +247,7 @@ extern "C" int b200mppi_tdm_create(const b200mppi_config* cfg, b200mppi_tdm** ou
         }
   }
   CU(cudaMalloc(&t->states, h.size() * sizeof(uint64_t)));
+  CU(cudaMalloc(&t->states_alt, h.size() * sizeof(uint64_t)));
   CU(cudaMemcpyAsync(t->states, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, t->stream));
   CU(cudaStreamSynchronize(t->stream));
   *out = t;
@@ -210,7 +258,7 @@ extern "C" int b200mppi_tdm_destroy(b200mppi_tdm* t) {
   if (!t) return B200MPPI_OK;
   cudaSetDevice(t->cfg.device);
   cudaFree(t->grid); cudaFree(t->states); cudaFree(t->pmf); cudaFree(t->cum); cudaFree(t->qvals);
-  cudaFree(t->obstacle); cudaFree(t->unknown); cudaFree(t->risk); cudaFree(t->thr_d);
+  cudaFree(t->obstacle); cudaFree(t->unknown); cudaFree(t->risk); cudaFree(t->thr_d); cudaFree(t->states_alt); cudaFree(t->jump_d);
   if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
   delete t;
   return B200MPPI_OK;

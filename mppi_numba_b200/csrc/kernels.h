@@ -23,14 +23,17 @@ struct SampleGridsArgs {
 void launch_sample_grids(const SampleGridsArgs& a, cudaStream_t st);
 // v2 (staged, integer-threshold, optionally lin+ang fused) sampler -- see sample.cu
 struct SampleTdm {
-  int8_t* grid; const int8_t* cum; uint64_t* states; const int8_t* qvals; int bpad;
+  int8_t* grid; const int8_t* cum; const uint64_t* states; uint64_t* states_out; const int8_t* qvals; int bpad;
 };
 struct SampleGridsV2Args {
   SampleTdm t[2];
   const uint64_t* thresholds;   // device, 136 entries
+  const uint64_t* jump;         // device, [(segs-1)*2][128][2]: A^(s*seg_rows*width) for width class 0 / 1
   uint32_t est_mul;
   int rows, cols, grid_rows, pitch, tx, ty, num_maps;
+  int segs, seg_rows;           // row segments per generator tile (jump-ahead split), rows per segment
 };
+void build_jump_matrices(const int64_t* ks, int count, uint64_t* out);
 bool build_sample_thresholds(double alpha, int q_cap, uint64_t* T, uint32_t* est_mul);
 bool sample_grids_v2_fits(const SampleGridsV2Args& a, int nt);
 void launch_sample_grids_v2(const SampleGridsV2Args& a, int nt, cudaStream_t st);

@@ -9,6 +9,7 @@
 // once per set_pmf (cell-major, so one cell's bins are contiguous) instead of re-summing B strided
 // int8 loads per cell per map as the reference does.
 #include <cmath>
+#include <cstring>
 #include "kernels.h"
 
 namespace b200 {
@@ -94,6 +95,25 @@ void launch_sample_grids(const SampleGridsArgs& a, cudaStream_t st) {
 //     streams are identical): the draw and the threshold are shared.
 constexpr int SG_GM = 8;          // maps per CTA
 
+// GF(2) jump-ahead: the xoroshiro128+ transition is linear, so advancing a state by K draws is a
+// 128x128 bit-matrix product.  `mat` holds the 128 columns (2 x u64 each) of A^K.
+__device__ __forceinline__ void xoro_jump(Xoro& s, const ulonglong2* __restrict__ mat) {
+  uint64_t a0 = 0, a1 = 0;
+#pragma unroll 4
+  for (int j = 0; j < 64; ++j) {
+    const ulonglong2 c = __ldg(mat + j);
+    const uint64_t mk = 0ULL - ((s.s0 >> j) & 1ULL);
+    a0 ^= c.x & mk; a1 ^= c.y & mk;
+  }
+#pragma unroll 4
+  for (int j = 0; j < 64; ++j) {
+    const ulonglong2 c = __ldg(mat + 64 + j);
+    const uint64_t mk = 0ULL - ((s.s1 >> j) & 1ULL);
+    a0 ^= c.x & mk; a1 ^= c.y & mk;
+  }
+  s.s0 = a0; s.s1 = a1;
+}
+
 template <int NT, int NW>
 __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const SampleGridsV2Args a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -109,7 +129,7 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int tiy = tid % a.ty, mloc = tid / a.ty;
-  const int tix = blockIdx.x;
+  const int tix = blockIdx.x / a.segs, seg = blockIdx.x % a.segs;
   const int m = blockIdx.y * SG_GM + mloc;
   const bool active = (mloc < SG_GM) && (m < a.num_maps);
 
@@ -130,14 +150,24 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
 
   const int ncol = (a.cols + a.ty - 1) / a.ty;
   const int nrow = (a.rows + a.tx - 1) / a.tx;
-  const int r0 = min(tix * nrow, a.rows), r1 = min(r0 + nrow, a.rows);
+  const int t0 = min(tix * nrow, a.rows), t1 = min(t0 + nrow, a.rows);          // the generator's tile rows
   const int c0 = min(tiy * ncol, a.cols), c1 = min(c0 + ncol, a.cols);
+  // this CTA's row segment of the tile.  A generator's stream is split into `segs` consecutive row
+  // segments handled by different CTAs: segment `seg` starts from the state jumped ahead by
+  // seg*seg_rows*(c1-c0) draws (GF(2) matrix), so the union of the segments is the reference's stream.
+  const int r0 = min(t0 + seg * a.seg_rows, t1), r1 = min(r0 + a.seg_rows, t1);
+  const int wc = c1 - c0;
+  const int last_seg = (t1 > t0 && wc > 0) ? (t1 - t0 - 1) / a.seg_rows : 0;     // owner of the final state
 
   const int64_t gen = (int64_t)tix * ((int64_t)a.ty * a.num_maps) + (int64_t)m * a.ty + tiy;
   Xoro s{0, 0};
   if (active) {
     const ulonglong2 raw = reinterpret_cast<const ulonglong2*>(a.t[0].states)[gen];
     s.s0 = raw.x; s.s1 = raw.y;
+    if (seg > 0 && r1 > r0 && wc > 0) {
+      const int cls = (wc == ncol) ? 0 : 1;                 // full-width tile column or the narrower last one
+      xoro_jump(s, reinterpret_cast<const ulonglong2*>(a.jump) + ((size_t)(seg - 1) * 2 + cls) * 128);
+    }
   }
   const uint32_t c32 = a.est_mul;
 
@@ -226,10 +256,11 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
       }
     }
   }
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < NT; ++k)
-      reinterpret_cast<ulonglong2*>(a.t[k].states)[gen] = make_ulonglong2(s.s0, s.s1);
+  // states are double-buffered (another segment of the same generator may still have to read the old
+  // state): exactly one segment per generator writes the new state
+  if (active && seg == last_seg) {
+    reinterpret_cast<ulonglong2*>(a.t[0].states_out)[gen] = make_ulonglong2(s.s0, s.s1);
+    if (NT == 2) reinterpret_cast<ulonglong2*>(a.t[1].states_out)[gen] = make_ulonglong2(s.s0, s.s1);
   }
 }
 
@@ -241,7 +272,7 @@ size_t sample_grids_v2_smem(const SampleGridsV2Args& a, int nt) {
 
 template <int NT>
 static void launch_v2_nt(const SampleGridsV2Args& a, cudaStream_t st) {
-  const dim3 grid(a.tx, (a.num_maps + SG_GM - 1) / SG_GM);
+  const dim3 grid(a.tx * a.segs, (a.num_maps + SG_GM - 1) / SG_GM);
   const int threads = ((a.ty * SG_GM + 31) / 32) * 32;
   const size_t smem = sample_grids_v2_smem(a, NT);
   const int nw = a.t[0].bpad / 4;
@@ -262,6 +293,46 @@ bool sample_grids_v2_fits(const SampleGridsV2Args& a, int nt) {
 
 void launch_sample_grids_v2(const SampleGridsV2Args& a, int nt, cudaStream_t st) {
   if (nt == 2) launch_v2_nt<2>(a, st); else launch_v2_nt<1>(a, st);
+}
+
+static inline void next_h(uint64_t& s0, uint64_t& s1);
+
+// ---------------------------------------------------------------------------------------------
+// Host: GF(2) transition matrices of xoroshiro128+ (columns as 2 x u64), A^K by square-and-multiply.
+struct Gf2Mat { uint64_t c[128][2]; };
+
+static void gf2_apply(const Gf2Mat& m, const uint64_t v[2], uint64_t out[2]) {
+  uint64_t a0 = 0, a1 = 0;
+  for (int w = 0; w < 2; ++w)
+    for (int j = 0; j < 64; ++j)
+      if ((v[w] >> j) & 1ULL) { a0 ^= m.c[64 * w + j][0]; a1 ^= m.c[64 * w + j][1]; }
+  out[0] = a0; out[1] = a1;
+}
+static void gf2_mul(const Gf2Mat& a, const Gf2Mat& b, Gf2Mat& out) {      // out = a * b (apply b, then a)
+  for (int j = 0; j < 128; ++j) gf2_apply(a, b.c[j], out.c[j]);
+}
+static void gf2_step_matrix(Gf2Mat& m) {
+  for (int j = 0; j < 128; ++j) {
+    uint64_t s0 = j < 64 ? (1ULL << j) : 0, s1 = j >= 64 ? (1ULL << (j - 64)) : 0;
+    next_h(s0, s1);
+    m.c[j][0] = s0; m.c[j][1] = s1;
+  }
+}
+// out: [count][128][2] u64, matrix i advances a state by ks[i] draws
+void build_jump_matrices(const int64_t* ks, int count, uint64_t* out) {
+  Gf2Mat step;
+  gf2_step_matrix(step);
+  for (int i = 0; i < count; ++i) {
+    Gf2Mat acc, base = step, tmp;
+    for (int j = 0; j < 128; ++j) {                      // identity
+      acc.c[j][0] = j < 64 ? (1ULL << j) : 0; acc.c[j][1] = j >= 64 ? (1ULL << (j - 64)) : 0;
+    }
+    for (uint64_t k = (uint64_t)ks[i]; k; k >>= 1) {
+      if (k & 1ULL) { gf2_mul(base, acc, tmp); acc = tmp; }
+      gf2_mul(base, base, tmp); base = tmp;
+    }
+    std::memcpy(out + (size_t)i * 256, acc.c, sizeof(acc.c));
+  }
 }
 
 // Host: breakpoints of q(v) = int8(ceil(f64(f32(v * 2^-53)) * 100.0 * alpha)) (terrain.py:682-683 as
