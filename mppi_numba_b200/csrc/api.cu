@@ -102,7 +102,7 @@ static int tdm_prepare_jump(b200mppi_tdm* t, cudaStream_t st) {
   const int tx = t->cfg.tdm_thread_x, ty = t->cfg.tdm_thread_y;
   const int nrow = (t->rows + tx - 1) / tx, ncol = (t->cols + ty - 1) / ty;
   const int groups = (t->num_maps + 7) / 8;
-  int segs = (4 * 148 + tx * groups - 1) / (tx * groups);
+  int segs = (4096 + tx * groups - 1) / (tx * groups);      // ~4k CTAs keep 148 SMs busy through the tail
   if (const char* e = getenv("B200MPPI_SAMPLE_SEGS")) segs = atoi(e);      // tuning / test hook
   if (segs > 8) segs = 8;
   if (segs > nrow) segs = nrow;
