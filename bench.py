@@ -230,10 +230,16 @@ def workload_name(args, sc):
 
 
 def run_b200(args, sc):
-    import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        # CPU baseline FIRST: it forks worker processes, which must happen before CUDA is initialised
+        n_s, m_s = (4096, 64) if sc["mode"] == "tdm" else (min(sc["N"], 4096), 1)
+        v, cores, desc, _ = run_cpu_baseline(sc, n_s, m_s)
+        cpu_base = {"value": v, "unit": "state-steps/s", "cores": cores, "kind": "port", "sample": desc}
+    import torch
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run" % (args.gpus, world))
     import __graft_entry__
@@ -364,10 +370,8 @@ def run_b200(args, sc):
                        "h2d_bytes_per_step": 8 * T + 88, "d2h_bytes_per_step": 8 * T},
                "gpu_launches": int(launches),
                "roofline": roofline}
-    if rank == 0 and world == 1 and not args.no_cpu:
-        n_s, m_s = (4096, 64) if sc["mode"] == "tdm" else (min(sc["N"], 4096), 1)
-        v, cores, desc, _ = run_cpu_baseline(sc, n_s, m_s)
-        out["cpu_baseline"] = {"value": v, "unit": "state-steps/s", "cores": cores, "kind": "port", "sample": desc}
+    if cpu_base is not None:
+        out["cpu_baseline"] = cpu_base
     if rank == 0:
         _emit(json.dumps(out))
     if world > 1:

@@ -49,6 +49,52 @@ def base_params(x0, xgoal, cvar_alpha=0.5):
                 obs_penalty=1e5, unknown_penalty=1e2)
 
 
+class _T(object):
+    """Stand-in for the reference's Terrain objects: the setter only uses them as dictionary keys."""
+    def __init__(self, name):
+        self.name = name
+
+
+def semantic_inputs():
+    rng = np.random.default_rng(23)
+    H, W, B = 9, 7, 6
+    sg = rng.integers(0, 3, (H, W))
+    bin_values = np.linspace(0.0, 1.0, B)               # float64 on purpose (the reference uploads it uncast)
+    names = {0: "grass", 1: "mud", 2: "road"}
+    pmfs = {"grass": np.array([0.05, 0.1, 0.2, 0.4, 0.2, 0.05]), "mud": np.array([0.3, 0.3, 0.2, 0.1, 0.1, 0.0]),
+            "road": np.array([0.0, 0.0, 0.02, 0.08, 0.3, 0.6])}
+    obstacle = (rng.random((H, W)) < 0.1).astype(np.int8)
+    unknown = (rng.random((H, W)) < 0.1).astype(np.int8)
+    return sg, bin_values, names, pmfs, obstacle, unknown
+
+
+def make_semantic_golden(Config, TDM_Numba):
+    sg, bin_values, names, pmfs, obstacle, unknown = semantic_inputs()
+    terr = {n: _T(n) for n in names.values()}
+    t2p = {terr[n]: (bin_values, pmfs[n]) for n in terr}
+    out = dict(sg=sg, bin_values=bin_values, obstacle=obstacle, unknown=unknown)
+    for mode, flags, alphas in (("tdm", dict(use_tdm=True), (None,)), ("det", dict(use_det_dynamics=True), (0.3, 1.0)),
+                                ("spd", dict(use_nom_dynamics_with_speed_map=True), (0.3, 1.0))):
+        for alpha in alphas:
+            cfg = _quiet(Config, T=1.0, dt=0.1, num_grid_samples=2, num_control_rollouts=100, seed=1,
+                         max_map_dim=(14, 12), tdm_sample_thread_dim=(3, 2), max_speed_padding=5.0, **flags)
+            tdm = _quiet(TDM_Numba, cfg)
+            _quiet(tdm.set_TDM_from_semantic_grid, sg, 0.5, len(bin_values), bin_values, np.array([0.0, 1.0]),
+                   np.array([0.0, 3.5]), np.array([0.0, 4.5]), names, terr, t2p, det_dynamics_cvar_alpha=alpha,
+                   obstacle_map=obstacle, unknown_map=unknown)
+            key = "%s_%s" % (mode, "none" if alpha is None else "a%02d" % int(alpha * 10))
+            out[key + "_pmf_padded"] = tdm.pmf_grid_d.copy_to_host()
+            out[key + "_semantic_cropped"] = np.asarray(tdm.semantic_grid)
+            if mode == "spd":
+                out[key + "_risk"] = tdm.risk_traction_map_d.copy_to_host()
+            # sampled maps: float64 bin values are uploaded uncast here, so the simulator's float64
+            # quantisation equals the compiled one (no NEP-50 caveat on this path)
+            tdm.sample_grid_batch_d.copy_to_device(np.zeros(tdm.sample_grid_batch_d.shape, dtype=np.int8))
+            out[key + "_grid1"] = _quiet(tdm.sample_grids, 0.9).copy_to_host().copy()
+            print("semantic", key, "done")
+    np.savez_compressed(os.path.join(OUT, "ref_semantic.npz"), **out)
+
+
 def main():
     from oracle.ref_loader import load_reference
     Config, TDM_Numba, MPPI_Numba, cuda = load_reference()
@@ -117,6 +163,9 @@ def main():
             out[key + "_states2"] = np.stack([st["s0"], st["s1"]], 1)
             print("terrain", key, "done", g1.shape)
     np.savez_compressed(os.path.join(OUT, "ref_terrain.npz"), **out)
+
+    # ---------------------------------------------------------------- 2b. semantic-grid setter (terrain.py:183-342)
+    make_semantic_golden(Config, TDM_Numba)
 
     # ---------------------------------------------------------------- 3. rollouts (mppi.py:613-1111)
     rng = np.random.default_rng(11)

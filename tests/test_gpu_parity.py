@@ -190,6 +190,32 @@ def test_setter_and_sampling_vs_reference_golden(eng, golden_dir, mode, alpha):
     assert (tdm.rng_states_d.copy_to_host() == g[key + "_states2"]).all()
 
 
+def test_semantic_grid_setter_vs_reference_golden(eng, golden_dir):
+    """set_TDM_from_semantic_grid (terrain.py:183-342) for the three modes: padded PMF, cropped semantic grid,
+    risk map and the sampled maps (float64 bin values are uploaded uncast on this path: 0.2 -> 20, 0.6 -> 60)."""
+    from oracle.make_golden import semantic_inputs, _T
+    g = load(golden_dir, "ref_semantic.npz")
+    sg, bin_values, names, pmfs, obstacle, unknown = semantic_inputs()
+    assert (sg == g["sg"]).all()
+    terr = {n: _T(n) for n in names.values()}
+    t2p = {terr[n]: (bin_values, pmfs[n]) for n in terr}
+    for mode, flags, alphas in (("tdm", dict(use_tdm=True), (None,)), ("det", dict(use_det_dynamics=True), (0.3, 1.0)),
+                                ("spd", dict(use_nom_dynamics_with_speed_map=True), (0.3, 1.0))):
+        for alpha in alphas:
+            cfg = eng.Config(T=1.0, dt=0.1, num_grid_samples=2, num_control_rollouts=100, seed=1, max_map_dim=(14, 12),
+                             tdm_sample_thread_dim=(3, 2), max_speed_padding=5.0, **flags)
+            tdm = eng.TDM_Numba(cfg)
+            tdm.set_TDM_from_semantic_grid(sg, 0.5, len(bin_values), bin_values, np.array([0.0, 1.0]),
+                                           np.array([0.0, 3.5]), np.array([0.0, 4.5]), names, terr, t2p,
+                                           det_dynamics_cvar_alpha=alpha, obstacle_map=obstacle, unknown_map=unknown)
+            key = "%s_%s" % (mode, "none" if alpha is None else "a%02d" % int(alpha * 10))
+            assert (tdm.pmf_grid_d.copy_to_host() == g[key + "_pmf_padded"]).all(), key
+            assert (np.asarray(tdm.semantic_grid) == g[key + "_semantic_cropped"]).all(), key
+            if mode == "spd":
+                assert (tdm.risk_traction_map_d.copy_to_host() == g[key + "_risk"]).all(), key
+            assert (tdm.sample_grids(0.9).copy_to_host() == g[key + "_grid1"]).all(), key
+
+
 def test_sampling_bit_exact_vs_oracle_config3_shape(eng):
     """512x512 map, 12 bins with non-representable bin values (compiled float64 truncation), M=64,
     16x16 thread tiles: bit-exact against the oracle's restatement of sample_grids_numba."""
