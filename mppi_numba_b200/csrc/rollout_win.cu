@@ -143,6 +143,13 @@ __device__ __forceinline__ double round_to_f32_precision(double a) {
   return __hiloint2double((int)hi2, (int)(lo2 & 0xE0000000u));
 }
 
+// obstacle / unknown penalties (mppi.py:700-701); out of line: taken for ~2 % of the steps, and as
+// predicated inline code its six instructions would be issued on every step
+static __device__ __noinline__ float add_penalties(float cost, int ob, int un, float obs_cost, float unk_cost) {
+  cost = ffma((float)ob, obs_cost, cost);
+  return ffma((float)un, unk_cost, cost);
+}
+
 struct WinSmem {                 // dynamic shared memory carve-up (all offsets multiples of 128)
   int plane;                     // bytes per plane = WW*WH
   int off_lut, off_u, off_bar, total;
@@ -220,6 +227,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     double x64 = widen(x), y64 = widen(y), th64 = widen(th);   // same values, float64 registers
     float cost = 0.0f, d2 = 1e9f;
     bool reached = false;
+#pragma unroll 2
     for (int t = 0; t < p.T; ++t, ep += a.npad) {
       // ---- cell index of both axes: floor(a/res) by round-down magic-number addition on the FP32 pipe;
       //      |frac - 0.5| < 0.5 - 5 ulp(y) proves it equals the reference's exact sequence, else run that
@@ -268,10 +276,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const float dx = fsub(gx, x), dy = fsub(gy, y);
       d2 = ffma(dx, dx, fmul(dy, dy));
       cost = fadd(cost, ffma(sqrt_approx(d2), p.dist_weight, p.dt));
-      if (ob | un) {
-        cost = ffma((float)ob, p.obs_cost, cost);
-        cost = ffma((float)un, p.unk_cost, cost);
-      }
+      if (__builtin_expect((ob | un) != 0, 0)) cost = add_penalties(cost, ob, un, p.obs_cost, p.unk_cost);
       if (d2 <= p.tol2) { reached = true; break; }
     }
     cost = fadd(cost, a.ctrl[n]);                                           // control cost (mppi.py:708-710)
