@@ -549,7 +549,7 @@ extern "C" int b200mppi_planner_create(const b200mppi_config* cfg, b200mppi_plan
   CU(cudaMalloc(&p->costs_nm, (size_t)p->n_local * p->M * sizeof(float)));
   if (p->shard_maps) CU(cudaMalloc(&p->costs_x, (size_t)p->n_local * p->M * sizeof(float)));
   p->npad = round_up(p->n_local, 32);
-  CU(cudaMalloc(&p->noiseT, (size_t)p->T * p->npad * 2 * sizeof(float)));
+  CU(cudaMalloc(&p->noiseT, (size_t)p->T * p->npad * 2 * sizeof(double)));
   CU(cudaMalloc(&p->ctrl, (size_t)p->npad * sizeof(float)));
   p->use_win = getenv("B200MPPI_NO_WINDOW") == nullptr;
   p->num_ctas = update_num_ctas(p->n_red);

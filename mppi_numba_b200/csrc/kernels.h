@@ -66,7 +66,7 @@ struct RolloutWinArgs {
   int WW, WH, wx0, wy0;     // window size / origin in cells
   int npad;                 // row length of noiseT
   const int8_t* lin_grid; const int8_t* ang_grid; const int8_t* obstacle; const int8_t* unknown;
-  const float* noiseT;      // [T][npad] float2: clipped noisy controls (v, w)
+  const float* noiseT;      // [T][npad] double2: clipped noisy controls (v, w), already widened to f64
   const float* ctrl;        // [npad]
   const float* u_cur;
   float* costs_nm;          // (N, M)

@@ -24,14 +24,14 @@
 namespace b200 {
 
 // ---------------------------------------------------------------------------------------------
-// prepare: noise (N,T,2) -> transposed CLIPPED NOISY CONTROLS ctlT [T][npad] float2
+// prepare: noise (N,T,2) -> transposed CLIPPED NOISY CONTROLS ctlT [T][npad] double2
 //   (v, w) = (clip(u_v[t] + e_v, vrange), clip(u_w[t] + e_w, wrange))           (mppi.py:686-689)
 // -- identical for all M maps of a control sequence, so computed once here (coalesced per-step loads
 // for lanes = consecutive n) -- and the per-n control cost sum_t lambda*(u_v/s_v^2*e_v + u_w/s_w^2*e_w)
 // (mppi.py:708-710), accumulated in the reference's order t = 0..T-1.
 __global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __restrict__ noise,
                                                               const float* __restrict__ u_cur,
-                                                              float2* __restrict__ noiseT,
+                                                              double2* __restrict__ noiseT,
                                                               float* __restrict__ ctrl, int N, int T, int npad,
                                                               float lambda, float sv2, float sw2, float v_lo,
                                                               float v_hi, float w_lo, float w_hi) {
@@ -49,9 +49,11 @@ __global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __re
       const int t = t0 + r;
       if (t < T) {
         const float2 e = tile[tx][r];
-        float2 c;
-        c.x = fmaxf(v_lo, fminf(v_hi, fadd(u_cur[2 * t], e.x)));
-        c.y = fmaxf(w_lo, fminf(w_hi, fadd(u_cur[2 * t + 1], e.y)));
+        // stored already widened to float64 (exact): the rollout kernel's per-step f2d(v), f2d(w) are
+        // XU-pipe conversions, and these values are shared by all M maps of the control sequence
+        double2 c;
+        c.x = f2d(fmaxf(v_lo, fminf(v_hi, fadd(u_cur[2 * t], e.x))));
+        c.y = f2d(fmaxf(w_lo, fminf(w_hi, fadd(u_cur[2 * t + 1], e.y))));
         noiseT[(size_t)t * npad + n0 + tx] = c;
       }
     }
@@ -73,7 +75,7 @@ void launch_prepare_rollout(const float* noise, const float* u_cur, float* noise
                             int npad, float lambda, float std_v, float std_w, const float vrange[2],
                             const float wrange[2], cudaStream_t st) {
   prepare_rollout_kernel<<<npad / 32, 256, 0, st>>>(reinterpret_cast<const float2*>(noise), u_cur,
-                                                   reinterpret_cast<float2*>(noiseT), ctrl, N, T, npad, lambda,
+                                                   reinterpret_cast<double2*>(noiseT), ctrl, N, T, npad, lambda,
                                                    std_v * std_v, std_w * std_w, vrange[0], vrange[1], wrange[0],
                                                    wrange[1]);
 }
@@ -222,12 +224,11 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   for (int tile = blockIdx.x; tile * THREADS < p.N; tile += gridDim.x) {
     const int n = tile * THREADS + tid;
     if (n >= p.N) break;
-    const float2* __restrict__ ep = reinterpret_cast<const float2*>(a.noiseT) + n;
+    const double2* __restrict__ ep = reinterpret_cast<const double2*>(a.noiseT) + n;
     float x = p.x0[0], y = p.x0[1], th = p.x0[2];
     double x64 = widen(x), y64 = widen(y), th64 = widen(th);   // same values, float64 registers
     float cost = 0.0f, d2 = 1e9f;
     bool reached = false;
-#pragma unroll 2
     for (int t = 0; t < p.T; ++t, ep += a.npad) {
       // ---- cell index of both axes: floor(a/res) by round-down magic-number addition on the FP32 pipe;
       //      |frac - 0.5| < 0.5 - 5 ulp(y) proves it equals the reference's exact sequence, else run that
@@ -261,15 +262,15 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
         un = __ldg(a.unknown + (size_t)my * p.g.mask_pitch + mx);
       }
       // ---- noisy clipped control (mppi.py:686-689), precomputed per (n, t) by the prepare kernel
-      const float2 c = __ldg(ep);
+      const double2 c = __ldg(ep);
       // ---- unicycle step (mppi.py:692-694): float64 FMA, one rounding to float32 per component.  The
       //      float64 copies hold the float32-rounded state, so the reference's f2d(x) costs nothing.
-      const double dv = lds_f64(sb_lutL + (uint32_t)(ql * 8)) * widen(c.x);
+      const double dv = lds_f64(sb_lutL + (uint32_t)(ql * 8)) * c.x;
       const float cs = cos_approx(th);
       const float sn = sin_approx(th);
       const double rx = fma(dv, widen(cs), x64);
       const double ry = fma(dv, widen(sn), y64);
-      const double rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), widen(c.y), th64);
+      const double rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), c.y, th64);
       x = narrow(rx); y = narrow(ry); th = narrow(rt);
       x64 = round_to_f32_precision(rx); y64 = round_to_f32_precision(ry); th64 = round_to_f32_precision(rt);
       // ---- stage cost (mppi.py:696-701)
