@@ -229,7 +229,10 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     double x64 = widen(x), y64 = widen(y), th64 = widen(th);   // same values, float64 registers
     float cost = 0.0f, d2 = 1e9f;
     bool reached = false;
-    for (int t = 0; t < p.T; ++t, ep += a.npad) {
+    double2 c = __ldg(ep);                                  // controls are prefetched one step ahead (L2 latency)
+    for (int t = 0; t < p.T; ++t) {
+      ep += a.npad;
+      const double2 c_next = (t + 1 < p.T) ? __ldg(ep) : c;
       // ---- cell index of both axes: floor(a/res) by round-down magic-number addition on the FP32 pipe;
       //      |frac - 0.5| < 0.5 - 5 ulp(y) proves it equals the reference's exact sequence, else run that
       const float ax = fsub(x, xlo), ay = fsub(y, ylo);
@@ -261,8 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
         ob = __ldg(a.obstacle + (size_t)my * p.g.mask_pitch + mx);
         un = __ldg(a.unknown + (size_t)my * p.g.mask_pitch + mx);
       }
-      // ---- noisy clipped control (mppi.py:686-689), precomputed per (n, t) by the prepare kernel
-      const double2 c = __ldg(ep);
+      // ---- noisy clipped control (mppi.py:686-689): `c`, precomputed per (n, t) by the prepare kernel
       // ---- unicycle step (mppi.py:692-694): float64 FMA, one rounding to float32 per component.  The
       //      float64 copies hold the float32-rounded state, so the reference's f2d(x) costs nothing.
       const double dv = lds_f64(sb_lutL + (uint32_t)(ql * 8)) * c.x;
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       cost = fadd(cost, ffma(sqrt_approx(d2), p.dist_weight, p.dt));
       if (__builtin_expect((ob | un) != 0, 0)) cost = add_penalties(cost, ob, un, p.obs_cost, p.unk_cost);
       if (d2 <= p.tol2) { reached = true; break; }
+      c = c_next;
     }
     cost = fadd(cost, a.ctrl[n]);                                           // control cost (mppi.py:708-710)
     const double num = (reached ? 0.0 : 1.0) * f2d(sqrt_approx(d2));         // terminal cost (mppi.py:26-28)
