@@ -43,7 +43,9 @@ enum {
 enum {
   B200MPPI_MODE_TDM = 0,        /* use_tdm: M sampled traction maps, CVaR of the cost        */
   B200MPPI_MODE_DET_DYN = 1,    /* use_det_dynamics: one worst-case-expectation map          */
-  B200MPPI_MODE_SPEED_MAP = 2   /* use_nom_dynamics_with_speed_map: nominal map + speed map  */
+  B200MPPI_MODE_SPEED_MAP = 2,  /* use_nom_dynamics_with_speed_map: nominal map + speed map  */
+  B200MPPI_MODE_BAREBONE = 3    /* map-free variant of barebone_mppi_numba.ipynb: quadratic cost,
+                                   circular obstacles, no TDMs (set_obstacles instead of set_tdms) */
 };
 
 /* Fixed sizes, == Config (config.py:16-100) after its clamps. */
@@ -145,6 +147,10 @@ int b200mppi_planner_set_stream(b200mppi_planner* pl, void* cuda_stream);
 /* MPPI_Numba.set_tdm (mppi.py:152-155): the TDMs are BORROWED; obstacle/unknown/risk maps and
  * the map geometry are read from lin (mppi.py:266-270). */
 int b200mppi_planner_set_tdms(b200mppi_planner* pl, b200mppi_tdm* lin, b200mppi_tdm* ang);
+/* MODE_BAREBONE: the notebook's obstacle_positions (K,2) / obstacle_radius (K) (barebone_mppi_numba.ipynb
+ * cell 3, move_mppi_task_vars_to_device); K = 0 clears them.  params.obs_penalty is the obstacle cost. */
+int b200mppi_planner_set_obstacles(b200mppi_planner* pl, const float* positions_xy, const float* radius,
+                                   int32_t count);
 /* move_mppi_task_vars_to_device (mppi.py:214-234): one POD struct instead of 7 cuda.to_device. */
 int b200mppi_planner_set_params(b200mppi_planner* pl, const b200mppi_params* p);
 /* u_cur_d = cuda.to_device(u) (mppi.py:114,542) / u_cur_d.copy_to_host(): float32 (T,2). */

@@ -13,7 +13,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libb200mppi.so")
 
-MODE_TDM, MODE_DET_DYN, MODE_SPEED_MAP = 0, 1, 2
+MODE_TDM, MODE_DET_DYN, MODE_SPEED_MAP, MODE_BAREBONE = 0, 1, 2, 3
 
 BUF_NOISE, BUF_U_CUR, BUF_COSTS, BUF_WEIGHTS, BUF_COSTS_NM, BUF_RNG, BUF_PARTIAL, BUF_U_PREV, \
     BUF_STATE_ROLLOUT = range(9)
@@ -70,6 +70,7 @@ def _load():
         "b200mppi_planner_destroy": (C.c_int, [P]),
         "b200mppi_planner_set_stream": (C.c_int, [P, P]),
         "b200mppi_planner_set_tdms": (C.c_int, [P, P, P]),
+        "b200mppi_planner_set_obstacles": (C.c_int, [P, P, P, I32]),
         "b200mppi_planner_set_params": (C.c_int, [P, C.POINTER(ParamsPOD)]),
         "b200mppi_planner_set_u": (C.c_int, [P, P]),
         "b200mppi_planner_get_u": (C.c_int, [P, P]),

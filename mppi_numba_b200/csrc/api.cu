@@ -443,6 +443,7 @@ struct b200mppi_planner {
   // M/ws maps (n_roll = N), exchanges per-(n,m) costs (all-to-all), and reduces its N/ws slice (n_red)
   bool shard_maps = false;
   int M_total = 1, n_roll = 0, n_red = 0, n_red_begin = 0;
+  float* obstacles = nullptr; int num_obstacles = 0, obstacles_cap = 0;   // MODE_BAREBONE: (K,3) x, y, r
   float* costs_x = nullptr;    // (ws, N/ws, M_local): per-(n,m) costs of this rank's n-slice after the exchange
   float* noise = nullptr; float* u_cur = nullptr; float* u_prev = nullptr;
   float* costs = nullptr; float* weights = nullptr; float* costs_nm = nullptr; float* w_raw = nullptr;
@@ -463,6 +464,8 @@ struct b200mppi_planner {
 };
 
 static int planner_check_ready(b200mppi_planner* p) {
+  if (p->cfg.mode == B200MPPI_MODE_BAREBONE)
+    return p->params_set ? B200MPPI_OK : fail(B200MPPI_ESTATE, "planner: params not set");
   if (!p->lin || !p->ang) return fail(B200MPPI_ESTATE, "planner: TDMs not set");
   if (!p->params_set) return fail(B200MPPI_ESTATE, "planner: params not set");
   if (!p->lin->pmf_set || !p->ang->pmf_set) return fail(B200MPPI_ESTATE, "planner: TDM PMF not initialised");
@@ -480,11 +483,16 @@ static int planner_check_ready(b200mppi_planner* p) {
 
 static void fill_rollout_params(b200mppi_planner* p, RolloutParams& r) {
   const b200mppi_tdm* l = p->lin; const b200mppi_tdm* a = p->ang;
-  r.g.res = l->res; r.g.inv_res = 1.0f / l->res;
-  r.g.xlo = l->pxl[0]; r.g.ylo = l->pyl[0];
-  r.g.rows = l->rows; r.g.cols = l->cols;
-  r.g.grid_rows = l->cfg.max_map_rows; r.g.grid_cols = l->cfg.max_map_cols; r.g.grid_pitch = l->pitch;
-  r.g.mask_pitch = l->mask_pitch;
+  if (l && a) {
+    r.g.res = l->res; r.g.inv_res = 1.0f / l->res;
+    r.g.xlo = l->pxl[0]; r.g.ylo = l->pyl[0];
+    r.g.rows = l->rows; r.g.cols = l->cols;
+    r.g.grid_rows = l->cfg.max_map_rows; r.g.grid_cols = l->cfg.max_map_cols; r.g.grid_pitch = l->pitch;
+    r.g.mask_pitch = l->mask_pitch;
+    r.lin_lo = l->bounds[0]; r.ang_lo = a->bounds[0];
+    r.lin_ratio = 0.01 * (double)(float)(l->bounds[1] - l->bounds[0]);
+    r.ang_ratio = 0.01 * (double)(float)(a->bounds[1] - a->bounds[0]);
+  }
   const b200mppi_params& q = p->prm;
   r.dt = q.dt;
   for (int i = 0; i < 3; ++i) r.x0[i] = q.x0[i];
@@ -495,9 +503,6 @@ static void fill_rollout_params(b200mppi_planner* p, RolloutParams& r) {
   r.vrange[0] = q.vrange[0]; r.vrange[1] = q.vrange[1];
   r.wrange[0] = q.wrange[0]; r.wrange[1] = q.wrange[1];
   r.obs_cost = q.obs_penalty; r.unk_cost = q.unknown_penalty; r.dist_weight = q.dist_weight;
-  r.lin_lo = l->bounds[0]; r.ang_lo = a->bounds[0];
-  r.lin_ratio = 0.01 * (double)(float)(l->bounds[1] - l->bounds[0]);
-  r.ang_ratio = 0.01 * (double)(float)(a->bounds[1] - a->bounds[0]);
   r.T = p->T; r.N = p->n_local; r.M = p->M;
 }
 
@@ -584,6 +589,7 @@ extern "C" int b200mppi_planner_destroy(b200mppi_planner* p) {
   cudaFree(p->noise); cudaFree(p->u_cur); cudaFree(p->u_prev); cudaFree(p->costs); cudaFree(p->weights);
   cudaFree(p->w_raw); cudaFree(p->costs_nm); cudaFree(p->cta_partials); cudaFree(p->rank_partial);
   cudaFree(p->state_rollout); cudaFree(p->states); cudaFree(p->noiseT); cudaFree(p->ctrl); cudaFree(p->costs_x);
+  cudaFree(p->obstacles);
   if (p->h_u) cudaFreeHost(p->h_u);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
@@ -659,8 +665,11 @@ static int stage_rollout(b200mppi_planner* p) {
   RolloutArgs a{};
   fill_rollout_params(p, a.p);
   a.mode = p->cfg.mode;
-  a.lin_grid = p->lin->grid; a.ang_grid = p->ang->grid;
-  a.obstacle = p->lin->obstacle; a.unknown = p->lin->unknown; a.risk = p->lin->risk;
+  if (p->cfg.mode != B200MPPI_MODE_BAREBONE) {
+    a.lin_grid = p->lin->grid; a.ang_grid = p->ang->grid;
+    a.obstacle = p->lin->obstacle; a.unknown = p->lin->unknown; a.risk = p->lin->risk;
+  }
+  a.obstacles = p->obstacles; a.num_obstacles = p->num_obstacles;
   a.noise = p->noise; a.u_cur = p->u_cur; a.costs_nm = p->costs_nm; a.costs = p->costs;
   bool done = false;
   if (p->cfg.mode == B200MPPI_MODE_TDM && p->use_win) {
@@ -730,7 +739,26 @@ static int stage_update_finish(b200mppi_planner* p, const float* gathered, int c
   return B200MPPI_OK;
 }
 
+extern "C" int b200mppi_planner_set_obstacles(b200mppi_planner* p, const float* xy, const float* rad, int32_t count) {
+  if (!p || count < 0 || (count > 0 && (!xy || !rad))) return fail(B200MPPI_EINVAL, "set_obstacles: bad argument");
+  CU(cudaSetDevice(p->cfg.device));
+  if (count > p->obstacles_cap) {
+    cudaFree(p->obstacles); p->obstacles = nullptr;
+    CU(cudaMalloc(&p->obstacles, (size_t)count * 3 * sizeof(float)));
+    p->obstacles_cap = count;
+  }
+  if (count > 0) {
+    std::vector<float> h((size_t)count * 3);
+    for (int k = 0; k < count; ++k) { h[3 * k] = xy[2 * k]; h[3 * k + 1] = xy[2 * k + 1]; h[3 * k + 2] = rad[k]; }
+    CU(cudaMemcpyAsync(p->obstacles, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+  }
+  p->num_obstacles = count;
+  return B200MPPI_OK;
+}
+
 static int stage_sample_tdms(b200mppi_planner* p) {
+  if (p->cfg.mode == B200MPPI_MODE_BAREBONE) return B200MPPI_OK;      // no maps
   // det / speed-map solves call sample_grids() with the default alpha_dyn = 1.0 (mppi.py:248-249,322-323)
   const double alpha = p->cfg.mode == B200MPPI_MODE_TDM ? p->prm.alpha_dyn : 1.0;
   return tdm_sample_pair_on(p->lin, p->ang, alpha, p->stream, &p->launches);
@@ -908,7 +936,7 @@ extern "C" int b200mppi_planner_get_state_rollout(b200mppi_planner* p, float* ou
   VisArgs a{};
   fill_rollout_params(p, a.p);
   a.mode = p->cfg.mode; a.V = V;
-  a.lin_grid = p->lin->grid; a.ang_grid = p->ang->grid;
+  if (p->cfg.mode != B200MPPI_MODE_BAREBONE) { a.lin_grid = p->lin->grid; a.ang_grid = p->ang->grid; }
   a.noise = p->noise; a.u_cur = p->u_cur; a.u_prev = p->u_prev; a.out = p->state_rollout;
   launch_state_rollout(a, p->stream);
   p->launches++;

@@ -58,6 +58,8 @@ struct RolloutArgs {
   const float* u_cur;       // (T, 2)
   float* costs_nm;          // (N, M)   MODE_TDM
   float* costs;             // (N)
+  const float* obstacles;   // MODE_BAREBONE: (num_obstacles, 3) = x, y, radius
+  int num_obstacles;
 };
 void launch_rollout(const RolloutArgs& a, cudaStream_t st);
 // windowed (TMA-staged) stochastic rollout kernel -- rollout_win.cu

@@ -141,8 +141,59 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// MODE 3: the map-free "barebone" MPPI of the reference's barebone_mppi_numba.ipynb (cell 3, rollout_numba):
+// nominal float32 unicycle, stage cost w*d^2, circular obstacles, terminal cost (1-reached)*d^2.
+// Contractions follow the SASS of the compiled notebook kernel (dv = FMUL(v, dt); x = FFMA(dv, cos, x);
+// theta = FFMA(w, dt, theta); d^2 - r^2 as one FFMA; the obstacle indicator enters through a float64 FMA).
+__global__ void __launch_bounds__(128) rollout_barebone_kernel(const RolloutArgs a) {
+  const RolloutParams& p = a.p;
+  extern __shared__ float s_u[];
+  for (int i = threadIdx.x; i < 2 * p.T; i += blockDim.x) s_u[i] = a.u_cur[i];
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const float2* __restrict__ eps = reinterpret_cast<const float2*>(a.noise) + (size_t)n * p.T;
+  const double obs_c64 = f2d(p.obs_cost);
+  float x = p.x0[0], y = p.x0[1], th = p.x0[2];
+  float cost = 0.0f, d2 = 1e9f;
+  bool reached = false;
+  for (int t = 0; t < p.T; ++t) {
+    const float2 e = __ldg(eps + t);
+    const float v = fmaxf(p.vrange[0], fminf(p.vrange[1], fadd(s_u[2 * t], e.x)));
+    const float w = fmaxf(p.wrange[0], fminf(p.wrange[1], fadd(s_u[2 * t + 1], e.y)));
+    const float dv = fmul(v, p.dt);
+    const float cs = cos_approx(th), sn = sin_approx(th);
+    x = ffma(dv, cs, x);
+    y = ffma(dv, sn, y);
+    th = ffma(w, p.dt, th);
+    const float dx = fsub(p.xgoal[0], x), dy = fsub(p.xgoal[1], y);
+    d2 = ffma(dx, dx, fmul(dy, dy));
+    cost = ffma(d2, p.dist_weight, cost);
+    for (int k = 0; k < a.num_obstacles; ++k) {
+      const float ox = __ldg(a.obstacles + 3 * k), oy = __ldg(a.obstacles + 3 * k + 1), orad = __ldg(a.obstacles + 3 * k + 2);
+      const float ddx = fsub(x, ox), ddy = fsub(y, oy);
+      const float diff = ffma(-orad, orad, ffma(ddx, ddx, fmul(ddy, ddy)));
+      const double inside = 1.0 - f2d(diff > 0.0f ? 1.0f : 0.0f);
+      cost = d2f(fma(inside, obs_c64, f2d(cost)));
+    }
+    if (d2 <= p.tol2) { reached = true; break; }
+  }
+  cost = fadd(cost, d2f((reached ? 0.0 : 1.0) * f2d(d2)));
+  const float sv2 = fmul(p.u_std[0], p.u_std[0]), sw2 = fmul(p.u_std[1], p.u_std[1]);
+  for (int t = 0; t < p.T; ++t) {
+    const float2 e = __ldg(eps + t);
+    cost = ffma(ctrl_term(s_u[2 * t], s_u[2 * t + 1], e.x, e.y, sv2, sw2), p.lambda, cost);
+  }
+  a.costs[n] = cost;
+}
+
 void launch_rollout(const RolloutArgs& a, cudaStream_t st) {
   const int threads = 128;
+  if (a.mode == 3) {
+    rollout_barebone_kernel<<<(a.p.N + threads - 1) / threads, threads, (size_t)2 * a.p.T * sizeof(float), st>>>(a);
+    return;
+  }
   const dim3 grid((a.p.N + threads - 1) / threads, a.mode == 0 ? a.p.M : 1);
   const size_t smem = (size_t)2 * a.p.T * sizeof(float);
   if (a.mode == 0) rollout_kernel<0><<<grid, threads, smem, st>>>(a);
@@ -237,6 +288,24 @@ __global__ void state_rollout_kernel(const VisArgs a) {
   float x = p.x0[0], y = p.x0[1], th = p.x0[2];
   out[0] = x; out[1] = y; out[2] = th;
   const bool noisy = (a.mode != 0) && (b != 0);
+  if (a.mode == 3) {                      // map-free variant (notebook cell 3, get_state_rollout_across_control_noise)
+    for (int t = 0; t < p.T; ++t) {
+      float v, w;
+      if (noisy) {
+        const float* e = a.noise + ((size_t)b * p.T + t) * 2;
+        v = fmaxf(c.v_lo, fminf(c.v_hi, fadd(a.u_prev[2 * t], e[0])));
+        w = fmaxf(c.w_lo, fminf(c.w_hi, fadd(a.u_prev[2 * t + 1], e[1])));
+      } else {
+        v = a.u_cur[2 * t];
+        w = a.u_cur[2 * t + 1];
+      }
+      const float dv = fmul(v, p.dt);
+      const float cs = cos_approx(th), sn = sin_approx(th);
+      x = ffma(dv, cs, x); y = ffma(dv, sn, y); th = ffma(w, p.dt, th);
+      out[(t + 1) * 3 + 0] = x; out[(t + 1) * 3 + 1] = y; out[(t + 1) * 3 + 2] = th;
+    }
+    return;
+  }
   for (int t = 0; t < p.T; ++t) {
     const int xi = cell_index(fsub(x, c.xlo), c.res, c.inv_res);
     const int yi = cell_index(fsub(y, c.ylo), c.res, c.inv_res);

@@ -95,6 +95,65 @@ def make_semantic_golden(Config, TDM_Numba):
     np.savez_compressed(os.path.join(OUT, "ref_semantic.npz"), **out)
 
 
+def load_barebone_notebook():
+    """Executes the code cells of the reference's barebone_mppi_numba.ipynb (its own Config / MPPI_Numba with
+    the map-free kernels, cells 2-3) in a namespace, under the simulator shims installed by load_reference()."""
+    import json
+    from oracle.ref_loader import REFERENCE_ROOT
+    nb = json.load(open(os.path.join(REFERENCE_ROOT, "barebone_mppi_numba.ipynb")))
+    ns = {}
+    exec("import numpy as np\nimport math\nimport copy\nimport numba\nimport time\nfrom numba import cuda\n"
+         "from numba.cuda.random import create_xoroshiro128p_states, xoroshiro128p_normal_float32\n", ns)
+    code = [c for c in nb["cells"] if c["cell_type"] == "code"]
+    exec("".join(code[1]["source"]), ns)          # Config (barebone_mppi_numba.ipynb cell 2)
+    exec("".join(code[2]["source"]), ns)          # stage/term cost + MPPI_Numba with 4 kernels (cell 3)
+    return ns["Config"], ns["MPPI_Numba"]
+
+
+def make_barebone_golden(cuda):
+    BConfig, BMPPI = load_barebone_notebook()
+    f32 = np.float32
+    rng = np.random.default_rng(29)
+    N, T = 40, 14
+    noise = (rng.standard_normal((N, T, 2)) * np.array([1.0, 1.0])).astype(f32)
+    u_cur = np.stack([rng.uniform(0.5, 1.8, T), rng.uniform(-0.6, 0.6, T)], 1).astype(f32)
+    x0 = np.array([0.0, 0.0, np.pi / 4], dtype=f32)
+    obs_pos = np.array([[1.4, 1.2], [0.6, 2.0], [2.4, 0.4]], dtype=f32)
+    obs_r = np.array([0.5, 0.4, 0.3], dtype=f32)
+    out = dict(noise=noise, u_cur=u_cur, x0=x0, obs_pos=obs_pos, obs_r=obs_r, vrange=[0.0, 2.0],
+               wrange=[-np.pi, np.pi], u_std=[1.0, 1.0], dt=0.1, lam=1.0, goal_tol=0.5, dist_weight=10,
+               obs_cost=1e6, goal_near=np.array([1.3, 1.5], f32), goal_far=np.array([7.0, 5.0], f32))
+    dev = cuda.to_device
+    for gname in ("near", "far"):
+        costs_d = cuda.device_array((N,), dtype=f32)
+        BMPPI.rollout_numba[N, 1](dev(np.array([0, 2], f32)), dev(np.array([-np.pi, np.pi], f32)), dev(out["goal_" + gname]),
+                                  f32(1e6), dev(obs_pos), dev(obs_r), f32(0.5), f32(1.0), dev(np.array([1, 1], f32)),
+                                  dev(x0), f32(0.1), 10, dev(noise), dev(u_cur), costs_d)
+        out["costs_" + gname] = costs_d.copy_to_host()
+    # whole solve through the notebook's public API (update launched with one thread, SURVEY 9-R1)
+    cfg = _quiet(BConfig, T=1.0, dt=0.1, num_control_rollouts=100, num_vis_state_rollouts=5, seed=1)
+    pl = _quiet(BMPPI, cfg)
+    params = dict(dt=0.1, x0=np.array([0.0, 0.0, np.pi / 4]), xgoal=np.array([7.0, 5.0]), goal_tolerance=0.5,
+                  dist_weight=10, lambda_weight=1.0, num_opt=1, u_std=np.array([1.0, 1.0]),
+                  vrange=np.array([0.0, 2.0]), wrange=np.array([-np.pi, np.pi]),
+                  obstacle_positions=np.array([[5, 4.5], [2, 1]]), obstacle_radius=np.array([1.5, 1.0]), obs_penalty=1e6)
+    pl.setup(params)
+    orig = BMPPI.update_useq_numba
+
+    class _One:
+        def __getitem__(self, cfg_):
+            return orig[1, 1]
+    pl.update_useq_numba = _One()
+    u1 = _quiet(pl.solve).copy()
+    out["solve_u1"] = u1
+    out["solve_noise1"] = pl.noise_samples_d.copy_to_host().copy()
+    out["solve_states1"] = _quiet(pl.get_state_rollout).copy()
+    pl.shift_and_update(np.array([0.05, 0.06, 0.8]), u1, num_shifts=1)
+    out["solve_u2"] = _quiet(pl.solve).copy()
+    np.savez_compressed(os.path.join(OUT, "ref_barebone.npz"), **out)
+    print("barebone done")
+
+
 def main():
     from oracle.ref_loader import load_reference
     Config, TDM_Numba, MPPI_Numba, cuda = load_reference()
@@ -166,6 +225,9 @@ def main():
 
     # ---------------------------------------------------------------- 2b. semantic-grid setter (terrain.py:183-342)
     make_semantic_golden(Config, TDM_Numba)
+
+    # ---------------------------------------------------------------- 2c. barebone map-free variant (notebook)
+    make_barebone_golden(cuda)
 
     # ---------------------------------------------------------------- 3. rollouts (mppi.py:613-1111)
     rng = np.random.default_rng(11)

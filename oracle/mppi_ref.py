@@ -187,6 +187,68 @@ def rollout_costs(mode, lin_grid, ang_grid, lin_bounds, ang_bounds, obstacle_map
     return cost
 
 
+def rollout_costs_barebone(obs_pos, obs_r, vrange, wrange, xgoal, obs_cost, goal_tolerance, lambda_weight, u_std,
+                           x0, dt, dist_weight, noise, u_cur, return_states=False):
+    """The map-free variant of the reference's barebone_mppi_numba.ipynb (cell 3, rollout_numba): nominal
+    unicycle in float32 (dv = dt*v; x = fma(dv, cos, x); theta = fma(w, dt, theta)), stage cost w*d^2,
+    circular obstacles (indicator of d^2 - r^2 <= 0, float64 FMA into the float32 cost), terminal cost
+    (1-reached)*d^2, then the control cost.  Contractions as in the SASS of the compiled kernel."""
+    noise = np.asarray(noise, dtype=F32)
+    u_cur = np.asarray(u_cur, dtype=F32)
+    N, T, _ = noise.shape
+    vr, wr = np.asarray(vrange, dtype=F32), np.asarray(wrange, dtype=F32)
+    xg, us = np.asarray(xgoal, dtype=F32), np.asarray(u_std, dtype=F32)
+    x0 = np.asarray(x0, dtype=F32)
+    dt, lam, w_dist, obs_c = F32(dt), F32(lambda_weight), F32(dist_weight), F32(obs_cost)
+    tol2 = F32(F32(goal_tolerance) * F32(goal_tolerance))
+    op = np.asarray(obs_pos, dtype=F32).reshape(-1, 2)
+    orad = np.asarray(obs_r, dtype=F32).reshape(-1)
+    x = np.full(N, x0[0], dtype=F32)
+    y = np.full(N, x0[1], dtype=F32)
+    th = np.full(N, x0[2], dtype=F32)
+    cost = np.zeros(N, dtype=F32)
+    d2 = np.full(N, 1e9, dtype=F32)
+    active = np.ones(N, dtype=bool)
+    reached = np.zeros(N, dtype=bool)
+    states = np.zeros((N, T + 1, 3), dtype=F32) if return_states else None
+    if return_states:
+        states[:, 0, :] = x0
+    for t in range(T):
+        if not active.any():
+            break
+        v = np.maximum(vr[0], np.minimum(vr[1], (u_cur[t, 0] + noise[:, t, 0]).astype(F32))).astype(F32)
+        w = np.maximum(wr[0], np.minimum(wr[1], (u_cur[t, 1] + noise[:, t, 1]).astype(F32))).astype(F32)
+        dv = (v * dt).astype(F32)
+        xn = _fma32(dv, np.cos(th).astype(F32), x)
+        yn = _fma32(dv, np.sin(th).astype(F32), y)
+        thn = _fma32(w, dt, th)
+        dx, dy = (xg[0] - xn).astype(F32), (xg[1] - yn).astype(F32)
+        d2n = _fma32(dx, dx, (dy * dy).astype(F32))
+        cn = _fma32(d2n, w_dist, cost)
+        for k in range(len(orad)):
+            ddx, ddy = (xn - op[k, 0]).astype(F32), (yn - op[k, 1]).astype(F32)
+            q = _fma32(ddx, ddx, (ddy * ddy).astype(F32))
+            diff = (q.astype(F64) - F64(orad[k]) * F64(orad[k])).astype(F32)          # FFMA(-r, r, q)
+            ind = (diff > 0).astype(F64)
+            cn = ((1.0 - ind) * F64(obs_c) + cn.astype(F64)).astype(F32)
+        x, y, th = np.where(active, xn, x), np.where(active, yn, y), np.where(active, thn, th)
+        cost, d2 = np.where(active, cn, cost), np.where(active, d2n, d2)
+        hit = active & (d2n <= tol2)
+        reached |= hit
+        active &= ~hit
+        if return_states:
+            states[:, t + 1, 0], states[:, t + 1, 1], states[:, t + 1, 2] = x, y, th
+    cost = (cost + np.where(reached, F32(0), d2).astype(F32)).astype(F32)
+    sv2, sw2 = F32(us[0] * us[0]), F32(us[1] * us[1])
+    for t in range(T):
+        a, b = F32(u_cur[t, 0] / sv2), F32(u_cur[t, 1] / sw2)
+        sterm = _fma32(np.full(N, a, dtype=F32), noise[:, t, 0], (b * noise[:, t, 1]).astype(F32))
+        cost = _fma32(sterm, lam, cost)
+    if return_states:
+        return cost, states
+    return cost
+
+
 def cvar_count(M, cvar_alpha):
     """mppi.py:744: ceil(int32 * float32) evaluated in float64."""
     return int(math.ceil(float(M) * float(F32(cvar_alpha))))

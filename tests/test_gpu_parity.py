@@ -601,6 +601,58 @@ def test_solve_preconditions_and_api_surface(eng, capsys):
     assert (t.cpu().numpy() == s).all()
 
 
+def test_barebone_variant_vs_reference_notebook_golden(eng, golden_dir):
+    """The map-free MPPI of barebone_mppi_numba.ipynb: kernel-level costs on injected noise, then the notebook's
+    public call sequence (setup / solve / get_state_rollout / shift_and_update / solve) against what the
+    notebook's own classes returned for the same seed."""
+    from mppi_numba_b200 import barebone as BB
+    g = load(golden_dir, "ref_barebone.npz")
+    L = eng._lib
+    N, T = g["noise"].shape[:2]
+    for gname in ("near", "far"):
+        rp_pod = L.ConfigPOD(num_steps=T, num_control_rollouts=N, num_grid_samples=1, max_map_rows=1, max_map_cols=1,
+                             tdm_thread_x=1, tdm_thread_y=1, num_vis_state_rollouts=1, mode=L.MODE_BAREBONE, device=0,
+                             rank=0, world_size=1, seed=1)
+        h = C.c_void_p()
+        L.check(L.lib.b200mppi_planner_create(C.byref(rp_pod), C.byref(h)))
+        try:
+            p = L.ParamsPOD()
+            p.dt = 0.1
+            p.x0 = L.c_floats(g["x0"], 3)
+            p.xgoal = L.c_floats(g["goal_" + gname], 2)
+            p.goal_tolerance, p.lambda_weight, p.cvar_alpha, p.num_opt, p.alpha_dyn = 0.5, 1.0, 1.0, 1, 1.0
+            p.u_std = L.c_floats([1.0, 1.0], 2)
+            p.vrange = L.c_floats([0.0, 2.0], 2)
+            p.wrange = L.c_floats(np.array([-np.pi, np.pi], np.float32), 2)
+            p.obs_penalty, p.dist_weight = 1e6, 10.0
+            L.check(L.lib.b200mppi_planner_set_params(h, C.byref(p)))
+            pos, rad = np.ascontiguousarray(g["obs_pos"]), np.ascontiguousarray(g["obs_r"])
+            L.check(L.lib.b200mppi_planner_set_obstacles(h, L.ptr(pos), L.ptr(rad), len(rad)))
+            noise, u_cur = np.ascontiguousarray(g["noise"]), np.ascontiguousarray(g["u_cur"])
+            L.check(L.lib.b200mppi_planner_copy_in(h, L.BUF_NOISE, L.ptr(noise), noise.nbytes))
+            L.check(L.lib.b200mppi_planner_copy_in(h, L.BUF_U_CUR, L.ptr(u_cur), u_cur.nbytes))
+            L.check(L.lib.b200mppi_planner_rollout(h))
+            c = np.empty(N, np.float32)
+            L.check(L.lib.b200mppi_planner_copy_out(h, L.BUF_COSTS, L.ptr(c), c.nbytes))
+            assert rel_err(c, g["costs_" + gname]).max() < 1e-4
+        finally:
+            L.lib.b200mppi_planner_destroy(h)
+    cfg = BB.Config(T=1.0, dt=0.1, num_control_rollouts=100, num_vis_state_rollouts=5, seed=1)
+    pl = BB.MPPI_Numba(cfg)
+    params = dict(dt=0.1, x0=np.array([0.0, 0.0, np.pi / 4]), xgoal=np.array([7.0, 5.0]), goal_tolerance=0.5,
+                  dist_weight=10, lambda_weight=1.0, num_opt=1, u_std=np.array([1.0, 1.0]),
+                  vrange=np.array([0.0, 2.0]), wrange=np.array([-np.pi, np.pi]),
+                  obstacle_positions=np.array([[5, 4.5], [2, 1]]), obstacle_radius=np.array([1.5, 1.0]), obs_penalty=1e6)
+    assert pl.solve() is None
+    pl.setup(params)
+    u1 = pl.solve()
+    np.testing.assert_allclose(pl.noise_samples_d.copy_to_host(), g["solve_noise1"], rtol=3e-6, atol=2e-6)
+    np.testing.assert_allclose(u1, g["solve_u1"], rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(pl.get_state_rollout(), g["solve_states1"], rtol=1e-3, atol=1e-3)
+    pl.shift_and_update(np.array([0.05, 0.06, 0.8]), g["solve_u1"], num_shifts=1)
+    np.testing.assert_allclose(pl.solve(), g["solve_u2"], rtol=2e-3, atol=5e-4)
+
+
 def test_determinism_and_checkpoint_resume(eng):
     sc = make_scenario("tdm", N=256, M=16, T=32, H=100, W=100, res=0.2, B=8, seed=6)
 

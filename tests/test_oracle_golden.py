@@ -148,3 +148,15 @@ def test_shift_keeps_tail():
     u = np.arange(10, dtype=np.float32).reshape(5, 2)
     s = MR.shift_useq(u, 2)
     assert (s[:3] == u[2:]).all() and (s[3:] == u[3:]).all()
+
+
+# ----------------------------------------------------------------------------- barebone (map-free) variant
+@pytest.mark.parametrize("gname", ["near", "far"])
+def test_barebone_rollout_matches_reference_notebook(golden_dir, gname):
+    g = load(golden_dir, "ref_barebone.npz")
+    c = MR.rollout_costs_barebone(g["obs_pos"], g["obs_r"], g["vrange"], g["wrange"], g["goal_" + gname], g["obs_cost"],
+                                  g["goal_tol"], g["lam"], g["u_std"], g["x0"], g["dt"], g["dist_weight"], g["noise"],
+                                  g["u_cur"])
+    np.testing.assert_allclose(c, g["costs_" + gname], rtol=3e-6)
+    if gname == "near":
+        assert (g["costs_near"] < 0.1 * np.median(g["costs_far"])).any()      # early exits exercised
