@@ -102,16 +102,28 @@ static int tdm_prepare_jump(b200mppi_tdm* t, cudaStream_t st) {
   const int tx = t->cfg.tdm_thread_x, ty = t->cfg.tdm_thread_y;
   const int nrow = (t->rows + tx - 1) / tx, ncol = (t->cols + ty - 1) / ty;
   const int groups = (t->num_maps + 7) / 8;
-  int segs = (4096 + tx * groups - 1) / (tx * groups);      // ~4k CTAs keep 148 SMs busy through the tail
+  // pick the segment count (<= 16) that minimises the busiest SM's load: CTAs are spread over 148 SMs,
+  // each CTA costs seg_rows rows plus ~0.3 row-equivalents for the 128-column matrix jump
+  int segs = 1;
+  {
+    double best = 1e30;
+    for (int c = 1; c <= 16 && c <= nrow; ++c) {
+      const int sr = (nrow + c - 1) / c;
+      const int nonempty = (nrow + sr - 1) / sr;
+      const long ctas = (long)tx * nonempty * groups;
+      const double load = (double)((ctas + 147) / 148) * (sr + (c > 1 ? 0.3 : 0.0));
+      if (load < best - 1e-9) { best = load; segs = c; }
+    }
+  }
   if (const char* e = getenv("B200MPPI_SAMPLE_SEGS")) segs = atoi(e);      // tuning / test hook
-  if (segs > 8) segs = 8;
+  if (segs > 16) segs = 16;
   if (segs > nrow) segs = nrow;
   if (segs < 1) segs = 1;
   const int seg_rows = (nrow + segs - 1) / segs;
   if (t->jump_d && t->jump_segs == segs && t->jump_seg_rows == seg_rows && t->jump_rows == t->rows &&
       t->jump_cols == t->cols)
     return B200MPPI_OK;
-  if (!t->jump_d) CU(cudaMalloc(&t->jump_d, (size_t)7 * 2 * 256 * sizeof(uint64_t)));
+  if (!t->jump_d) CU(cudaMalloc(&t->jump_d, (size_t)15 * 2 * 256 * sizeof(uint64_t)));
   if (segs > 1) {
     // width classes: 0 = full tile column (ncol cells), 1 = the last, narrower column
     int last_w = t->cols - (ty - 1) * ncol;

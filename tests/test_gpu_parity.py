@@ -653,6 +653,58 @@ def test_barebone_variant_vs_reference_notebook_golden(eng, golden_dir):
     np.testing.assert_allclose(pl.solve(), g["solve_u2"], rtol=2e-3, atol=5e-4)
 
 
+def test_full_size_config5_properties(eng):
+    """BASELINE config 5 at FULL size (N 8192, M 256, T 128, 1034x1034 maps) through size-independent
+    properties: run-to-run determinism, CVaR == host selection on the engine's own per-(n,m) costs,
+    sampled values drawn from the quantised bin set with the right marginal, normalised weights, clipped u,
+    and oracle parity on a slice (256 control sequences x 8 maps x 128 steps)."""
+    from bench import build_scenario
+    sc = build_scenario("c5")
+    L = eng._lib
+
+    def build():
+        cfg = eng.Config(**sc["cfg"])
+        lin, ang = eng.TDM_Numba(cfg), eng.TDM_Numba(cfg)
+        lin.set_TDM_from_PMF_grid(sc["pmf_lin"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+        ang.set_TDM_from_PMF_grid(sc["pmf_ang"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+        pl = eng.MPPI_Numba(cfg)
+        pl.setup(sc["params"], lin, ang)
+        return pl, lin, ang
+    a, alin, aang = build()
+    u1 = a.solve()
+    u2 = a.solve()
+    cnm = a.costs_nm_d.copy_to_host()
+    cv = a.costs_d.copy_to_host()
+    N, M = cnm.shape
+    assert (N, M) == (8192, 256)
+    k = MR.cvar_count(M, sc["params"]["cvar_alpha"])
+    top = np.sort(cnm, axis=1)[:, M - k:]                       # the k largest per control sequence
+    np.testing.assert_allclose(cv, top.astype(np.float64).mean(axis=1), rtol=3e-6)
+    w = a.weights_d.copy_to_host()
+    assert abs(float(w.sum(dtype=np.float64)) - 1.0) < 1e-5 and (w >= 0).all()
+    for u in (u1, u2):
+        assert np.isfinite(u).all() and (u[:, 0] >= 0).all() and (u[:, 0] <= 3).all()
+        assert (np.abs(u[:, 1]) <= np.float32(np.pi)).all()
+    # sampled maps: every value is one of the quantised bin values; marginal frequency of the top bin
+    g = alin.sample_grid_batch_d.copy_to_host()
+    q = TR.quantise_bin_values(alin.bin_values, alin.bin_values_bounds)
+    assert np.isin(g[:, 5:-5, 5:-5], q).all()
+    pad = alin.pad_cells
+    exp_top = sc["pmf_lin"][-1].astype(np.float64).mean() / 100.0
+    got_top = float((g[:8, pad:-pad, pad:-pad] == q[-1]).mean())
+    assert abs(got_top - exp_top) < 2e-3
+    # determinism: a second engine with the same seed reproduces both solves bit for bit
+    b, blin, bang = build()
+    assert (b.solve() == u1).all() and (b.solve() == u2).all()
+    # oracle parity on a slice of the second solve's inputs
+    noise = b.noise_samples_d.copy_to_host()[:256]
+    gl, ga = blin.sample_grid_batch_d.copy_to_host()[:8], bang.sample_grid_batch_d.copy_to_host()[:8]
+    want = oracle_rollout_costs(sc, blin, bang, noise, u1, grids=(gl, ga))     # u1 was the warm start of solve 2
+    got = b.costs_nm_d.copy_to_host()[:256, :8]
+    r = rel_err(got, want)
+    assert (r < 1e-4).mean() >= 0.99 and np.median(r) < 2e-6, ((r < 1e-4).mean(), np.median(r))
+
+
 def test_determinism_and_checkpoint_resume(eng):
     sc = make_scenario("tdm", N=256, M=16, T=32, H=100, W=100, res=0.2, B=8, seed=6)
 
