@@ -102,19 +102,9 @@ static int tdm_prepare_jump(b200mppi_tdm* t, cudaStream_t st) {
   const int tx = t->cfg.tdm_thread_x, ty = t->cfg.tdm_thread_y;
   const int nrow = (t->rows + tx - 1) / tx, ncol = (t->cols + ty - 1) / ty;
   const int groups = (t->num_maps + 7) / 8;
-  // pick the segment count (<= 16) that minimises the busiest SM's load: CTAs are spread over 148 SMs,
-  // each CTA costs seg_rows rows plus ~0.3 row-equivalents for the 128-column matrix jump
-  int segs = 1;
-  {
-    double best = 1e30;
-    for (int c = 1; c <= 16 && c <= nrow; ++c) {
-      const int sr = (nrow + c - 1) / c;
-      const int nonempty = (nrow + sr - 1) / sr;
-      const long ctas = (long)tx * nonempty * groups;
-      const double load = (double)((ctas + 147) / 148) * (sr + (c > 1 ? 0.3 : 0.0));
-      if (load < best - 1e-9) { best = load; segs = c; }
-    }
-  }
+  // enough CTAs (~4k, i.e. several waves of the 5 resident CTAs per SM) to keep 148 SMs busy through the
+  // tail; measured on config 5: 1 / 2 / 4 / 8 segments -> 1.63 / 1.50 / 1.37 / 1.32 ms
+  int segs = (4096 + tx * groups - 1) / (tx * groups);
   if (const char* e = getenv("B200MPPI_SAMPLE_SEGS")) segs = atoi(e);      // tuning / test hook
   if (segs > 16) segs = 16;
   if (segs > nrow) segs = nrow;
