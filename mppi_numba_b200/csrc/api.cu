@@ -66,7 +66,6 @@ struct b200mppi_tdm {
   uint64_t* thr_d = nullptr;    // device copy of the q(v) breakpoints for thr_alpha
   double thr_alpha = -1.0;
   bool thr_ok = false;
-  uint32_t est_mul = 0;
   uint64_t sig = 0;             // identifies the generator-state history (equal sig <=> equal states)
 };
 
@@ -79,11 +78,9 @@ static inline uint64_t mix_sig(uint64_t h, uint64_t v) {
 
 static int tdm_prepare_thresholds(b200mppi_tdm* t, double alpha, cudaStream_t st) {
   if (t->thr_alpha == alpha && t->thr_d) return B200MPPI_OK;
-  uint64_t T[136];
-  uint32_t mul = 0;
-  t->thr_ok = t->pmf_valid && build_sample_thresholds(alpha, t->min_total, T, &mul);
+  uint64_t T[256];
+  t->thr_ok = t->pmf_valid && build_sample_thresholds(alpha, t->min_total, T);
   t->thr_alpha = alpha;
-  t->est_mul = mul;
   if (!t->thr_d) CU(cudaMalloc(&t->thr_d, sizeof(T)));
   if (t->thr_ok) {
     // pageable source: the copy is staged by the driver before the call returns
@@ -139,7 +136,7 @@ static void fill_v2(const b200mppi_tdm* t, SampleGridsV2Args& a, int slot) {
   a.t[slot].states_out = t->states_alt;
   a.t[slot].qvals = t->qvals; a.t[slot].bpad = t->bpad;
   if (slot == 0) {
-    a.thresholds = t->thr_d; a.est_mul = t->est_mul; a.jump = t->jump_d;
+    a.thresholds = t->thr_d; a.jump = t->jump_d;
     a.rows = t->rows; a.cols = t->cols; a.grid_rows = t->cfg.max_map_rows; a.pitch = t->pitch;
     a.tx = t->cfg.tdm_thread_x; a.ty = t->cfg.tdm_thread_y; a.num_maps = t->num_maps;
     a.segs = t->jump_segs; a.seg_rows = t->jump_seg_rows;

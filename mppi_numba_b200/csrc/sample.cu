@@ -10,6 +10,7 @@
 // int8 loads per cell per map as the reference does.
 #include <cmath>
 #include <cstring>
+#include <vector>
 #include "kernels.h"
 
 namespace b200 {
@@ -84,9 +85,10 @@ void launch_sample_grids(const SampleGridsArgs& a, cudaStream_t st) {
 //     re-reads B strided int8 per cell per map from global memory);
 //   * the threshold q = int8(ceil(f64(f32(v*2^-53))*100*alpha)) is obtained WITHOUT the five float64 /
 //     conversion (XU-pipe) instructions: q(v) is a monotone step function of the 53-bit draw v, so the
-//     host tabulates its breakpoints T[k] = min{v : q(v) >= k} with the exact float arithmetic and the
-//     kernel does an integer estimate + <= 3 table compares (the host verifies est <= q <= est+3 at
-//     every breakpoint, otherwise the generic kernel is used);
+//     host tabulates its breakpoints T[k] = min{v : q(v) >= k} with the exact float arithmetic and folds
+//     them into a 256-entry table over the top 8 bits of v: (q at the bucket start, the one breakpoint
+//     inside the bucket) -- one shared-memory load and one 64-bit compare per draw (the host verifies that
+//     no bucket holds two breakpoints, otherwise the generic kernel is used);
 //   * the first bin whose cumulative mass reaches q is found with a SIMD-in-register byte compare and
 //     one POPC instead of a loop;
 //   * sampled bytes are staged per row in shared memory and written with coalesced 16-byte stores;
@@ -124,8 +126,8 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
   const int stage_pitch = (a.cols + 15) & ~15;
   unsigned char* s_cum = smem;                               // [NT][row_bytes_al]
   unsigned char* s_stage = s_cum + NT * row_bytes_al;        // [NT][GM][stage_pitch]
-  uint64_t* s_T = reinterpret_cast<uint64_t*>(s_stage + NT * SG_GM * stage_pitch);   // [136]
-  unsigned char* s_q = reinterpret_cast<unsigned char*>(s_T + 136);                  // [NT][128]
+  uint64_t* s_T = reinterpret_cast<uint64_t*>(s_stage + NT * SG_GM * stage_pitch);   // [256] bucket table
+  unsigned char* s_q = reinterpret_cast<unsigned char*>(s_T + 256);                  // [NT][128]
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int tiy = tid % a.ty, mloc = tid / a.ty;
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
   const int m = blockIdx.y * SG_GM + mloc;
   const bool active = (mloc < SG_GM) && (m < a.num_maps);
 
-  for (int i = tid; i < 136; i += nthreads) s_T[i] = a.thresholds[i];
+  for (int i = tid; i < 256; i += nthreads) s_T[i] = a.thresholds[i];
   for (int i = tid; i < 128; i += nthreads) {
     s_q[i] = (unsigned char)a.t[0].qvals[i];
     if (NT == 2) s_q[128 + i] = (unsigned char)a.t[1].qvals[i];
@@ -169,7 +171,6 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
       xoro_jump(s, reinterpret_cast<const ulonglong2*>(a.jump) + ((size_t)(seg - 1) * 2 + cls) * 128);
     }
   }
-  const uint32_t c32 = a.est_mul;
 
   for (int ri = r0; ri < r1; ++ri) {
     __syncthreads();                                          // previous row's stage fully drained
@@ -186,8 +187,9 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
       // Returns the sampled value byte of each TDM; the caller stores them AFTER a group of cells so that
       // the shared-memory loads of the whole group are independent of the byte stores (ILP).
       auto cell = [&](int ci, uint64_t v, uint32_t (&outv)[NT]) {
-        const uint32_t est = __umulhi((uint32_t)(v >> 21), c32) >> 25;
-        const uint32_t q = est + (v >= s_T[est + 1]) + (v >= s_T[est + 2]) + (v >= s_T[est + 3]);
+        // bucket of the draw's top 8 bits: q at the bucket start and the single breakpoint inside it
+        const uint64_t e = s_T[(uint32_t)(v >> 45)];
+        const uint32_t q = (uint32_t)(e >> 56) + (v >= (e & 0x00FFFFFFFFFFFFFFULL));
         const uint32_t qq = q * 0x01010101u;
 #pragma unroll
         for (int k = 0; k < NT; ++k) {
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
 size_t sample_grids_v2_smem(const SampleGridsV2Args& a, int nt) {
   const int row_bytes_al = (a.cols * a.t[0].bpad + 15) & ~15;
   const int stage_pitch = (a.cols + 15) & ~15;
-  return (size_t)nt * row_bytes_al + (size_t)nt * SG_GM * stage_pitch + 136 * 8 + (size_t)nt * 128;
+  return (size_t)nt * row_bytes_al + (size_t)nt * SG_GM * stage_pitch + 256 * 8 + (size_t)nt * 128;
 }
 
 template <int NT>
@@ -348,69 +350,35 @@ static inline int q_of_v(uint64_t v, double alpha) {
   return (int)(int8_t)(int16_t)c;
 }
 
-bool build_sample_thresholds(double alpha, int q_cap, uint64_t* T /*[136]*/, uint32_t* est_mul) {
+bool build_sample_thresholds(double alpha, int q_cap, uint64_t* B /*[256]*/) {
   if (!(alpha >= 0.0) || !(alpha * 100.0 <= 127.0)) return false;
   const uint64_t VMAX = (1ULL << 53) - 1;
   const int qmax = q_of_v(VMAX, alpha);
   if (qmax < 0 || qmax > q_cap || qmax > 127 || q_of_v(0, alpha) != 0) return false;
-  for (int k = 0; k < 136; ++k) T[k] = ~0ULL;
+  std::vector<uint64_t> T((size_t)qmax + 2, ~0ULL);
   T[0] = 0;
   for (int k = 1; k <= qmax; ++k) {                   // smallest v with q(v) >= k (q monotone in v)
     uint64_t lo = 0, hi = VMAX;                       // q(lo) < k <= q(hi)
-    if (q_of_v(0, alpha) >= k) { T[k] = 0; continue; }
     while (hi - lo > 1) {
       const uint64_t mid = lo + (hi - lo) / 2;
       if (q_of_v(mid, alpha) >= k) hi = mid; else lo = mid;
     }
     T[k] = hi;
   }
-  const double c = std::floor(alpha * 100.0 * 33554432.0);          // 100*alpha * 2^25
-  if (!(c >= 0.0 && c < 4294967296.0)) return false;
-  const uint32_t c32 = (uint32_t)c;
-  auto est = [&](uint64_t v) { return (uint32_t)(((uint64_t)(uint32_t)(v >> 21) * c32) >> 57); };
-  // est is monotone; q == k on [T[k], T[k+1]).  Need est <= k and est >= k-3 on that interval.
-  for (int k = 0; k <= qmax; ++k) {
-    if (T[k] == ~0ULL) continue;
-    const uint64_t first = T[k];
-    const uint64_t last = (k < qmax) ? T[k + 1] - 1 : VMAX;
-    if (last < first) continue;                        // empty level
-    if ((int)est(last) > k || (int)est(first) + 3 < k) return false;
+  // bucket b covers v in [b << 45, (b+1) << 45): entry = q(start) << 56 | first breakpoint above start
+  // (2^53 = "none").  Valid iff at most one breakpoint lies strictly inside each bucket.
+  for (int b = 0; b < 256; ++b) {
+    const uint64_t start = (uint64_t)b << 45, end = start + (1ULL << 45);
+    const int qb = q_of_v(start, alpha);
+    uint64_t next = 1ULL << 53;
+    int inside = 0;
+    for (int k = 1; k <= qmax; ++k)
+      if (T[k] > start && T[k] < end) { if (!inside) next = T[k]; ++inside; }
+    if (inside > 1 || qb < 0 || qb > 127) return false;
+    if (inside == 1 && q_of_v(next, alpha) != qb + 1) return false;     // the breakpoint raises q by exactly one
+    B[b] = ((uint64_t)qb << 56) | next;
   }
-  *est_mul = c32;
   return true;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Host: numba-compatible generator states.  State 0 = splitmix64(seed) in both words; state i is
-// state i-1 jumped 2^64 steps (random.py:47-69,103-126,226-241).
-static inline uint64_t rotl_h(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
-static inline void next_h(uint64_t& s0, uint64_t& s1) {
-  uint64_t t = s1 ^ s0;
-  s0 = rotl_h(s0, 55) ^ t ^ (t << 14);
-  s1 = rotl_h(t, 36);
-}
-static inline void jump_h(uint64_t& s0, uint64_t& s1) {
-  static const uint64_t JUMP[2] = {0xbeac0467eba5facbULL, 0xd86b048b86aa9922ULL};
-  uint64_t a0 = 0, a1 = 0;
-  for (int i = 0; i < 2; ++i)
-    for (int b = 0; b < 64; ++b) {
-      if (JUMP[i] & (1ULL << b)) { a0 ^= s0; a1 ^= s1; }
-      next_h(s0, s1);
-    }
-  s0 = a0; s1 = a1;
-}
-
-void create_xoroshiro_states(uint64_t* out, int64_t first, int64_t count, uint64_t seed) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ULL;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-  z = z ^ (z >> 31);
-  uint64_t s0 = z, s1 = z;
-  for (int64_t i = 0; i < first; ++i) jump_h(s0, s1);
-  for (int64_t i = 0; i < count; ++i) {
-    out[2 * i] = s0; out[2 * i + 1] = s1;
-    jump_h(s0, s1);
-  }
 }
 
 }  // namespace b200
