@@ -381,4 +381,37 @@ bool build_sample_thresholds(double alpha, int q_cap, uint64_t* B /*[256]*/) {
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Host: numba-compatible generator states.  State 0 = splitmix64(seed) in both words; state i is
+// state i-1 jumped 2^64 steps (random.py:47-69,103-126,226-241).
+static inline uint64_t rotl_h(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static inline void next_h(uint64_t& s0, uint64_t& s1) {
+  uint64_t t = s1 ^ s0;
+  s0 = rotl_h(s0, 55) ^ t ^ (t << 14);
+  s1 = rotl_h(t, 36);
+}
+static inline void jump_h(uint64_t& s0, uint64_t& s1) {
+  static const uint64_t JUMP[2] = {0xbeac0467eba5facbULL, 0xd86b048b86aa9922ULL};
+  uint64_t a0 = 0, a1 = 0;
+  for (int i = 0; i < 2; ++i)
+    for (int b = 0; b < 64; ++b) {
+      if (JUMP[i] & (1ULL << b)) { a0 ^= s0; a1 ^= s1; }
+      next_h(s0, s1);
+    }
+  s0 = a0; s1 = a1;
+}
+
+void create_xoroshiro_states(uint64_t* out, int64_t first, int64_t count, uint64_t seed) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z = z ^ (z >> 31);
+  uint64_t s0 = z, s1 = z;
+  for (int64_t i = 0; i < first; ++i) jump_h(s0, s1);
+  for (int64_t i = 0; i < count; ++i) {
+    out[2 * i] = s0; out[2 * i + 1] = s1;
+    jump_h(s0, s1);
+  }
+}
+
 }  // namespace b200
