@@ -147,29 +147,45 @@ __device__ void merge_partials(const float* __restrict__ parts, int count, int T
     s_scale[i] = (b == INFINITY) ? 0.0f : softmax_weight(b, beta, lambda);
   }
   __syncthreads();
+  float S = 0.0f;                                   // block reduction in a fixed order (deterministic)
+  for (int i = threadIdx.x; i < count; i += blockDim.x) S = fmaf(parts[(size_t)i * (2 * T + 2) + 1], s_scale[i], S);
+  S = warp_sum(S);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = S;
+  __syncthreads();
   if (threadIdx.x == 0) {
-    float S = 0.0f;
-    for (int i = 0; i < count; ++i) S = fmaf(parts[(size_t)i * (2 * T + 2) + 1], s_scale[i], S);
+    float t = 0.0f;
+    for (int i = 0; i < UPD_THREADS / 32; ++i) t += s_red[i];
     *out_beta = beta;
-    *out_S = S;
+    *out_S = t;
   }
   __syncthreads();
 }
 
 constexpr int MAX_PARTS = 512;
 
-// CTA partials -> this rank's partial (rank_partial).  One CTA.
+// CTA partials -> this rank's partial (rank_partial).  Grid = ceil(2T/32) CTAs: every CTA derives the merge
+// scales itself (<= 296 exps) and reduces 32 columns; 256 threads = 32 columns x 8 slices of the partials
+// (coalesced 128-byte rows), slices combined through shared memory.
 __global__ void __launch_bounds__(UPD_THREADS) update_rank_kernel(const UpdateArgs a) {
   __shared__ float s_scale[MAX_PARTS];
   __shared__ float s_bS[2];
+  __shared__ float s_acc[8][33];
   merge_partials(a.cta_partials, a.num_ctas, a.T, a.lambda, &s_bS[0], &s_bS[1], s_scale);
   const int stride = 2 * a.T + 2;
-  for (int j = threadIdx.x; j < 2 * a.T; j += blockDim.x) {
-    float v = 0.0f;
-    for (int i = 0; i < a.num_ctas; ++i) v = fmaf(a.cta_partials[(size_t)i * stride + 2 + j], s_scale[i], v);
-    a.rank_partial[2 + j] = v;
+  const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + col;
+  float v = 0.0f;
+  if (j < 2 * a.T)
+    for (int i = slice; i < a.num_ctas; i += 8) v = fmaf(a.cta_partials[(size_t)i * stride + 2 + j], s_scale[i], v);
+  s_acc[slice][col] = v;
+  __syncthreads();
+  if (slice == 0 && j < 2 * a.T) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s_acc[k][col];
+    a.rank_partial[2 + j] = t;
   }
-  if (threadIdx.x == 0) { a.rank_partial[0] = s_bS[0]; a.rank_partial[1] = s_bS[1]; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { a.rank_partial[0] = s_bS[0]; a.rank_partial[1] = s_bS[1]; }
 }
 
 // gathered rank partials -> u_cur (clipped), plus this rank's normalised weights
@@ -203,7 +219,7 @@ __global__ void __launch_bounds__(UPD_THREADS) update_apply_kernel(const UpdateA
 
 void launch_update_partial(const UpdateArgs& a, cudaStream_t st) {
   update_partial_kernel<<<a.num_ctas, UPD_THREADS, 0, st>>>(a);
-  update_rank_kernel<<<1, UPD_THREADS, 0, st>>>(a);
+  update_rank_kernel<<<(2 * a.T + 31) / 32, UPD_THREADS, 0, st>>>(a);
 }
 
 void launch_update_finish(const UpdateArgs& a, const float* gathered, int count, cudaStream_t st) {

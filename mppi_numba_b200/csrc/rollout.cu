@@ -217,6 +217,8 @@ __device__ __forceinline__ float key_float(uint32_t k) {   // inverse of float_k
 
 constexpr int CVAR_MAX_PER_LANE = 32;   // M <= 1024 (the reference's one-block limit, mppi.py:199)
 
+// PER = values held per lane (compile time: the select loop is fully unrolled over them)
+template <int PER>
 __global__ void __launch_bounds__(128) cvar_kernel(const float* __restrict__ costs_nm,
                                                    float* __restrict__ costs, int N, int Mc, int chunks, int numel) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -225,17 +227,17 @@ __global__ void __launch_bounds__(128) cvar_kernel(const float* __restrict__ cos
   const int M = Mc * chunks;                                  // values per control sequence
   const size_t chunk_stride = (size_t)N * Mc;
   const float* row = costs_nm + (size_t)warp * Mc;
-  float v[CVAR_MAX_PER_LANE];
-  const int per = (M + 31) >> 5;
+  float v[PER];
+  constexpr int per = PER;
 #pragma unroll
-  for (int i = 0; i < CVAR_MAX_PER_LANE; ++i) {
+  for (int i = 0; i < PER; ++i) {
     const int j = i * 32 + lane;
-    v[i] = (i < per && j < M) ? row[(size_t)(j / Mc) * chunk_stride + (j % Mc)] : -INFINITY;
+    v[i] = (j < M) ? row[(size_t)(j / Mc) * chunk_stride + (j % Mc)] : -INFINITY;
   }
   float sum = 0.0f;
   if (numel >= M) {
 #pragma unroll
-    for (int i = 0; i < CVAR_MAX_PER_LANE; ++i) if (i < per && i * 32 + lane < M) sum += v[i];
+    for (int i = 0; i < PER; ++i) if (i * 32 + lane < M) sum += v[i];
     sum = warp_sum(sum);
   } else {
     // find the key of the numel-th largest value
@@ -244,8 +246,7 @@ __global__ void __launch_bounds__(128) cvar_kernel(const float* __restrict__ cos
       const uint32_t cand = prefix | (1u << bit);
       int cnt = 0;
 #pragma unroll
-      for (int i = 0; i < CVAR_MAX_PER_LANE; ++i)
-        if (i < per) cnt += (float_key(v[i]) >= cand) ? 1 : 0;
+      for (int i = 0; i < PER; ++i) cnt += (float_key(v[i]) >= cand) ? 1 : 0;
       cnt = __reduce_add_sync(0xffffffffu, cnt);
       if (cnt >= numel) prefix = cand;
     }
@@ -253,8 +254,8 @@ __global__ void __launch_bounds__(128) cvar_kernel(const float* __restrict__ cos
     // (all holders of the k-th key hold the same float: the key map is a bijection)
     int greater = 0;
 #pragma unroll
-    for (int i = 0; i < CVAR_MAX_PER_LANE; ++i) {
-      if (i < per && float_key(v[i]) > prefix) { sum += v[i]; ++greater; }
+    for (int i = 0; i < PER; ++i) {
+      if (float_key(v[i]) > prefix) { sum += v[i]; ++greater; }
     }
     sum = warp_sum(sum);
     greater = __reduce_add_sync(0xffffffffu, greater);
@@ -270,7 +271,14 @@ void launch_cvar(const float* costs_nm, float* costs, int N, int Mc, int chunks,
   if (numel > M) numel = M;
   const int threads = 128;
   const int warps_per_block = threads / 32;
-  cvar_kernel<<<(N + warps_per_block - 1) / warps_per_block, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
+  const unsigned blocks = (unsigned)((N + warps_per_block - 1) / warps_per_block);
+  const int per = (M + 31) / 32;
+  if (per <= 1) cvar_kernel<1><<<blocks, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
+  else if (per <= 2) cvar_kernel<2><<<blocks, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
+  else if (per <= 4) cvar_kernel<4><<<blocks, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
+  else if (per <= 8) cvar_kernel<8><<<blocks, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
+  else if (per <= 16) cvar_kernel<16><<<blocks, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
+  else cvar_kernel<32><<<blocks, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
 }
 
 // ---------------------------------------------------------------------------------------------
