@@ -216,6 +216,53 @@ def test_semantic_grid_setter_vs_reference_golden(eng, golden_dir):
             assert (tdm.sample_grids(0.9).copy_to_host() == g[key + "_grid1"]).all(), key
 
 
+def test_sampling_generic_path_ill_formed_pmf_and_large_alpha(eng):
+    """PMF columns that do not reach 100 and alpha_dyn > 1 (thresholds above every cumulative sum, int8 wrap
+    above 127) take the generic kernel: cells whose column never reaches the threshold KEEP their previous
+    content, like the reference (terrain.py:683-694).  Bit-exact against the oracle."""
+    rng = np.random.default_rng(31)
+    B, H, W = 6, 30, 26
+    pmf = rng.integers(0, 18, (B, H, W)).astype(np.int8)            # column sums 0..102, mostly < 100
+    cfg = eng.Config(T=1.0, dt=0.1, num_grid_samples=5, num_control_rollouts=100, seed=3, max_map_dim=(36, 34),
+                     tdm_sample_thread_dim=(4, 5), max_speed_padding=5.0, use_tdm=True)
+    tdm = eng.TDM_Numba(cfg)
+    d = dict(res=0.5, xlimits=np.array([0.0, W * 0.5]), ylimits=np.array([0.0, H * 0.5]),
+             bin_values=np.array([0.0, 0.2, 0.4, 0.6, 0.8, 1.0]), bin_values_bounds=np.array([0.0, 1.0]),
+             det_dynamics_cvar_alpha=1.0)
+    tdm.set_TDM_from_PMF_grid(pmf, d)
+    padded = tdm.pmf_grid_d.copy_to_host()
+    st = TR.sample_rng_states(cfg.seed, 5, cfg.tdm_sample_thread_dim, False)
+    want = np.zeros(tdm.sample_grid_batch_d.shape, dtype=np.int8)
+    for alpha in (1.0, 1.5, 0.3):
+        got = tdm.sample_grids(alpha).copy_to_host()
+        TR.sample_grids(want, padded, st, tdm.bin_values, tdm.bin_values_bounds, alpha, cfg.tdm_sample_thread_dim, 5)
+        assert (got == want).all(), alpha
+        assert (tdm.rng_states_d.copy_to_host() == st).all(), alpha
+
+
+def test_long_horizon_uses_smaller_window(eng):
+    """T = 800 steps (> 700): the windowed kernel switches to its 224-row variant; parity with the oracle."""
+    sc = make_scenario("tdm", N=128, M=4, T=800, H=200, W=200, res=0.2, B=5, seed=14, warm_start=True)
+    cfg = eng.Config(**sc["cfg"])
+    assert cfg.num_steps == 800
+    lin, ang = eng.TDM_Numba(cfg), eng.TDM_Numba(cfg)
+    lin.set_TDM_from_PMF_grid(sc["pmf_lin"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+    ang.set_TDM_from_PMF_grid(sc["pmf_ang"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+    pl = eng.MPPI_Numba(cfg)
+    pl.setup(sc["params"], lin, ang)
+    pl.u_cur_d.copy_to_device(sc["u0"])
+    pl.move_mppi_task_vars_to_device()
+    L = eng._lib
+    lin.sample_grids(1.0)
+    ang.sample_grids(1.0)
+    L.check(L.lib.b200mppi_planner_sample_noise(pl._handle))
+    L.check(L.lib.b200mppi_planner_rollout(pl._handle))
+    want = oracle_rollout_costs(sc, lin, ang, pl.noise_samples_d.copy_to_host(), pl.u_cur_d.copy_to_host())
+    r = rel_err(pl.costs_nm_d.copy_to_host(), want)
+    assert (r < 1e-4).mean() >= 0.98 and np.median(r) < 5e-6, ((r < 1e-4).mean(), float(np.median(r)))
+    assert pl.solve().shape == (800, 2)
+
+
 def test_sampling_bit_exact_vs_oracle_config3_shape(eng):
     """512x512 map, 12 bins with non-representable bin values (compiled float64 truncation), M=64,
     16x16 thread tiles: bit-exact against the oracle's restatement of sample_grids_numba."""
