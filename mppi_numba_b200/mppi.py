@@ -44,6 +44,8 @@ class MPPI_Numba(object):
         self.device, self.rank, self.world_size = int(device), int(rank), int(world_size)
         self.process_group = process_group
         self._handle = None
+        self._pod = _lib.ParamsPOD()
+        self._pod_f32 = np.frombuffer(self._pod, dtype=np.float32, count=19)     # dt .. dist_weight
         self._gathered = None            # torch tensor (world_size, 2T+2) for the exchange
         self._partial_t = None
         self._stream = None
@@ -172,21 +174,20 @@ class MPPI_Numba(object):
         space replaces the reference's seven cuda.to_device allocations per solve, mppi.py:214-234).
         Casts to float32 exactly where the reference casts."""
         p = self.params
-        f = np.float32
-        pod = _lib.ParamsPOD()
-        pod.dt = f(p['dt'])
-        pod.x0 = _lib.c_floats(np.asarray(p['x0']).astype(f), 3)
-        pod.xgoal = _lib.c_floats(np.asarray(p['xgoal']).astype(f), 2)
-        pod.goal_tolerance = f(p['goal_tolerance'])
-        pod.v_post_rollout = f(p['v_post_rollout'])
-        pod.cvar_alpha = f(p['cvar_alpha'])
-        pod.lambda_weight = f(p['lambda_weight'])
-        pod.u_std = _lib.c_floats(np.asarray(p['u_std']).astype(f), 2)
-        pod.vrange = _lib.c_floats(np.asarray(p['vrange']).astype(f), 2)
-        pod.wrange = _lib.c_floats(np.asarray(p['wrange']).astype(f), 2)
-        pod.obs_penalty = f(p.get('obs_penalty', DEFAULT_OBS_COST))
-        pod.unknown_penalty = f(p.get('unknown_penalty', DEFAULT_UNKNOWN_COST))
-        pod.dist_weight = f(p.get('dist_weight', DEFAULT_DIST_WEIGHT))
+        pod, v = self._pod, self._pod_f32          # persistent POD + float32 view of its 19 leading floats
+        v[0] = p['dt']
+        v[1:4] = p['x0']
+        v[4:6] = p['xgoal']
+        v[6] = p['goal_tolerance']
+        v[7] = p['v_post_rollout']
+        v[8] = p['cvar_alpha']
+        v[9] = p['lambda_weight']
+        v[10:12] = p['u_std']
+        v[12:14] = p['vrange']
+        v[14:16] = p['wrange']
+        v[16] = p.get('obs_penalty', DEFAULT_OBS_COST)
+        v[17] = p.get('unknown_penalty', DEFAULT_UNKNOWN_COST)
+        v[18] = p.get('dist_weight', DEFAULT_DIST_WEIGHT)
         pod.num_opt = int(p['num_opt'])
         pod.alpha_dyn = float(p.get('alpha_dyn', 1.0))
         check(lib.b200mppi_planner_set_tdms(self._handle, self.lin_tdm._handle, self.ang_tdm._handle))
