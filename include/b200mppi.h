@@ -108,6 +108,18 @@ int b200mppi_tdm_set_pmf(b200mppi_tdm* tdm, const int8_t* pmf_padded, int32_t nu
                          int32_t rows, int32_t cols, const float* bin_values,
                          const float bounds[2], float res, const float padded_xlimits[2],
                          const float padded_ylimits[2]);
+/* The one-map modes' PMF preprocessing of set_TDM_from_PMF_grid ON THE DEVICE (terrain.py:408-495 fused with
+ * the crop + zero-traction padding of :511-543): raw int8 PMF (B, H, W) in percent -> per cell the mean
+ * (alpha == 1) or the expectation over the worst alpha tail -> one-hot PMF at the first bin >= it
+ * (MODE_DET_DYN) or nominal PMF + int8 worst-case speed map (MODE_SPEED_MAP); the top-left keep_rows x
+ * keep_cols cells are kept and surrounded by `pad` padding cells.  Ends like set_pmf (+ set_risk_map).
+ * Optional host outputs: the padded PMF (B, keep_rows+2pad, keep_cols+2pad), the padded risk map, and the
+ * number of raw columns that do not sum to 100 (the reference prints a warning for them). */
+int b200mppi_tdm_set_pmf_collapsed(b200mppi_tdm* tdm, const int8_t* pmf_raw, int32_t num_bins, int32_t rows,
+                                   int32_t cols, int32_t keep_rows, int32_t keep_cols, int32_t pad,
+                                   const float* bin_values, const float bounds[2], float res,
+                                   const float padded_xlimits[2], const float padded_ylimits[2], double alpha,
+                                   int8_t* pmf_padded_out, int8_t* risk_padded_out, int32_t* bad_columns_out);
 /* Override the int8 value written for each bin (default: terrain.py:689 evaluated with float32
  * bin values as set_TDM_from_PMF_grid uploads them).  set_TDM_from_semantic_grid uploads the
  * caller's bin_values UNCAST (terrain.py:331-332), so with float64 inputs Numba evaluates the same

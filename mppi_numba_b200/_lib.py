@@ -56,6 +56,7 @@ def _load():
         "b200mppi_tdm_destroy": (C.c_int, [P]),
         "b200mppi_tdm_set_stream": (C.c_int, [P, P]),
         "b200mppi_tdm_set_pmf": (C.c_int, [P, P, I32, I32, I32, P, P, F, P, P]),
+        "b200mppi_tdm_set_pmf_collapsed": (C.c_int, [P, P, I32, I32, I32, I32, I32, I32, P, P, F, P, P, D, P, P, C.POINTER(I32)]),
         "b200mppi_tdm_set_bin_quantisation": (C.c_int, [P, P, I32]),
         "b200mppi_tdm_sample_grid_view": (C.c_int, [P, C.POINTER(P), C.POINTER(I32)]),
         "b200mppi_tdm_set_masks": (C.c_int, [P, P, P, I32, I32]),

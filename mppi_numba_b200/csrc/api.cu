@@ -325,6 +325,62 @@ extern "C" int b200mppi_tdm_set_pmf(b200mppi_tdm* t, const int8_t* pmf, int32_t 
   return B200MPPI_OK;
 }
 
+extern "C" int b200mppi_tdm_set_pmf_collapsed(b200mppi_tdm* t, const int8_t* raw, int32_t B, int32_t H, int32_t W,
+                                              int32_t keep_r, int32_t keep_c, int32_t pad, const float* bin_values,
+                                              const float bounds[2], float res, const float pxl[2], const float pyl[2],
+                                              double alpha, int8_t* pmf_out, int8_t* risk_out, int32_t* bad_out) {
+  if (!t || !raw || !bin_values || !bounds || !pxl || !pyl) return fail(B200MPPI_EINVAL, "set_pmf_collapsed: null argument");
+  if (t->cfg.mode != B200MPPI_MODE_DET_DYN && t->cfg.mode != B200MPPI_MODE_SPEED_MAP)
+    return fail(B200MPPI_ESTATE, "set_pmf_collapsed: only for the one-map modes");
+  if (B < 1 || B > 127 || H < 1 || W < 1 || keep_r < 1 || keep_c < 1 || keep_r > H || keep_c > W || pad < 0 ||
+      !(alpha > 0.0 && alpha <= 1.0))
+    return fail(B200MPPI_EINVAL, "set_pmf_collapsed: bad shape / alpha");
+  const int Hp = keep_r + 2 * pad, Wp = keep_c + 2 * pad;
+  if (Hp > t->cfg.max_map_rows || Wp > t->cfg.max_map_cols)
+    return fail(B200MPPI_EINVAL, "set_pmf_collapsed: padded map larger than max_map_dim");
+  CU(cudaSetDevice(t->cfg.device));
+  const bool speed = t->cfg.mode == B200MPPI_MODE_SPEED_MAP;
+  const size_t raw_bytes = (size_t)B * H * W, out_bytes = (size_t)B * Hp * Wp;
+  int8_t* raw_d = nullptr; float* bv_d = nullptr; int* bad_d = nullptr;
+  CU(cudaMalloc(&raw_d, raw_bytes));
+  CU(cudaMalloc(&bv_d, (size_t)B * sizeof(float)));
+  CU(cudaMalloc(&bad_d, sizeof(int)));
+  std::vector<int8_t> host_out(out_bytes);
+  int rc = B200MPPI_OK;
+  do {
+    if (out_bytes > t->pmf_cap) { cudaFree(t->pmf); t->pmf = nullptr; if (cudaMalloc(&t->pmf, out_bytes) != cudaSuccess) { rc = fail(B200MPPI_ENOMEM, "set_pmf_collapsed: cudaMalloc"); break; } t->pmf_cap = out_bytes; }
+    const int rpitch = round_up(Wp, 16);
+    if (speed) {
+      const size_t rbytes = (size_t)Hp * rpitch;
+      if (rbytes > t->risk_cap) { cudaFree(t->risk); t->risk = nullptr; if (cudaMalloc(&t->risk, rbytes) != cudaSuccess) { rc = fail(B200MPPI_ENOMEM, "set_pmf_collapsed: cudaMalloc"); break; } t->risk_cap = rbytes; }
+      cudaMemsetAsync(t->risk, 0, rbytes, t->stream);
+    }
+    cudaMemcpyAsync(raw_d, raw, raw_bytes, cudaMemcpyHostToDevice, t->stream);
+    cudaMemcpyAsync(bv_d, bin_values, (size_t)B * sizeof(float), cudaMemcpyHostToDevice, t->stream);
+    cudaMemsetAsync(bad_d, 0, sizeof(int), t->stream);
+    launch_collapse_pad(raw_d, t->pmf, speed ? t->risk : nullptr, bad_d, bv_d, B, H, W, keep_r, keep_c, pad, rpitch, alpha,
+                        bounds[0], bounds[1] - bounds[0], t->cfg.mode, t->stream);
+    t->launches++;
+    int bad = 0;
+    cudaMemcpyAsync(&bad, bad_d, sizeof(int), cudaMemcpyDeviceToHost, t->stream);
+    cudaMemcpyAsync(host_out.data(), t->pmf, out_bytes, cudaMemcpyDeviceToHost, t->stream);
+    if (speed && risk_out)
+      cudaMemcpy2DAsync(risk_out, Wp, t->risk, rpitch, Wp, Hp, cudaMemcpyDeviceToHost, t->stream);
+    if (cudaStreamSynchronize(t->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+      rc = fail(B200MPPI_ECUDA, "set_pmf_collapsed: CUDA error");
+      break;
+    }
+    if (bad_out) *bad_out = bad;
+    if (speed) t->risk_set = true;
+  } while (0);
+  cudaFree(raw_d); cudaFree(bv_d); cudaFree(bad_d);
+  if (rc) return rc;
+  if (pmf_out) std::memcpy(pmf_out, host_out.data(), out_bytes);
+  // the collapsed PMF is already resident in t->pmf: finish exactly like set_pmf (cumulative table, bin
+  // quantisation, validity, geometry) from the host copy
+  return b200mppi_tdm_set_pmf(t, host_out.data(), B, Hp, Wp, bin_values, bounds, res, pxl, pyl);
+}
+
 extern "C" int b200mppi_tdm_set_bin_quantisation(b200mppi_tdm* t, const int8_t* qvals, int32_t n) {
   if (!t || !qvals) return fail(B200MPPI_EINVAL, "set_bin_quantisation: null argument");
   if (!t->pmf_set || n != t->B) return fail(B200MPPI_EINVAL, "set_bin_quantisation: call after set_pmf with num_bins values");

@@ -40,6 +40,10 @@ void launch_sample_grids_v2(const SampleGridsV2Args& a, int nt, cudaStream_t st)
 void launch_build_cum(const int8_t* pmf, int8_t* cum, int num_bins, int bpad, int rows, int cols,
                       cudaStream_t st);
 
+void launch_collapse_pad(const int8_t* raw, int8_t* out, int8_t* risk, int* bad_columns, const float* bin_values, int B,
+                         int H, int W, int keep_r, int keep_c, int pad, int risk_pitch, double alpha, float lo,
+                         float range, int mode, cudaStream_t st);
+
 // sample_noise_numba (mppi.py:1354-1370): generators (n_global*T + t); writes noise (N,T,2).
 void launch_sample_noise(uint64_t* states, float* noise, int n_local, int T, float std_v,
                          float std_w, cudaStream_t st);

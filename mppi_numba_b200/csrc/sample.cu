@@ -36,6 +36,64 @@ void launch_build_cum(const int8_t* pmf, int8_t* cum, int num_bins, int bpad, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Device version of the PMF preprocessing of set_TDM_from_PMF_grid for the one-map planner modes
+// (terrain.py:408-495) fused with cropping + zero-traction padding (terrain.py:511-543): one thread per
+// PADDED cell.  The float64 arithmetic repeats numpy's operation order (0.01*cumsum, (0.01*p)*v, sequential
+// cumsum, +1e-6 in the denominator) with explicitly rounded, uncontracted operations, so the chosen bin is
+// the one the reference's host code chooses.
+//   mode 1 (use_det_dynamics): all mass on the first bin whose value is >= the statistic
+//   mode 2 (speed map)       : all mass on the last bin, risk = int8(100*(stat-lo)/range)
+__global__ void collapse_pad_kernel(const int8_t* __restrict__ raw, int8_t* __restrict__ out,
+                                    int8_t* __restrict__ risk, int* __restrict__ bad_columns, const float* __restrict__ bin_values,
+                                    int B, int H, int W, int keep_r, int keep_c, int pad, int risk_pitch, double alpha,
+                                    float lo, float range, int mode) {
+  const int Hp = keep_r + 2 * pad, Wp = keep_c + 2 * pad;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= Hp * Wp) return;
+  const int r = cell / Wp, c = cell % Wp;
+  const size_t plane = (size_t)Hp * Wp;
+  const bool inner = r >= pad && r < pad + keep_r && c >= pad && c < pad + keep_c;
+  if (!inner) {                                         // padding ring: zero traction, no risk information
+    for (int b = 0; b < B; ++b) out[b * plane + cell] = (b == 0) ? 100 : 0;
+    if (risk) risk[(size_t)r * risk_pitch + c] = 0;
+    return;
+  }
+  const size_t src = (size_t)(r - pad) * W + (c - pad);
+  const size_t splane = (size_t)H * W;
+  int isum = 0;
+  double wcum = 0.0, stat_m = 0.0, stat_w = 0.0;
+  bool found = false;
+  for (int b = 0; b < B; ++b) {
+    const int pv = raw[b * splane + src];
+    isum += pv;
+    const double mass = __dmul_rn(0.01, (double)isum);
+    wcum = __dadd_rn(wcum, __dmul_rn(__dmul_rn(0.01, (double)pv), (double)bin_values[b]));
+    if (alpha != 1.0 && !found && mass >= alpha) { found = true; stat_m = mass; stat_w = wcum; }
+    if (alpha != 1.0 && b == 0 && !found) { stat_m = mass; stat_w = wcum; }     // argmax of all-False is 0
+  }
+  if (isum != 100) atomicAdd(bad_columns, 1);
+  const double stat = (alpha == 1.0) ? wcum : __ddiv_rn(stat_w, __dadd_rn(stat_m, 1e-6));
+  if (mode == 1) {
+    int chosen = 0;
+    for (int b = 0; b < B; ++b)
+      if (stat <= (double)bin_values[b]) { chosen = b; break; }
+    for (int b = 0; b < B; ++b) out[b * plane + cell] = (b == chosen) ? 100 : 0;
+  } else {
+    for (int b = 0; b < B; ++b) out[b * plane + cell] = (b == B - 1) ? 100 : 0;
+    const double v = __ddiv_rn(__dmul_rn(100.0, __dadd_rn(stat, -(double)lo)), (double)range);
+    risk[(size_t)r * risk_pitch + c] = (int8_t)(long long)v;          // astype(int8): truncate, wrap
+  }
+}
+
+void launch_collapse_pad(const int8_t* raw, int8_t* out, int8_t* risk, int* bad_columns, const float* bin_values, int B,
+                         int H, int W, int keep_r, int keep_c, int pad, int risk_pitch, double alpha, float lo,
+                         float range, int mode, cudaStream_t st) {
+  const int cells = (keep_r + 2 * pad) * (keep_c + 2 * pad);
+  collapse_pad_kernel<<<(cells + 255) / 256, 256, 0, st>>>(raw, out, risk, bad_columns, bin_values, B, H, W, keep_r,
+                                                          keep_c, pad, risk_pitch, alpha, lo, range, mode);
+}
+
+// ---------------------------------------------------------------------------------------------
 // v1 sampler: one thread per generator, direct global accesses.
 __global__ void __launch_bounds__(128) sample_grids_kernel(const SampleGridsArgs a) {
   // thread order: ty fastest, then tx, then map -- a warp works on neighbouring tiles of one map

@@ -221,18 +221,6 @@ class TDM_Numba(object):
         self.prepare_obstacle_and_unknown_map(obstacle_map, unknown_map, num_rows, num_cols, res)
 
     # ------------------------------------------------------------------ setter 1: PMF grid
-    @staticmethod
-    def _worst_case_stats(pmf_grid, bin_values, alpha):
-        """Per cell: mean traction (alpha == 1) or the expectation over the worst ``alpha`` tail
-        (first bin whose cumulative mass reaches alpha, whole bin included, +1e-6 in the
-        denominator) -- terrain.py:416-452 / 473-493."""
-        mass = 0.01 * pmf_grid.cumsum(axis=0).astype(float)
-        moment = np.cumsum(0.01 * pmf_grid.astype(float) * bin_values.reshape((-1, 1, 1)), axis=0)
-        if alpha == 1.0:
-            return moment[-1]
-        cut = np.argmax(mass >= alpha, axis=0)[None]
-        return (np.take_along_axis(moment, cut, axis=0) / (np.take_along_axis(mass, cut, axis=0) + 1e-6))[0]
-
     def set_TDM_from_PMF_grid(self, pmf_grid, tdm_dict, obstacle_map=None, unknown_map=None):
         """``pmf_grid``: int (num_bins, rows, cols), each column summing to 100.  ``tdm_dict`` keys:
         res, xlimits, ylimits, bin_values, bin_values_bounds, det_dynamics_cvar_alpha."""
@@ -251,30 +239,44 @@ class TDM_Numba(object):
         assert self.bin_values[0] == 0, "Assume minimum bin value is 0 for now"
         assert self.bin_values_bounds[0] == 0, "Assume minimum traction is 0 for now"
 
-        risk_map = None
         if self.use_det_dynamics or self.use_nom_dynamics_with_speed_map:
-            bad = np.argwhere(np.sum(pmf_grid, axis=0) != 100)
-            if len(bad):
-                print("WARNING: the provided PMF has columns that don't sum up to 100: {}".format(bad))
-            stat = self._worst_case_stats(np.asarray(pmf_grid), self.bin_values, alpha)
-            self.pmf_grid = np.zeros((self.num_pmf_bins, num_rows, num_cols), dtype=np.int8)
-            if self.use_det_dynamics:
-                # all mass on the first bin whose value is >= the statistic (rounds up)
-                chosen = np.argmax(stat[None] <= self.bin_values.reshape((-1, 1, 1)), axis=0)
-                np.put_along_axis(self.pmf_grid, chosen[None], np.int8(100), axis=0)
-            else:
-                # nominal dynamics (last bin) + worst-case speed map in percent of the traction range
-                self.pmf_grid[-1] = np.int8(100)
-                span = self.bin_values_bounds[1] - self.bin_values_bounds[0]
-                risk_map = (100 * (stat - self.bin_values_bounds[0]) / span).reshape(
-                    (1, num_rows, num_cols)).astype(np.int8)
+            # one-map modes: the CVaR / mean collapse (terrain.py:408-495), the crop and the zero-traction
+            # padding run on the GPU (b200mppi_tdm_set_pmf_collapsed); the host keeps mirrors of the results
+            self._set_collapsed_on_device(np.asarray(pmf_grid), alpha, res, obstacle_map, unknown_map)
         else:
             self.pmf_grid = np.asarray(pmf_grid).astype(np.int8)
-        off = np.argwhere(np.sum(self.pmf_grid, axis=0) != 100)
-        if len(off):
-            print("WARNING: some PMF columns do not sum to 100: {}".format(off))
-        self._upload(res, self.xlimits, self.ylimits, obstacle_map, unknown_map, risk_map)
+            off = np.argwhere(np.sum(self.pmf_grid, axis=0) != 100)
+            if len(off):
+                print("WARNING: some PMF columns do not sum to 100: {}".format(off))
+            self._upload(res, self.xlimits, self.ylimits, obstacle_map, unknown_map, None)
         self.pmf_grid_initialized = True
+
+    def _set_collapsed_on_device(self, pmf_grid, alpha, res, obstacle_map, unknown_map):
+        B, num_rows, num_cols = pmf_grid.shape
+        keep_r, keep_c, pad = self.get_padding_info(pmf_grid.shape, self.max_speed_padding, self.dt, res)
+        self.pad_cells = pad
+        self.padded_xlimits, self.padded_ylimits = self._padded_limits(self.xlimits, self.ylimits, keep_r, keep_c, pad, res)
+        raw = np.ascontiguousarray(pmf_grid, dtype=np.int8)
+        bv = np.ascontiguousarray(self.bin_values, dtype=np.float32)
+        bb = np.ascontiguousarray(self.bin_values_bounds, dtype=np.float32)
+        pxl = np.ascontiguousarray(self.padded_xlimits, dtype=np.float32)
+        pyl = np.ascontiguousarray(self.padded_ylimits, dtype=np.float32)
+        Hp, Wp = keep_r + 2 * pad, keep_c + 2 * pad
+        padded = np.empty((B, Hp, Wp), dtype=np.int8)
+        risk_p = np.empty((1, Hp, Wp), dtype=np.int8) if self.use_nom_dynamics_with_speed_map else None
+        bad = C.c_int32(0)
+        check(lib.b200mppi_tdm_set_pmf_collapsed(
+            self._handle, ptr(raw), B, num_rows, num_cols, keep_r, keep_c, pad, ptr(bv), ptr(bb), np.float32(res),
+            ptr(pxl), ptr(pyl), float(alpha), ptr(padded), ptr(risk_p) if risk_p is not None else None, C.byref(bad)))
+        if bad.value:
+            print("WARNING: the provided PMF has {} columns that don't sum up to 100".format(bad.value))
+        self.pmf_grid = padded[:, pad:pad + keep_r, pad:pad + keep_c].copy()
+        self.pmf_grid_d = _host_mirror(self, padded)
+        self.bin_values_d = _host_mirror(self, bv)
+        self.bin_values_bounds_d = _host_mirror(self, bb)
+        if risk_p is not None:
+            self.risk_traction_map_d = _host_mirror(self, risk_p)
+        self.prepare_obstacle_and_unknown_map(obstacle_map, unknown_map, num_rows, num_cols, res)
 
     # ------------------------------------------------------------------ setter 2: semantic grid
     def set_TDM_from_semantic_grid(self, sg, res, num_pmf_bins, bin_values, bin_values_bounds,
