@@ -300,7 +300,7 @@ def run_b200(args, sc):
         pl.solve()
     barrier()
     clocks.lines.clear()
-    l0 = pl.launch_count() + lin_launches(lin) + lin_launches(ang)
+    l0 = pl.launch_count()          # includes the TDM kernels launched inside solve()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         e0.record(stream)
@@ -309,7 +309,7 @@ def run_b200(args, sc):
         e1.record(stream)
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    launches = pl.launch_count() + lin_launches(lin) + lin_launches(ang) - l0      # kernels launched in the timed region
+    launches = pl.launch_count() - l0      # kernels launched in the timed region
     if len(clocks.lines) < 3:                         # very short timed region: extend the load for the sampler only
         t_more = time.perf_counter()
         while time.perf_counter() - t_more < 0.4:
@@ -388,10 +388,6 @@ def run_b200(args, sc):
 
 
 _emit = print
-
-
-def lin_launches(tdm):
-    return 0        # TDM launches issued inside solve() are counted by the planner
 
 
 def main():

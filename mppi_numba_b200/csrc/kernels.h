@@ -18,7 +18,6 @@ struct SampleGridsArgs {
   int grid_rows, pitch;
   int tx, ty, num_maps;
   double alpha_dyn;
-  int col_sums_ok;         // every column reaches >= 100 (no "nothing written" cells)
 };
 void launch_sample_grids(const SampleGridsArgs& a, cudaStream_t st);
 // v2 (staged, integer-threshold, optionally lin+ang fused) sampler -- see sample.cu

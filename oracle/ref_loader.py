@@ -1,8 +1,8 @@
 """Import the UNMODIFIED reference (mit-acl/mppi_numba) under Numba's CUDA simulator so that its own
 kernels can be run in the GPU-less build container (TEST INFRASTRUCTURE, see oracle/__init__.py).
 
-Used only by oracle/make_golden.py (fixture generation, build container) and by
-tests/test_oracle_vs_reference.py (skipped when /root/reference is absent, e.g. on the GPU box).
+Used only by oracle/make_golden.py (fixture generation in the build container; /root/reference does not
+exist on the GPU box).
 Nothing here copies reference source: the package is imported from where it lies.
 
 Shims: NUMBA_ENABLE_CUDASIM=1; ``np.float`` (mppi.py:32-33 uses the removed alias);
