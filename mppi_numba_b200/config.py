@@ -51,9 +51,10 @@ class Config:
 
         # M: sampled traction maps (reference: > 1024 switches to its "oversized" kernel)
         if num_grid_samples > max_threads_per_block:
-            print("WARNING: num_grid_samples({}) > max_threads_per_block({}): the reference's "
-                  "oversized path; not supported by the B200 engine.".format(num_grid_samples,
-                                                                             max_threads_per_block))
+            print("WARNING: num_grid_samples({})>max_threads_per_block({}): the reference switches to its "
+                  "oversized kernel here (mppi.py:199-203), whose CVaR is only meaningful for cvar_alpha=1; this "
+                  "engine evaluates the mean of the ceil(M*cvar_alpha) largest costs for any M.".format(
+                      num_grid_samples, max_threads_per_block))
         self.num_grid_samples = _clamp_with_note("num_grid_samples", num_grid_samples, 1, max_rec_blocks)
         # N: control sequences
         self.num_control_rollouts = _clamp_with_note("num_control_rollouts", num_control_rollouts,

@@ -69,7 +69,6 @@ struct b200mppi_tdm {
   uint64_t sig = 0;             // identifies the generator-state history (equal sig <=> equal states)
 };
 
-static uint64_t g_sig_counter = 0x9E3779B97F4A7C15ULL;
 static inline uint64_t mix_sig(uint64_t h, uint64_t v) {
   h ^= v + 0x9E3779B97F4A7C15ULL + (h << 6) + (h >> 2);
   h *= 0xBF58476D1CE4E5B9ULL;
@@ -531,8 +530,8 @@ static int planner_check_ready(b200mppi_planner* p) {
     return fail(B200MPPI_EINVAL, "planner: lin/ang TDM shapes differ");
   if (p->lin->mask_rows != p->lin->rows || p->lin->mask_cols != p->lin->cols)
     return fail(B200MPPI_EINVAL, "planner: mask shape differs from padded PMF shape");
-  if (p->cfg.mode == B200MPPI_MODE_TDM && p->M_total > 1024)
-    return fail(B200MPPI_EINVAL, "planner: num_grid_samples > 1024 is not supported (reference's oversized kernel is out of scope)");
+  if (p->cfg.mode == B200MPPI_MODE_TDM && p->M_total > cvar_max_maps())
+    return fail(B200MPPI_EINVAL, "planner: num_grid_samples exceeds the CVaR kernel's limit (16384)");
   return B200MPPI_OK;
 }
 
@@ -955,7 +954,7 @@ extern "C" int b200mppi_planner_cvar(b200mppi_planner* p) {
   if (!p) return fail(B200MPPI_EINVAL, "null planner");
   if (!p->params_set) return fail(B200MPPI_ESTATE, "cvar: params not set");
   if (p->cfg.mode != B200MPPI_MODE_TDM) return fail(B200MPPI_ESTATE, "cvar: only MODE_TDM has per-(n,m) costs");
-  if (p->M > 1024) return fail(B200MPPI_EINVAL, "cvar: num_grid_samples > 1024");
+  if (p->M > cvar_max_maps()) return fail(B200MPPI_EINVAL, "cvar: num_grid_samples exceeds the CVaR kernel's limit (16384)");
   CU(cudaSetDevice(p->cfg.device));
   if (p->shard_maps) return fail(B200MPPI_ESTATE, "cvar: maps are sharded, use solve_reduce");
   launch_cvar(p->costs_nm, p->costs, p->n_local, p->M, 1, p->prm.cvar_alpha, p->stream);

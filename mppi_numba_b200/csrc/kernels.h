@@ -87,6 +87,7 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
 // costs_nm is laid out as `chunks` blocks of (N, M): value j of rollout n lives in block j / M at
 // (n, j % M) -- chunks = 1 is the plain (N, M) buffer; chunks = world_size is the all-to-all result of a
 // map-sharded solve (block g = rank g's maps).  The CVaR is over all chunks*M values.
+int cvar_max_maps();   // largest M the CVaR kernels accept
 void launch_cvar(const float* costs_nm, float* costs, int N, int M, int chunks, float cvar_alpha,
                  cudaStream_t st);
 

@@ -215,7 +215,8 @@ __device__ __forceinline__ float key_float(uint32_t k) {   // inverse of float_k
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-constexpr int CVAR_MAX_PER_LANE = 32;   // M <= 1024 (the reference's one-block limit, mppi.py:199)
+constexpr int CVAR_MAX_PER_LANE = 32;   // warp kernel: M <= 1024 (the reference's one-block limit, mppi.py:199)
+constexpr int CVAR_LARGE_MAX_MAPS = 16384;   // CTA kernel: 64 KB of keys (Config clamps M to 15000, config.py:63)
 
 // PER = values held per lane (compile time: the select loop is fully unrolled over them)
 template <int PER>
@@ -228,7 +229,6 @@ __global__ void __launch_bounds__(128) cvar_kernel(const float* __restrict__ cos
   const size_t chunk_stride = (size_t)N * Mc;
   const float* row = costs_nm + (size_t)warp * Mc;
   float v[PER];
-  constexpr int per = PER;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const int j = i * 32 + lane;
@@ -264,11 +264,74 @@ __global__ void __launch_bounds__(128) cvar_kernel(const float* __restrict__ cos
   if (lane == 0) costs[warp] = (float)((double)sum / (double)numel);
 }
 
+// M > 1024 (the reference switches to rollout_oversized_numba, mppi.py:199-203, 760-913, whose "sort" swaps
+// unconditionally, so only its alpha = 1 mean is meaningful; this kernel computes the INTENDED statistic, the
+// mean of the ceil(M*alpha) largest costs, for any M that fits shared memory).  One CTA per control
+// sequence, the M keys in shared memory, the same bitwise radix select with a CTA-wide count per bit.
+constexpr int CVAR_LARGE_THREADS = 256;
+
+__global__ void __launch_bounds__(CVAR_LARGE_THREADS) cvar_large_kernel(const float* __restrict__ costs_nm,
+                                                                        float* __restrict__ costs, int N, int Mc,
+                                                                        int chunks, int numel) {
+  extern __shared__ uint32_t s_keys[];
+  __shared__ int s_cnt[2][CVAR_LARGE_THREADS / 32];
+  __shared__ float s_sum[CVAR_LARGE_THREADS / 32];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = Mc * chunks;
+  const size_t chunk_stride = (size_t)N * Mc;
+  const float* row = costs_nm + (size_t)n * Mc;
+  for (int j = tid; j < M; j += CVAR_LARGE_THREADS)
+    s_keys[j] = float_key(row[(size_t)(j / Mc) * chunk_stride + (j % Mc)]);
+  __syncthreads();
+  uint32_t prefix = 0;
+  int greater_total = 0;
+  if (numel < M) {
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
+      int cnt = 0;
+      for (int j = tid; j < M; j += CVAR_LARGE_THREADS) cnt += (s_keys[j] >= cand) ? 1 : 0;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (lane == 0) s_cnt[bit & 1][warp] = cnt;
+      __syncthreads();
+      int total = 0;
+#pragma unroll
+      for (int w = 0; w < CVAR_LARGE_THREADS / 32; ++w) total += s_cnt[bit & 1][w];
+      if (total >= numel) prefix = cand;
+    }
+  }
+  float sum = 0.0f;
+  int greater = 0;
+  for (int j = tid; j < M; j += CVAR_LARGE_THREADS) {
+    const uint32_t k = s_keys[j];
+    if (numel >= M || k > prefix) { sum += key_float(k); ++greater; }
+  }
+  sum = warp_sum(sum);
+  greater = __reduce_add_sync(0xffffffffu, greater);
+  __syncthreads();                           // the last select round has finished reading s_cnt
+  if (lane == 0) { s_sum[warp] = sum; s_cnt[0][warp] = greater; }
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.0f;
+    for (int w = 0; w < CVAR_LARGE_THREADS / 32; ++w) { tot += s_sum[w]; greater_total += s_cnt[0][w]; }
+    if (numel < M) tot += (float)(numel - greater_total) * key_float(prefix);
+    costs[n] = (float)((double)tot / (double)numel);
+  }
+}
+
+int cvar_max_maps() { return CVAR_LARGE_MAX_MAPS; }
+
 void launch_cvar(const float* costs_nm, float* costs, int N, int Mc, int chunks, float cvar_alpha, cudaStream_t st) {
   const int M = Mc * chunks;
   int numel = (int)ceil((double)M * (double)cvar_alpha);    // mppi.py:744 (float32 alpha, f64 product)
   if (numel < 1) numel = 1;
   if (numel > M) numel = M;
+  if (M > 32 * CVAR_MAX_PER_LANE) {
+    const size_t smem = (size_t)M * sizeof(uint32_t);
+    cudaFuncSetAttribute(cvar_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,   // per device
+                         CVAR_LARGE_MAX_MAPS * (int)sizeof(uint32_t));
+    cvar_large_kernel<<<(unsigned)N, CVAR_LARGE_THREADS, smem, st>>>(costs_nm, costs, N, Mc, chunks, numel);
+    return;
+  }
   const int threads = 128;
   const int warps_per_block = threads / 32;
   const unsigned blocks = (unsigned)((N + warps_per_block - 1) / warps_per_block);

@@ -233,9 +233,12 @@ class MPPI_Numba(object):
         return self._solve_on_device()
 
     def solve_stochastic_oversized(self):
-        raise NotImplementedError(
-            "num_grid_samples > 1024: the reference's oversized kernel (mppi.py:760-913) computes a "
-            "meaningless CVaR (unconditional swaps, SURVEY.md 9-B1) and is outside this engine's scope.")
+        """num_grid_samples > 1024 (mppi.py:454-531).  The reference's oversized kernel swaps unconditionally
+        instead of sorting (SURVEY.md 9-B1), so its result is meaningful only for cvar_alpha = 1 (the mean);
+        the engine has no block-size limit on M and evaluates the same statistic as solve_stochastic:
+        the mean of the ceil(M * cvar_alpha) largest costs."""
+        assert self.num_grid_samples > self.cfg.max_threads_per_block
+        return self._solve_on_device()
 
     # ---- multi-GPU: N sharded over ranks, one all-gather of 2T+2 floats per iteration
     def _ensure_exchange(self):

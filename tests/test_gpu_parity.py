@@ -336,6 +336,7 @@ def test_rollouts_vs_reference_golden(eng, golden_dir, gname):
     ("det", 4096, 1, 128, 512, 0.2, 32, False, True),      # BASELINE config 4 (CVaR-dynamics alpha 0.3)
     ("spd", 1024, 1, 64, 256, 0.2, 12, True, True),        # speed-map mode
     ("tdm", 512, 16, 128, 900, 0.05, 12, False, True),     # fine grid: rollouts LEAVE the staged window
+    ("tdm", 256, 1100, 32, 128, 0.1, 12, False, True),     # M > 1024: the reference's "oversized" dispatch
 ])
 def test_rollout_costs_vs_oracle(eng, mode, N, M, T, H, res, B, near, warm):
     sc = make_scenario(mode, N=N, M=M, T=T, H=H, W=H, res=res, B=B, seed=4, near_goal=near, warm_start=warm,
@@ -412,7 +413,8 @@ def test_cvar_selection_properties(eng):
     cases; against the oracle's sort-based restatement (mppi.py:718-755)."""
     L = eng._lib
     rng = np.random.default_rng(0)
-    for M, alpha in ((6, 0.5), (33, 0.1), (100, 0.999), (256, 0.5), (1000, 0.25), (1024, 1.0), (7, 0.01), (1, 0.5)):
+    for M, alpha in ((6, 0.5), (33, 0.1), (100, 0.999), (256, 0.5), (1000, 0.25), (1024, 1.0), (7, 0.01), (1, 0.5),
+                     (1025, 0.5), (3000, 0.1), (2048, 1.0), (15000, 0.999), (4097, 0.0001)):   # CTA kernel (M > 1024)
         N = 130
         rp = RawPlanner(eng, 0, N, M, 4, 8, 8)
         try:
@@ -773,6 +775,39 @@ def test_determinism_and_checkpoint_resume(eng):
     c.set_state(st)
     assert (c.solve() == ua[2]).all()                            # resume from checkpoint == uninterrupted
     assert not (ua[0] == ua[1]).all()                            # streams advance between solves
+
+
+def test_oversized_map_count_solve(eng, capsys):
+    """num_grid_samples > 1024: solve() dispatches to solve_stochastic_oversized (mppi.py:199-203) and equals
+    the stage-by-stage replay through the C-ABI, whose CVaR stage is checked against the oracle's sort."""
+    sc = make_scenario("tdm", N=128, M=1030, T=16, H=40, W=40, res=0.25, B=6, seed=21, cvar_alpha=0.3)
+
+    def build():
+        cfg = eng.Config(**sc["cfg"])
+        lin, ang = eng.TDM_Numba(cfg), eng.TDM_Numba(cfg)
+        lin.set_TDM_from_PMF_grid(sc["pmf_lin"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+        ang.set_TDM_from_PMF_grid(sc["pmf_ang"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+        pl = eng.MPPI_Numba(cfg)
+        pl.setup(sc["params"], lin, ang)
+        return pl, lin, ang
+    a, *_ka = build()
+    assert "oversized kernel" in capsys.readouterr().out          # Config's warning, like the reference's
+    assert a.cfg.num_grid_samples == 1030
+    u = a.solve()
+    assert u.shape == (16, 2) and np.isfinite(u).all()
+    b, lin, ang = build()
+    L = eng._lib
+    b.move_mppi_task_vars_to_device()
+    lin.sample_grids(1.0)
+    ang.sample_grids(1.0)
+    for stage in ("sample_noise", "rollout"):
+        L.check(getattr(L.lib, "b200mppi_planner_" + stage)(b._handle))
+    nm = b.costs_nm_d.copy_to_host()
+    cv = b.costs_d.copy_to_host()
+    np.testing.assert_allclose(cv, MR.cvar_reduce(nm, 0.3), rtol=2e-6)
+    c = np.ascontiguousarray(cv)
+    L.check(L.lib.b200mppi_planner_update(b._handle, L.ptr(c)))
+    assert (b.u_cur_d.copy_to_host() == u).all()
 
 
 def test_closed_loop_reaches_goal(eng):

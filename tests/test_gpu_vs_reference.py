@@ -5,7 +5,8 @@ git-ignored scratch copy baseline/_ref/ (which travels to the GPU box with gpuru
 the tests skip.  What is asserted (same inputs on both sides: seed, PMFs, masks, params):
   * control noise: bit-identical;  sampled traction maps: bit-identical
   * deterministic-mode rollout costs: bit-identical
-  * stochastic CVaR costs: within 1e-4 relative (only the summation order of the CVaR mean differs)
+  * stochastic CVaR costs: within 1e-4 relative (only the summation order of the CVaR mean differs),
+    including M > 1024 against the reference's oversized kernel at cvar_alpha = 1
   * updated control sequence given the reference's costs: within 1e-4
 """
 import io
@@ -58,6 +59,8 @@ def ref():
 @pytest.mark.parametrize("mode,N,M,T,H,res,B,det_alpha", [
     ("tdm", 1024, 64, 64, 512, 0.1, 12, 1.0),        # BASELINE config 3
     ("det", 4096, 1, 128, 512, 0.2, 32, 0.3),        # BASELINE config 4
+    ("tdm", 128, 1100, 32, 128, 0.1, 12, 1.0),       # M > 1024: rollout_oversized_numba, cvar_alpha = 1 (its
+                                                     # "sort" for alpha < 1 swaps unconditionally)
 ])
 def test_kernels_vs_reference_numba_cuda(ref, mode, N, M, T, H, res, B, det_alpha):
     RConfig, RTDM, RMPPI, cuda = ref
@@ -65,7 +68,8 @@ def test_kernels_vs_reference_numba_cuda(ref, mode, N, M, T, H, res, B, det_alph
     __graft_entry__.build()
     import mppi_numba_b200 as E
     from tests.scenarios import make_scenario
-    sc = make_scenario(mode, N=N, M=M, T=T, H=H, W=H, res=res, B=B, seed=1, det_alpha=det_alpha, warm_start=True)
+    sc = make_scenario(mode, N=N, M=M, T=T, H=H, W=H, res=res, B=B, seed=1, det_alpha=det_alpha, warm_start=True,
+                       cvar_alpha=1.0 if M > 1024 else 0.5)
     p = sc["params"]
     rcfg = _quiet(RConfig, **sc["cfg"])
     rl, ra = _quiet(RTDM, rcfg), _quiet(RTDM, rcfg)
@@ -100,7 +104,8 @@ def test_kernels_vs_reference_numba_cuda(ref, mode, N, M, T, H, res, B, det_alph
     noise = rp.noise_samples_d.copy_to_host()
     assert (noise == ep.noise_samples_d.copy_to_host()).all()
     if mode == "tdm":
-        RMPPI.rollout_numba[N, M, 0, 4 * M](
+        kern = RMPPI.rollout_numba[N, M, 0, 4 * M] if M <= 1024 else RMPPI.rollout_oversized_numba[N, 1024, 0, 4 * M]
+        kern(
             lin_g, ang_g, rl.bin_values_bounds_d, ra.bin_values_bounds_d, rl.obstacle_map_d, rl.unknown_map_d, res_d,
             xl_d, yl_d, vr_d, wr_d, xg_d, vpost_d, obs_c, unk_c, tol_d, lam_d, ustd_d, cvar_d, x0_d, dt_d, 1.0,
             rp.noise_samples_d, rp.u_cur_d, rp.costs_d)
