@@ -197,6 +197,29 @@ int b200mppi_planner_solve_reduce(b200mppi_planner* pl, const float* exchanged_c
 int b200mppi_planner_solve_local(b200mppi_planner* pl, int32_t first_iteration);
 int b200mppi_planner_solve_finish(b200mppi_planner* pl, const float* gathered_partials_dev,
                                   float* u_out);
+/* Peer-memory exchange (NVLink / NVSwitch): the same sharded solve with this library's own kernels doing
+ * both exchanges -- plain stores into the peers' buffers + epoch flags -- instead of two collective calls
+ * of a communication library.  world_size <= 16, all ranks on one node with peer access.
+ *   p2p_export        : allocates this planner's exchange buffer and returns its CUDA IPC handle (64 bytes).
+ *   p2p_import        : `handles` = the world_size exported handles in rank order (the caller all-gathers them
+ *                       once, with any transport); opens the peers' buffers.
+ *   p2p_connect_local : same for planners living in THIS process (peers[s] = rank s; devices may differ).
+ *   p2p_push          : after solve_local (MODE_TDM): block d of the (N, M/ws) costs -> rank d, then signal.
+ *   p2p_reduce        : wait for every rank's block, CVaR + softmax partial (as solve_reduce), store the
+ *                       partial into every rank's gather buffer, signal.
+ *   p2p_finish        : wait for every rank's partial, combine (as solve_finish); u_out may be NULL.
+ *   solve_p2p         : num_opt x (solve_local, p2p_push, p2p_reduce, p2p_finish) -- the whole sharded solve()
+ *                       in one call, no host synchronisation until the final copy of u.
+ * A rank that never arrives does not hang the device: the waits give up after B200MPPI_P2P_TIMEOUT_MS
+ * (environment, default 2000) and the call returns B200MPPI_ECUDA naming the missing rank. */
+int b200mppi_planner_p2p_export(b200mppi_planner* pl, void* ipc_handle_out, size_t bytes);
+int b200mppi_planner_p2p_import(b200mppi_planner* pl, const void* ipc_handles, size_t bytes);
+int b200mppi_planner_p2p_connect_local(b200mppi_planner* pl, b200mppi_planner* const* peers, int32_t count);
+int b200mppi_planner_p2p_push(b200mppi_planner* pl);
+int b200mppi_planner_p2p_reduce(b200mppi_planner* pl);
+int b200mppi_planner_p2p_finish(b200mppi_planner* pl, float* u_out);
+int b200mppi_planner_solve_p2p(b200mppi_planner* pl, float* u_out);
+
 /* Host-side reference combine of gathered partials (used by CPU tests of the N>1 logic; tiny). */
 int b200mppi_combine_partials_host(const float* gathered, int32_t world_size, int32_t num_steps,
                                    float lambda_weight, const float* u_in, const float vrange[2],

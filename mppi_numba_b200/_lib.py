@@ -80,6 +80,13 @@ def _load():
         "b200mppi_planner_solve_local": (C.c_int, [P, I32]),
         "b200mppi_planner_solve_reduce": (C.c_int, [P, P]),
         "b200mppi_planner_solve_finish": (C.c_int, [P, P, P]),
+        "b200mppi_planner_p2p_export": (C.c_int, [P, P, C.c_size_t]),
+        "b200mppi_planner_p2p_import": (C.c_int, [P, P, C.c_size_t]),
+        "b200mppi_planner_p2p_connect_local": (C.c_int, [P, P, C.c_int32]),
+        "b200mppi_planner_p2p_push": (C.c_int, [P]),
+        "b200mppi_planner_p2p_reduce": (C.c_int, [P]),
+        "b200mppi_planner_p2p_finish": (C.c_int, [P, P]),
+        "b200mppi_planner_solve_p2p": (C.c_int, [P, P]),
         "b200mppi_combine_partials_host": (C.c_int, [P, I32, I32, F, P, P, P, P]),
         "b200mppi_planner_sample_noise": (C.c_int, [P]),
         "b200mppi_planner_set_noise": (C.c_int, [P, P, SZ]),

@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libb200mppi.so")
-SOURCES = ["api.cu", "rollout.cu", "rollout_win.cu", "reduce.cu", "sample.cu"]
+SOURCES = ["api.cu", "rollout.cu", "rollout_win.cu", "reduce.cu", "sample.cu", "p2p.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join(ROOT, "include", "b200mppi.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -506,7 +506,16 @@ struct b200mppi_planner {
   float* noiseT = nullptr; float* ctrl = nullptr; int npad = 0;   // windowed rollout kernel inputs
   alignas(64) unsigned char tmaps[4][128];
   bool use_win = true;
-  float* h_u = nullptr;        // pinned staging for the T x 2 result
+  float* h_u = nullptr;        // pinned staging for the T x 2 result (+ one int: exchange status)
+  // peer-memory exchange (p2p.cu): ONE allocation per planner so that one IPC handle describes it:
+  // [ receive buffer (ws, N/ws, M/ws) | gather buffers 2 x (ws, 2T+2) | cost flags | partial flags | counter | status ]
+  unsigned char* xbuf = nullptr;
+  size_t x_gather = 0, x_flags_cost = 0, x_flags_part = 0, x_counter = 0, x_status = 0, x_bytes = 0;
+  unsigned char* peer_x[P2P_MAX_PEERS] = {};
+  bool peer_ipc[P2P_MAX_PEERS] = {};
+  bool p2p_ready = false;
+  uint32_t epoch_cost = 0, epoch_part = 0;
+  unsigned long long p2p_timeout_ns = 2000000000ull;
   int num_ctas = 1, rows_per_cta = 1;
   b200mppi_tdm* lin = nullptr; b200mppi_tdm* ang = nullptr;
   b200mppi_params prm{};
@@ -624,7 +633,7 @@ extern "C" int b200mppi_planner_create(const b200mppi_config* cfg, b200mppi_plan
   CU(cudaMemsetAsync(p->costs, 0, (size_t)p->n_red * sizeof(float), p->stream));
   CU(cudaMemsetAsync(p->weights, 0, (size_t)p->n_red * sizeof(float), p->stream));
   CU(cudaMemsetAsync(p->state_rollout, 0, (size_t)V * (p->T + 1) * 3 * sizeof(float), p->stream));
-  CU(cudaMallocHost(&p->h_u, (size_t)p->T * 2 * sizeof(float)));
+  CU(cudaMallocHost(&p->h_u, ((size_t)p->T * 2 + 4) * sizeof(float)));
   // generators n_global*T + t of this shard (mppi.py:118,1367)
   std::vector<uint64_t> h(nT * 2);
   create_xoroshiro_states(h.data(), p->shard_maps ? 0 : (int64_t)p->n_begin * p->T, (int64_t)nT, cfg->seed);
@@ -644,6 +653,9 @@ extern "C" int b200mppi_planner_destroy(b200mppi_planner* p) {
   cudaFree(p->w_raw); cudaFree(p->costs_nm); cudaFree(p->cta_partials); cudaFree(p->rank_partial);
   cudaFree(p->state_rollout); cudaFree(p->states); cudaFree(p->noiseT); cudaFree(p->ctrl); cudaFree(p->costs_x);
   cudaFree(p->obstacles);
+  for (int s = 0; s < P2P_MAX_PEERS; ++s)
+    if (p->peer_ipc[s] && p->peer_x[s]) cudaIpcCloseMemHandle(p->peer_x[s]);
+  cudaFree(p->xbuf);
   if (p->h_u) cudaFreeHost(p->h_u);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
@@ -901,6 +913,185 @@ extern "C" int b200mppi_planner_solve_finish(b200mppi_planner* p, const float* g
     std::memcpy(u_out, p->h_u, (size_t)p->T * 2 * sizeof(float));
     collect_timings(p);
   }
+  return B200MPPI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer-memory exchange (p2p.cu): the sharded solve without NCCL on the data path.
+static int p2p_alloc(b200mppi_planner* p) {
+  if (p->xbuf) return B200MPPI_OK;
+  const int ws = p->cfg.world_size;
+  if (ws < 2) return fail(B200MPPI_ESTATE, "p2p: world_size is 1");
+  if (ws > P2P_MAX_PEERS) return fail(B200MPPI_EINVAL, "p2p: world_size > 16 (use the NCCL exchange)");
+  CU(cudaSetDevice(p->cfg.device));
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t len = (size_t)(2 * p->T + 2);
+  size_t off = 0;
+  off += up(p->shard_maps ? (size_t)p->n_local * p->M * sizeof(float) : 0);
+  p->x_gather = off;      off += up(2 * (size_t)ws * len * sizeof(float));
+  p->x_flags_cost = off;  off += up((size_t)ws * sizeof(uint32_t));
+  p->x_flags_part = off;  off += up((size_t)ws * sizeof(uint32_t));
+  p->x_counter = off;     off += 256;
+  p->x_status = off;      off += 256;
+  p->x_bytes = off;
+  CU(cudaMalloc(&p->xbuf, off));
+  CU(cudaMemset(p->xbuf, 0, off));
+  if (const char* e = getenv("B200MPPI_P2P_TIMEOUT_MS")) {
+    const long ms = atol(e);
+    if (ms > 0) p->p2p_timeout_ns = (unsigned long long)ms * 1000000ull;
+  }
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_p2p_export(b200mppi_planner* p, void* handle_out, size_t bytes) {
+  if (!p || !handle_out) return fail(B200MPPI_EINVAL, "p2p_export: null argument");
+  if (bytes < sizeof(cudaIpcMemHandle_t)) return fail(B200MPPI_EINVAL, "p2p_export: handle buffer < 64 bytes");
+  int rc = p2p_alloc(p);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, p->xbuf));
+  std::memcpy(handle_out, &h, sizeof(h));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_p2p_import(b200mppi_planner* p, const void* handles, size_t bytes) {
+  if (!p || !handles) return fail(B200MPPI_EINVAL, "p2p_import: null argument");
+  const int ws = p->cfg.world_size;
+  if (bytes < (size_t)ws * sizeof(cudaIpcMemHandle_t)) return fail(B200MPPI_EINVAL, "p2p_import: need world_size handles");
+  int rc = p2p_alloc(p);
+  if (rc) return rc;
+  CU(cudaSetDevice(p->cfg.device));
+  for (int s = 0; s < ws; ++s) {
+    if (s == p->cfg.rank) { p->peer_x[s] = p->xbuf; continue; }
+    if (p->peer_x[s]) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const unsigned char*)handles + (size_t)s * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->peer_x[s] = (unsigned char*)ptr;
+    p->peer_ipc[s] = true;
+  }
+  p->p2p_ready = true;
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_p2p_connect_local(b200mppi_planner* p, b200mppi_planner* const* peers, int32_t count) {
+  if (!p || !peers) return fail(B200MPPI_EINVAL, "p2p_connect_local: null argument");
+  if (count != p->cfg.world_size) return fail(B200MPPI_EINVAL, "p2p_connect_local: need world_size planners");
+  for (int s = 0; s < count; ++s) {
+    b200mppi_planner* q = peers[s];
+    if (!q || q->cfg.rank != s || q->cfg.world_size != count || q->T != p->T || q->n_local != p->n_local || q->M != p->M)
+      return fail(B200MPPI_EINVAL, "p2p_connect_local: peers[s] must be rank s of the same configuration");
+    int rc = p2p_alloc(q);
+    if (rc) return rc;
+    if (q->cfg.device != p->cfg.device) {
+      CU(cudaSetDevice(p->cfg.device));
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, p->cfg.device, q->cfg.device));
+      if (!can) return fail(B200MPPI_ECUDA, "p2p_connect_local: no peer access between the devices");
+      const cudaError_t e = cudaDeviceEnablePeerAccess(q->cfg.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+      (void)cudaGetLastError();
+    }
+    p->peer_x[s] = q->xbuf;
+  }
+  p->p2p_ready = true;
+  return B200MPPI_OK;
+}
+
+static int p2p_check(b200mppi_planner* p, const char* who) {
+  if (!p) return fail(B200MPPI_EINVAL, "null planner");
+  if (!p->p2p_ready) return fail(B200MPPI_ESTATE, std::string(who) + ": peers not connected (p2p_import / p2p_connect_local)");
+  CU(cudaSetDevice(p->cfg.device));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_p2p_push(b200mppi_planner* p) {
+  int rc = p2p_check(p, "p2p_push");
+  if (rc) return rc;
+  if (!p->shard_maps) return fail(B200MPPI_ESTATE, "p2p_push: only MODE_TDM shards the maps");
+  P2PPushArgs a{};
+  a.costs_nm = p->costs_nm;
+  a.ws = p->cfg.world_size; a.rank = p->cfg.rank; a.n_red = p->n_red; a.Mc = p->M;
+  a.counter = (unsigned*)(p->xbuf + p->x_counter);
+  a.epoch = ++p->epoch_cost;
+  for (int s = 0; s < a.ws; ++s) {
+    a.peer_recv[s] = (float*)p->peer_x[s];
+    a.peer_flags[s] = (uint32_t*)(p->peer_x[s] + p->x_flags_cost);
+  }
+  launch_p2p_push(a, p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_p2p_reduce(b200mppi_planner* p) {
+  int rc = p2p_check(p, "p2p_reduce");
+  if (rc) return rc;
+  const int ws = p->cfg.world_size;
+  int* status = (int*)(p->xbuf + p->x_status);
+  if (p->shard_maps) {
+    launch_p2p_wait((const uint32_t*)(p->xbuf + p->x_flags_cost), ws, p->epoch_cost, p->p2p_timeout_ns, status, p->stream);
+    launch_cvar((const float*)p->xbuf, p->costs, p->n_red, p->M, ws, p->prm.cvar_alpha, p->stream);
+    p->launches += 2;
+    CHECK_LAUNCH();
+    if (p->profiling) cudaEventRecord(p->ev[4], p->stream);
+    if ((rc = stage_update_partial(p, nullptr))) return rc;
+  }
+  P2PBcastArgs b{};
+  b.partial = p->rank_partial;
+  b.ws = ws; b.rank = p->cfg.rank; b.len = 2 * p->T + 2;
+  b.epoch = ++p->epoch_part;
+  const size_t parity_off = (size_t)(b.epoch & 1u) * ws * b.len * sizeof(float);
+  for (int s = 0; s < ws; ++s) {
+    b.peer_gather[s] = (float*)(p->peer_x[s] + p->x_gather + parity_off);
+    b.peer_flags[s] = (uint32_t*)(p->peer_x[s] + p->x_flags_part);
+  }
+  launch_p2p_bcast(b, p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_p2p_finish(b200mppi_planner* p, float* u_out) {
+  int rc = p2p_check(p, "p2p_finish");
+  if (rc) return rc;
+  const int ws = p->cfg.world_size;
+  int* status = (int*)(p->xbuf + p->x_status);
+  launch_p2p_wait((const uint32_t*)(p->xbuf + p->x_flags_part), ws, p->epoch_part, p->p2p_timeout_ns, status, p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
+  const size_t parity_off = (size_t)(p->epoch_part & 1u) * ws * (2 * p->T + 2) * sizeof(float);
+  if ((rc = stage_update_finish(p, (const float*)(p->xbuf + p->x_gather + parity_off), ws))) return rc;
+  if (p->profiling) cudaEventRecord(p->ev[5], p->stream);
+  if (u_out) {
+    int* h_status = (int*)(p->h_u + (size_t)p->T * 2);
+    CU(cudaMemcpyAsync(p->h_u, p->u_cur, (size_t)p->T * 2 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(h_status, status, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    if (*h_status != 0) {
+      const int who = *h_status - 1;
+      cudaMemsetAsync(status, 0, sizeof(int), p->stream);
+      return fail(B200MPPI_ECUDA, "p2p exchange: timed out waiting for rank " + std::to_string(who));
+    }
+    std::memcpy(u_out, p->h_u, (size_t)p->T * 2 * sizeof(float));
+    collect_timings(p);
+  }
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_solve_p2p(b200mppi_planner* p, float* u_out) {
+  int rc = p2p_check(p, "solve_p2p");
+  if (rc) return rc;
+  if (!u_out) return fail(B200MPPI_EINVAL, "solve_p2p: null output");
+  const int num_opt = p->prm.num_opt;
+  for (int k = 0; k < num_opt; ++k) {
+    if ((rc = b200mppi_planner_solve_local(p, k == 0 ? 1 : 0))) return rc;
+    if (p->shard_maps && (rc = b200mppi_planner_p2p_push(p))) return rc;
+    if ((rc = b200mppi_planner_p2p_reduce(p))) return rc;
+    if ((rc = b200mppi_planner_p2p_finish(p, k == num_opt - 1 ? u_out : nullptr))) return rc;
+  }
+  if (num_opt <= 0) return b200mppi_planner_get_u(p, u_out);
   return B200MPPI_OK;
 }
 

@@ -120,6 +120,28 @@ struct VisArgs {
 };
 void launch_state_rollout(const VisArgs& a, cudaStream_t st);
 
+// peer-memory exchange of the sharded solve (p2p.cu)
+constexpr int P2P_MAX_PEERS = 16;
+struct P2PPushArgs {
+  const float* costs_nm;              // local (N, Mc): block d = rows [d*n_red, (d+1)*n_red)
+  float* peer_recv[P2P_MAX_PEERS];    // peer d's receive buffer (ws, n_red, Mc)
+  uint32_t* peer_flags[P2P_MAX_PEERS];// peer d's cost flags [ws]
+  unsigned* counter;                  // local, zero between launches
+  int ws, rank, n_red, Mc;
+  uint32_t epoch;
+};
+struct P2PBcastArgs {
+  const float* partial;               // local (len)
+  float* peer_gather[P2P_MAX_PEERS];  // peer d's gather buffer of this epoch's parity, (ws, len)
+  uint32_t* peer_flags[P2P_MAX_PEERS];// peer d's partial flags [ws]
+  int ws, rank, len;
+  uint32_t epoch;
+};
+void launch_p2p_push(const P2PPushArgs& a, cudaStream_t st);
+void launch_p2p_bcast(const P2PBcastArgs& a, cudaStream_t st);
+void launch_p2p_wait(const uint32_t* flags, int ws, uint32_t epoch, unsigned long long timeout_ns, int* status,
+                     cudaStream_t st);
+
 // host: numba-compatible generator states (random.py:226-241)
 void create_xoroshiro_states(uint64_t* host_out, int64_t first, int64_t count, uint64_t seed);
 

@@ -47,6 +47,7 @@ class MPPI_Numba(object):
         self._pod = _lib.ParamsPOD()
         self._pod_f32 = np.frombuffer(self._pod, dtype=np.float32, count=19)     # dt .. dist_weight
         self._gathered = None            # torch tensor (world_size, 2T+2) for the exchange
+        self._p2p = False                # peer-memory exchange connected (csrc/p2p.cu)
         self._partial_t = None
         self._stream = None
 
@@ -252,17 +253,60 @@ class MPPI_Numba(object):
         check(lib.b200mppi_planner_set_stream(self._handle, C.c_void_p(self._stream.cuda_stream)))
         for tdm in (self.lin_tdm, self.ang_tdm):
             check(lib.b200mppi_tdm_set_stream(tdm._handle, C.c_void_p(self._stream.cuda_stream)))
+        self._p2p = self._connect_peers()
+        if self._p2p:
+            self._gathered = True          # exchange buffers live inside the library
+            return
         self._partial_t = torch.as_tensor(self.partial_d, device=dev)          # zero-copy view
         self._gathered = torch.empty((self.world_size * (2 * self.num_steps + 2),), dtype=torch.float32, device=dev)
         if self.shard_maps:
             self._costs_send = torch.as_tensor(self.costs_nm_d, device=dev).reshape(-1)   # (N, M/ws), zero-copy
             self._costs_recv = torch.empty_like(self._costs_send)                         # (ws, N/ws, M/ws)
 
+    def _connect_peers(self):
+        """Peer-memory exchange (csrc/p2p.cu): every rank exports the CUDA IPC handle of its exchange buffer,
+        one all-gather of the 64-byte handles, every rank maps its peers' buffers.  Used when all ranks
+        succeed; B200MPPI_EXCHANGE=nccl keeps the collective-library exchange, =p2p makes failure an error."""
+        import os
+        import sys
+        import torch
+        import torch.distributed as dist
+        want = os.environ.get("B200MPPI_EXCHANGE", "auto").lower()
+        if want == "nccl":
+            return False
+        with torch.cuda.device(self.device):
+            h = (C.c_ubyte * 64)()
+            rc = lib.b200mppi_planner_p2p_export(self._handle, h, 64)
+            why = "" if rc == 0 else lib.b200mppi_last_error().decode()
+            handles = [None] * self.world_size
+            dist.all_gather_object(handles, bytes(h) if rc == 0 else None, group=self.process_group)
+            ok = all(x is not None for x in handles)
+            if ok:
+                blob = b"".join(handles)
+                buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+                ok = lib.b200mppi_planner_p2p_import(self._handle, buf, len(blob)) == 0
+                if not ok:
+                    why = lib.b200mppi_last_error().decode()
+            votes = [None] * self.world_size
+            dist.all_gather_object(votes, (bool(ok), why), group=self.process_group)
+        ok = all(v[0] for v in votes)
+        if not ok:
+            reasons = "; ".join("rank %d: %s" % (r, v[1]) for r, v in enumerate(votes) if not v[0])
+            if want == "p2p":
+                raise RuntimeError("peer-memory exchange unavailable (%s)" % reasons)
+            if self.rank == 0:
+                print("mppi_numba_b200: peer-memory exchange unavailable (%s); using the NCCL exchange" % reasons,
+                      file=sys.stderr)
+        return ok
+
     def _solve_sharded(self, u_out):
         import torch
         import torch.distributed as dist
         self._ensure_exchange()
         num_opt = int(self.params['num_opt'])
+        if self._p2p:
+            check(lib.b200mppi_planner_solve_p2p(self._handle, ptr(u_out)))
+            return
         with torch.cuda.stream(self._stream):
             for k in range(num_opt):
                 check(lib.b200mppi_planner_solve_local(self._handle, 1 if k == 0 else 0))

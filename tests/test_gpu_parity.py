@@ -574,6 +574,88 @@ def test_map_sharded_solve_equals_single_rank(eng):
         np.testing.assert_allclose(u, u_single, rtol=1e-5, atol=2e-6)
 
 
+def _connect_local(L, planners):
+    hs = [pl._handle.value if hasattr(pl._handle, "value") else pl._handle for pl in planners]
+    arr = (C.c_void_p * len(hs))(*hs)
+    for pl in planners:
+        L.check(L.lib.b200mppi_planner_p2p_connect_local(pl._handle, arr, len(hs)))
+
+
+@pytest.mark.parametrize("mode,ws", [("tdm", 2), ("tdm", 4), ("det", 4)])
+def test_p2p_exchange_equals_single_rank(eng, mode, ws):
+    """The peer-memory exchange (p2p.cu): ws 'ranks' living in this process on this GPU, connected with
+    p2p_connect_local, run the phase calls of solve_p2p interleaved (local / push / reduce / finish) without
+    host synchronisation in between; three consecutive solves (epoch flags, double-buffered gather) give
+    the single-rank u on every rank, and the CVaR costs of each rank's slice are bit-identical."""
+    L = eng._lib
+    sc = make_scenario(mode, N=512, M=16 if mode == "tdm" else 1, T=32, H=120, W=120, res=0.2, B=8, seed=14,
+                       warm_start=True)
+
+    def build(rank, world):
+        cfg = eng.Config(**sc["cfg"])
+        lin = eng.TDM_Numba(cfg, rank=rank, world_size=world)
+        ang = eng.TDM_Numba(cfg, rank=rank, world_size=world)
+        lin.set_TDM_from_PMF_grid(sc["pmf_lin"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+        ang.set_TDM_from_PMF_grid(sc["pmf_ang"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+        pl = eng.MPPI_Numba(cfg, rank=rank, world_size=world)
+        pl.setup(sc["params"], lin, ang)
+        pl.u_cur_d.copy_to_device(sc["u0"])
+        pl.move_mppi_task_vars_to_device()
+        return pl, lin, ang
+    single = build(0, 1)
+    ranks = [build(r, ws) for r in range(ws)]
+    pls = [r[0] for r in ranks]
+    _connect_local(L, pls)
+    N = sc["N"]
+    for it in range(3):
+        u_single = single[0].solve()
+        costs_single = single[0].costs_d.copy_to_host()
+        for pl in pls:
+            L.check(L.lib.b200mppi_planner_solve_local(pl._handle, 1))
+        if mode == "tdm":
+            for pl in pls:
+                L.check(L.lib.b200mppi_planner_p2p_push(pl._handle))
+        for pl in pls:
+            L.check(L.lib.b200mppi_planner_p2p_reduce(pl._handle))
+        us = []
+        for pl in pls:
+            u = np.empty_like(u_single)
+            L.check(L.lib.b200mppi_planner_p2p_finish(pl._handle, L.ptr(u)))
+            us.append(u)
+        for d, pl in enumerate(pls):
+            assert (pl.costs_d.copy_to_host() == costs_single[d * N // ws:(d + 1) * N // ws]).all(), (it, d)
+            np.testing.assert_allclose(us[d], u_single, rtol=1e-5, atol=2e-6, err_msg="solve %d rank %d" % (it, d))
+            assert (us[d] == us[0]).all()                      # every rank combines the same partials
+            pl.u_cur_d.copy_to_device(u_single)                # (u differs from 1 rank by summation order only;
+                                                               #  re-align so the next solve's costs compare bitwise)
+
+
+def test_p2p_wait_times_out_instead_of_hanging(eng, monkeypatch):
+    """A rank that never arrives: the wait kernel gives up after B200MPPI_P2P_TIMEOUT_MS and the call
+    reports which rank was missing (no hung GPU)."""
+    L = eng._lib
+    monkeypatch.setenv("B200MPPI_P2P_TIMEOUT_MS", "50")
+    sc = make_scenario("det", N=256, M=1, T=16, H=60, W=60, res=0.2, B=4, seed=15)
+    pls = []
+    for r in range(2):
+        cfg = eng.Config(**sc["cfg"])
+        lin, ang = eng.TDM_Numba(cfg, rank=r, world_size=2), eng.TDM_Numba(cfg, rank=r, world_size=2)
+        lin.set_TDM_from_PMF_grid(sc["pmf_lin"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+        ang.set_TDM_from_PMF_grid(sc["pmf_ang"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+        pl = eng.MPPI_Numba(cfg, rank=r, world_size=2)
+        pl.setup(sc["params"], lin, ang)
+        pl.move_mppi_task_vars_to_device()
+        pls.append((pl, lin, ang))
+    _connect_local(L, [p[0] for p in pls])
+    pl = pls[0][0]
+    L.check(L.lib.b200mppi_planner_solve_local(pl._handle, 1))
+    L.check(L.lib.b200mppi_planner_p2p_reduce(pl._handle))
+    u = np.empty((16, 2), np.float32)
+    rc = L.lib.b200mppi_planner_p2p_finish(pl._handle, L.ptr(u))          # rank 1 never posts its partial
+    assert rc != 0
+    assert "rank 1" in L.lib.b200mppi_last_error().decode()
+
+
 # ----------------------------------------------------------------------------- 5. whole solve through the public API
 @pytest.mark.parametrize("mode", ["tdm", "det", "spd"])
 def test_solve_vs_reference_golden(eng, golden_dir, mode):
