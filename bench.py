@@ -8,8 +8,10 @@ A "step" is one MPPI_Numba.solve() (num_opt = 1): sample both traction-distribut
 each), sample control noise, N x M x T rollouts with cost accumulation, CVaR over M, softmax update,
 D2H of the T x 2 control sequence.  Workload (BASELINE.json configs[4], the one the metric and the
 north-star target are quoted on; it fits one GPU): CVaR-cost MPPI, N=8192, M=256, T=128, 1024x1024
-PMF grid (12 bins, res 0.1 m) -- at N GPUs the 8192 control sequences are sharded over the ranks
-("strong" scaling) with one all-gather of 2T+2 floats per solve.
+PMF grid (12 bins, res 0.1 m) -- at N GPUs the 256 sampled maps are sharded over the ranks ("strong"
+scaling): every rank rolls all 8192 control sequences out on its M/N maps, the per-(n,m) costs are
+exchanged all-to-all and the 2T+2-float softmax partials all-gathered, by the library's own
+peer-memory kernels over NVLink (B200MPPI_EXCHANGE=nccl: by two NCCL collectives).
 
 `value`  : device-timed (CUDA events on the planner's stream), inputs resident in HBM.
 `e2e`    : the same metric through the public Python API from HOST buffers -- every step does
@@ -293,10 +295,15 @@ def run_b200(args, sc):
 
     # ---- device-timed region: K solves, inputs resident
     clocks = ClockSampler(local)          # started before the warm-up: nvidia-smi needs ~0.3 s to produce a sample
+    t_w = time.perf_counter()
     for _ in range(args.warmup):
         pl.solve()
-    t_settle = time.perf_counter()
-    while time.perf_counter() - t_settle < 0.5:       # keep the GPU under the benchmark load while sampling starts
+    per_solve = max((time.perf_counter() - t_w) / args.warmup, 1e-5) if args.warmup > 0 else 2e-3
+    # keep the GPU under the benchmark load for ~0.5 s while the clock sampler starts.  Every solve() of a
+    # multi-rank run contains exchanges, so the NUMBER of extra solves must be the same on every rank:
+    # agree on it (max over ranks) instead of looping on each rank's own wall clock.
+    n_settle = int(max_over_ranks(float(min(5000, int(0.5 / per_solve) + 1))))
+    for _ in range(n_settle):
         pl.solve()
     barrier()
     clocks.lines.clear()
@@ -310,9 +317,9 @@ def run_b200(args, sc):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     launches = pl.launch_count() - l0      # kernels launched in the timed region
-    if len(clocks.lines) < 3:                         # very short timed region: extend the load for the sampler only
-        t_more = time.perf_counter()
-        while time.perf_counter() - t_more < 0.4:
+    # very short timed region: extend the load for the clock sampler only (same count on every rank)
+    if max_over_ranks(1.0 if len(clocks.lines) < 3 else 0.0) > 0.0:
+        for _ in range(int(min(5000, int(0.4 / (ms * 1e-3)) + 1))):
             pl.solve()
     clk = clocks.stop()
     value = units / (ms * 1e-3)
@@ -371,6 +378,9 @@ def run_b200(args, sc):
                "data": "synthetic",
                "config": {"workload": workload_name(args, sc), "global_rollouts": N, "maps": M, "horizon": T,
                           "parallelism": ("maps sharded x%d (M/G maps per rank, all N rollouts), all-to-all of N*M/G costs + all-gather of %d floats per solve" if sc["mode"] == "tdm" else "N-sharded x%d, 1 all-gather of %d floats per solve") % (world, 2 * T + 2),
+                          "exchange": ("none (1 rank)" if world == 1 else
+                                       "peer-memory kernels over NVLink (csrc/p2p.cu)" if getattr(pl, "_p2p", False)
+                                       else "NCCL all_to_all_single + all_gather"),
                           "l2": "per-step working set (2 x %d MB sampled maps) exceeds the 126 MB L2; no explicit flush"
                                 % (M * cfg.max_map_dim[0] * cfg.max_map_dim[1] // 2 ** 20)},
                "clocks": clk,

@@ -211,7 +211,7 @@ int b200mppi_planner_solve_finish(b200mppi_planner* pl, const float* gathered_pa
  *   solve_p2p         : num_opt x (solve_local, p2p_push, p2p_reduce, p2p_finish) -- the whole sharded solve()
  *                       in one call, no host synchronisation until the final copy of u.
  * A rank that never arrives does not hang the device: the waits give up after B200MPPI_P2P_TIMEOUT_MS
- * (environment, default 2000) and the call returns B200MPPI_ECUDA naming the missing rank. */
+ * (environment, default 20000) and the call returns B200MPPI_ECUDA naming the missing rank. */
 int b200mppi_planner_p2p_export(b200mppi_planner* pl, void* ipc_handle_out, size_t bytes);
 int b200mppi_planner_p2p_import(b200mppi_planner* pl, const void* ipc_handles, size_t bytes);
 int b200mppi_planner_p2p_connect_local(b200mppi_planner* pl, b200mppi_planner* const* peers, int32_t count);

@@ -94,6 +94,7 @@ static void tdm_advance_sig(b200mppi_tdm* t) {
 
 // Row segments per generator tile: enough CTAs to fill the GPU (the stream of a generator is sequential,
 // so parallelism beyond M*tx*ty generators comes from GF(2) jump-ahead), at most 8.
+constexpr int SAMPLE_MAX_SEGS = 33;
 static int tdm_prepare_jump(b200mppi_tdm* t, cudaStream_t st) {
   const int tx = t->cfg.tdm_thread_x, ty = t->cfg.tdm_thread_y;
   const int nrow = (t->rows + tx - 1) / tx, ncol = (t->cols + ty - 1) / ty;
@@ -102,14 +103,14 @@ static int tdm_prepare_jump(b200mppi_tdm* t, cudaStream_t st) {
   // tail; measured on config 5: 1 / 2 / 4 / 8 segments -> 1.63 / 1.50 / 1.37 / 1.32 ms
   int segs = (4096 + tx * groups - 1) / (tx * groups);
   if (const char* e = getenv("B200MPPI_SAMPLE_SEGS")) segs = atoi(e);      // tuning / test hook
-  if (segs > 16) segs = 16;
+  if (segs > SAMPLE_MAX_SEGS) segs = SAMPLE_MAX_SEGS;
   if (segs > nrow) segs = nrow;
   if (segs < 1) segs = 1;
   const int seg_rows = (nrow + segs - 1) / segs;
   if (t->jump_d && t->jump_segs == segs && t->jump_seg_rows == seg_rows && t->jump_rows == t->rows &&
       t->jump_cols == t->cols)
     return B200MPPI_OK;
-  if (!t->jump_d) CU(cudaMalloc(&t->jump_d, (size_t)15 * 2 * 256 * sizeof(uint64_t)));
+  if (!t->jump_d) CU(cudaMalloc(&t->jump_d, (size_t)(SAMPLE_MAX_SEGS - 1) * 2 * 256 * sizeof(uint64_t)));
   if (segs > 1) {
     // width classes: 0 = full tile column (ncol cells), 1 = the last, narrower column
     int last_w = t->cols - (ty - 1) * ncol;
@@ -515,7 +516,7 @@ struct b200mppi_planner {
   bool peer_ipc[P2P_MAX_PEERS] = {};
   bool p2p_ready = false;
   uint32_t epoch_cost = 0, epoch_part = 0;
-  unsigned long long p2p_timeout_ns = 2000000000ull;
+  unsigned long long p2p_timeout_ns = 20000000000ull;   // 20 s: start-up skew between ranks is seconds
   int num_ctas = 1, rows_per_cta = 1;
   b200mppi_tdm* lin = nullptr; b200mppi_tdm* ang = nullptr;
   b200mppi_params prm{};
