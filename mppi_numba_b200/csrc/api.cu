@@ -93,14 +93,15 @@ static void tdm_advance_sig(b200mppi_tdm* t) {
 }
 
 // Row segments per generator tile: enough CTAs to fill the GPU (the stream of a generator is sequential,
-// so parallelism beyond M*tx*ty generators comes from GF(2) jump-ahead), at most 8.
+// so parallelism beyond M*tx*ty generators comes from GF(2) jump-ahead), at most SAMPLE_MAX_SEGS.
 constexpr int SAMPLE_MAX_SEGS = 33;
 static int tdm_prepare_jump(b200mppi_tdm* t, cudaStream_t st) {
   const int tx = t->cfg.tdm_thread_x, ty = t->cfg.tdm_thread_y;
   const int nrow = (t->rows + tx - 1) / tx, ncol = (t->cols + ty - 1) / ty;
   const int groups = (t->num_maps + 7) / 8;
   // enough CTAs (~4k, i.e. several waves of the 5 resident CTAs per SM) to keep 148 SMs busy through the
-  // tail; measured on config 5: 1 / 2 / 4 / 8 segments -> 1.63 / 1.50 / 1.37 / 1.32 ms
+  // tail; measured on config 5: 1 / 2 / 4 / 8 segments -> 1.63 / 1.50 / 1.37 / 1.32 ms.  A rank holding M/8 = 32
+  // maps (8 GPUs) needs 2-row segments (33 of them): 0.183 ms against 0.208 ms with 16 (tools/sampler_segs.py)
   int segs = (4096 + tx * groups - 1) / (tx * groups);
   if (const char* e = getenv("B200MPPI_SAMPLE_SEGS")) segs = atoi(e);      // tuning / test hook
   if (segs > SAMPLE_MAX_SEGS) segs = SAMPLE_MAX_SEGS;
