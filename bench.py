@@ -377,7 +377,7 @@ def run_b200(args, sc):
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
                "config": {"workload": workload_name(args, sc), "global_rollouts": N, "maps": M, "horizon": T,
-                          "parallelism": ("maps sharded x%d (M/G maps per rank, all N rollouts), all-to-all of N*M/G costs + all-gather of %d floats per solve" if sc["mode"] == "tdm" else "N-sharded x%d, 1 all-gather of %d floats per solve") % (world, 2 * T + 2),
+                          "parallelism": "single GPU" if world == 1 else ("maps sharded x%d (M/G maps per rank, all N rollouts), all-to-all of N*M/G costs + all-gather of %d floats per solve" if sc["mode"] == "tdm" else "N-sharded x%d, 1 all-gather of %d floats per solve") % (world, 2 * T + 2),
                           "exchange": ("none (1 rank)" if world == 1 else
                                        "peer-memory kernels over NVLink (csrc/p2p.cu)" if getattr(pl, "_p2p", False)
                                        else "NCCL all_to_all_single + all_gather"),
