@@ -154,8 +154,40 @@ def make_barebone_golden(cuda):
     print("barebone done")
 
 
+def make_oversized_golden(MPPI_Numba, cuda):
+    """rollout_oversized_numba (mppi.py:760-913), the kernel behind solve_stochastic_oversized, on the inputs
+    of ref_rollout.npz.  Launched with FEWER threads than maps (4 threads, 6 maps -> 2 maps per thread), which
+    is exactly the regime the reference uses it in (num_grid_samples > 1024 threads).  alpha = 1 is its
+    meaningful output (the mean).  alpha < 1 cannot be recorded: besides swapping unconditionally
+     its "sort" indexes thread_cost_shared[tid + ri*num_threads] without bounding it by M
+    (mppi.py:879-895) -- the simulator raises IndexError, a GPU reads past the array."""
+    f32 = np.float32
+    g = np.load(os.path.join(OUT, "ref_rollout.npz"))
+    dev = cuda.to_device
+    N = g["noise"].shape[0]
+    M = g["lin"].shape[0]
+    out = {}
+    for gname in ("near", "far"):
+        goal = g["xgoal_" + gname]
+        for alpha in (1.0,):
+            costs_d = cuda.device_array((N,), dtype=f32)
+            MPPI_Numba.rollout_oversized_numba[N, 4, 0, 4 * M](
+                dev(g["lin"]), dev(g["ang"]), dev(np.array([0, 1], f32)), dev(np.array([0, 1], f32)), dev(g["obs"]),
+                dev(g["unk"]), f32(g["res"]), dev(g["xlim"]), dev(g["ylim"]), dev(np.array([0, 3], f32)),
+                dev(np.array([-np.pi, np.pi], f32)), dev(goal), f32(0.01), f32(1e5), f32(1e2), f32(0.5), f32(1.0),
+                dev(np.array([2, 3], f32)), f32(alpha), dev(g["x0"]), f32(0.1), 1.0, dev(g["noise"]), dev(g["u_cur"]),
+                costs_d)
+            out["over_a%02d_%s" % (int(alpha * 10), gname)] = costs_d.copy_to_host()
+        print("oversized", gname, "done")
+    np.savez_compressed(os.path.join(OUT, "ref_oversized.npz"), threads=4, **out)
+
+
 def main():
     from oracle.ref_loader import load_reference
+    if "--only-oversized" in sys.argv:
+        Config, TDM_Numba, MPPI_Numba, cuda = load_reference()
+        make_oversized_golden(MPPI_Numba, cuda)
+        return
     Config, TDM_Numba, MPPI_Numba, cuda = load_reference()
     os.makedirs(OUT, exist_ok=True)
     f32 = np.float32
@@ -288,6 +320,7 @@ def main():
         common["spd_" + gname] = launch_det(goal, True)
         print("rollouts", gname, "done")
     np.savez_compressed(os.path.join(OUT, "ref_rollout.npz"), **common)
+    make_oversized_golden(MPPI_Numba, cuda)          # the M > 1024 kernel on the same inputs
 
     # ---------------------------------------------------------------- 4. update (mppi.py:1113-1191), launched [1,1]
     rng = np.random.default_rng(13)

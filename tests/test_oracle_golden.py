@@ -123,6 +123,17 @@ def test_rollouts_match_reference(golden_dir, gname):
     np.testing.assert_allclose(spd, g["spd_" + gname], rtol=2e-6)
 
 
+@pytest.mark.parametrize("gname", ["near", "far"])
+def test_oversized_kernel_mean_matches_reference(golden_dir, gname):
+    """rollout_oversized_numba (mppi.py:760-913; num_grid_samples > threads per block, several maps per thread)
+    at cvar_alpha = 1, its only meaningful setting (for alpha < 1 it swaps unconditionally and
+    indexes shared memory out of bounds): the oracle's mean over the M per-map costs is what it returns."""
+    g = load(golden_dir, "ref_rollout.npz")
+    o = load(golden_dir, "ref_oversized.npz")
+    cnm = _rollout(g, MR.MODE_STOCHASTIC, g["xgoal_" + gname], g["lin"], g["ang"])
+    np.testing.assert_allclose(MR.cvar_reduce(cnm, 1.0), o["over_a10_" + gname], rtol=2e-6)
+
+
 def test_near_goal_case_exercises_early_exit(golden_dir):
     g = load(golden_dir, "ref_rollout.npz")
     # a reached rollout has no terminal cost: far smaller than dist/v_post of the others
