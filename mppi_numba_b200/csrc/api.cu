@@ -201,24 +201,15 @@ static int tdm_sample_pair_on(b200mppi_tdm* l, b200mppi_tdm* g, double alpha_dyn
   return B200MPPI_OK;
 }
 
-extern "C" int b200mppi_tdm_create(const b200mppi_config* cfg, b200mppi_tdm** out) {
-  if (!cfg || !out) return fail(B200MPPI_EINVAL, "tdm_create: null argument");
-  if (cfg->max_map_rows < 1 || cfg->max_map_cols < 1 || cfg->tdm_thread_x < 1 || cfg->tdm_thread_y < 1 ||
-      cfg->num_grid_samples < 1)
-    return fail(B200MPPI_EINVAL, "tdm_create: bad sizes");
-  if (b200mppi_device_count() < 1) return fail(B200MPPI_ECUDA, "tdm_create: no CUDA device (no CPU fallback)");
-  CU(cudaSetDevice(cfg->device));
-  b200mppi_tdm* t = new b200mppi_tdm();
+static int tdm_init(b200mppi_tdm* t, const b200mppi_config* cfg) {
   t->cfg = *cfg;
   t->det_dyn = cfg->mode != B200MPPI_MODE_TDM;
   // MODE_TDM with world_size > 1: the M sampled maps are sharded over the ranks (rank r owns maps
   // [r*M/ws, (r+1)*M/ws)); generator (tid_x, m, tid_y) keeps its GLOBAL index, so the union of the ranks'
   // maps is bit-identical to a single-rank run
   const int ws = cfg->world_size < 1 ? 1 : cfg->world_size;
-  if (!t->det_dyn && ws > 1 && cfg->num_grid_samples % ws != 0) {
-    delete t;
+  if (!t->det_dyn && ws > 1 && cfg->num_grid_samples % ws != 0)
     return fail(B200MPPI_EINVAL, "tdm_create: num_grid_samples must be divisible by world_size");
-  }
   t->num_maps = t->det_dyn ? 1 : cfg->num_grid_samples / ws;
   const int m_total = t->det_dyn ? 1 : cfg->num_grid_samples;
   const int m_begin = t->det_dyn ? 0 : cfg->rank * t->num_maps;
@@ -250,6 +241,26 @@ extern "C" int b200mppi_tdm_create(const b200mppi_config* cfg, b200mppi_tdm** ou
   CU(cudaMalloc(&t->states_alt, h.size() * sizeof(uint64_t)));
   CU(cudaMemcpyAsync(t->states, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, t->stream));
   CU(cudaStreamSynchronize(t->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_tdm_destroy(b200mppi_tdm* t);
+
+extern "C" int b200mppi_tdm_create(const b200mppi_config* cfg, b200mppi_tdm** out) {
+  if (!cfg || !out) return fail(B200MPPI_EINVAL, "tdm_create: null argument");
+  if (cfg->max_map_rows < 1 || cfg->max_map_cols < 1 || cfg->tdm_thread_x < 1 || cfg->tdm_thread_y < 1 ||
+      cfg->num_grid_samples < 1)
+    return fail(B200MPPI_EINVAL, "tdm_create: bad sizes");
+  if (b200mppi_device_count() < 1) return fail(B200MPPI_ECUDA, "tdm_create: no CUDA device (no CPU fallback)");
+  CU(cudaSetDevice(cfg->device));
+  b200mppi_tdm* t = new b200mppi_tdm();
+  const int rc = tdm_init(t, cfg);
+  if (rc) {                                   // release whatever was allocated before the failure
+    const std::string keep = g_err;
+    b200mppi_tdm_destroy(t);
+    g_err = keep;
+    return rc;
+  }
   *out = t;
   return B200MPPI_OK;
 }
@@ -582,26 +593,17 @@ static void fill_update_args(b200mppi_planner* p, UpdateArgs& u, const float* co
   u.wrange[0] = p->prm.wrange[0]; u.wrange[1] = p->prm.wrange[1];
 }
 
-extern "C" int b200mppi_planner_create(const b200mppi_config* cfg, b200mppi_planner** out) {
-  if (!cfg || !out) return fail(B200MPPI_EINVAL, "planner_create: null argument");
-  if (cfg->num_steps < 1 || cfg->num_steps > 1024 || cfg->num_control_rollouts < 1 || cfg->world_size < 1 ||
-      cfg->rank < 0 || cfg->rank >= cfg->world_size || cfg->num_grid_samples < 1)
-    return fail(B200MPPI_EINVAL, "planner_create: bad sizes (1 <= num_steps <= 1024)");
-  if (b200mppi_device_count() < 1) return fail(B200MPPI_ECUDA, "planner_create: no CUDA device (no CPU fallback)");
-  CU(cudaSetDevice(cfg->device));
-  b200mppi_planner* p = new b200mppi_planner();
+static int planner_init(b200mppi_planner* p, const b200mppi_config* cfg) {
   p->cfg = *cfg;
   const int64_t N = cfg->num_control_rollouts;
   p->n_begin = (int)(N * cfg->rank / cfg->world_size);
   p->n_local = (int)(N * (cfg->rank + 1) / cfg->world_size) - p->n_begin;
-  if (p->n_local < 1) { delete p; return fail(B200MPPI_EINVAL, "planner_create: empty shard"); }
+  if (p->n_local < 1) return fail(B200MPPI_EINVAL, "planner_create: empty shard");
   p->T = cfg->num_steps;
   p->M_total = cfg->mode == B200MPPI_MODE_TDM ? cfg->num_grid_samples : 1;
   p->shard_maps = cfg->mode == B200MPPI_MODE_TDM && cfg->world_size > 1;
-  if (p->shard_maps && (p->M_total % cfg->world_size != 0 || N % cfg->world_size != 0)) {
-    delete p;
+  if (p->shard_maps && (p->M_total % cfg->world_size != 0 || N % cfg->world_size != 0))
     return fail(B200MPPI_EINVAL, "planner_create: MODE_TDM sharding needs num_grid_samples and num_control_rollouts divisible by world_size");
-  }
   p->M = p->shard_maps ? p->M_total / cfg->world_size : p->M_total;
   p->n_roll = p->shard_maps ? (int)N : p->n_local;          // rollouts simulated by this rank
   p->n_red = p->n_local;                                    // rollouts reduced (CVaR, softmax) by this rank
@@ -643,6 +645,26 @@ extern "C" int b200mppi_planner_create(const b200mppi_config* cfg, b200mppi_plan
   CU(cudaMemcpyAsync(p->states, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
   for (auto& e : p->ev) CU(cudaEventCreate(&e));
   CU(cudaStreamSynchronize(p->stream));
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_destroy(b200mppi_planner* p);
+
+extern "C" int b200mppi_planner_create(const b200mppi_config* cfg, b200mppi_planner** out) {
+  if (!cfg || !out) return fail(B200MPPI_EINVAL, "planner_create: null argument");
+  if (cfg->num_steps < 1 || cfg->num_steps > 1024 || cfg->num_control_rollouts < 1 || cfg->world_size < 1 ||
+      cfg->rank < 0 || cfg->rank >= cfg->world_size || cfg->num_grid_samples < 1)
+    return fail(B200MPPI_EINVAL, "planner_create: bad sizes (1 <= num_steps <= 1024)");
+  if (b200mppi_device_count() < 1) return fail(B200MPPI_ECUDA, "planner_create: no CUDA device (no CPU fallback)");
+  CU(cudaSetDevice(cfg->device));
+  b200mppi_planner* p = new b200mppi_planner();
+  const int rc = planner_init(p, cfg);
+  if (rc) {                                   // release whatever was allocated before the failure
+    const std::string keep = g_err;
+    b200mppi_planner_destroy(p);
+    g_err = keep;
+    return rc;
+  }
   *out = p;
   return B200MPPI_OK;
 }
