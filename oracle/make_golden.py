@@ -182,8 +182,61 @@ def make_oversized_golden(MPPI_Numba, cuda):
     np.savez_compressed(os.path.join(OUT, "ref_oversized.npz"), threads=4, **out)
 
 
+def make_state_rollout_golden(Config, TDM_Numba, MPPI_Numba):
+    """get_state_rollout (mppi.py:545-608) and its two kernels (mppi.py:1194-1351) after the first solve() of
+    the ref_solve.npz scenario, for the three planner modes.  Everything the kernels read is stored next to
+    their output so that the oracle's restatement can be checked without re-running the solve."""
+    g = np.load(os.path.join(OUT, "ref_solve.npz"))
+    H, W = g["obstacle"].shape
+    res = float(g["res"])
+    out = {}
+    for mode, flags in (("tdm", dict(use_tdm=True)), ("det", dict(use_det_dynamics=True)),
+                        ("spd", dict(use_nom_dynamics_with_speed_map=True))):
+        cfg = _quiet(Config, T=float(g["T_s"]), dt=float(g["dt"]), num_grid_samples=int(g["M"]),
+                     num_control_rollouts=int(g["N"]), seed=int(g["seed"]),
+                     max_map_dim=tuple(int(v) for v in g["max_map_dim"]),
+                     tdm_sample_thread_dim=tuple(int(v) for v in g["thread_dim"]),
+                     max_speed_padding=float(g["max_speed_padding"]), num_vis_state_rollouts=5, **flags)
+        lt, at = _quiet(TDM_Numba, cfg), _quiet(TDM_Numba, cfg)
+        d = dict(res=res, xlimits=np.array([0.0, W * res]), ylimits=np.array([0.0, H * res]),
+                 bin_values=g["bin_values"], bin_values_bounds=np.array([0.0, 1.0]), det_dynamics_cvar_alpha=0.4)
+        _quiet(lt.set_TDM_from_PMF_grid, g["pmf_lin"], d, g["obstacle"], g["unknown"])
+        _quiet(at.set_TDM_from_PMF_grid, g["pmf_ang"], d, g["obstacle"], g["unknown"])
+        for t_ in (lt, at):
+            t_.sample_grid_batch_d.copy_to_device(np.zeros(t_.sample_grid_batch_d.shape, dtype=np.int8))
+        pl = _quiet(MPPI_Numba, cfg)
+        p = base_params([2.3, 3.1, 0.3], [5.0, 4.5], cvar_alpha=0.5)
+        pl.setup(p, lt, at)
+        orig = MPPI_Numba.update_useq_numba
+
+        class _One:                                  # SURVEY 9-R1: the update kernel is racy with 32 threads
+            def __getitem__(self, cfg_):
+                return orig[1, 1]
+        pl.update_useq_numba = _One()
+        u1 = _quiet(pl.solve).copy()
+        assert np.array_equal(u1, g[mode + "_u1"]), mode            # same run as ref_solve.npz
+        states = _quiet(pl.get_state_rollout).copy()
+        out[mode + "_states"] = states
+        out[mode + "_u_cur"] = pl.u_cur_d.copy_to_host().copy()
+        out[mode + "_u_prev"] = pl.u_prev_d.copy_to_host().copy()
+        out[mode + "_noise"] = pl.noise_samples_d.copy_to_host().copy()
+        out[mode + "_lin_grid"] = lt.sample_grid_batch_d.copy_to_host().copy()
+        out[mode + "_ang_grid"] = at.sample_grid_batch_d.copy_to_host().copy()
+        out[mode + "_pxl"] = np.asarray(lt.padded_xlimits, dtype=np.float64)
+        out[mode + "_pyl"] = np.asarray(lt.padded_ylimits, dtype=np.float64)
+        out[mode + "_V"] = int(pl.num_vis_state_rollouts)
+        print("state rollouts", mode, states.shape, "done")
+    out.update(x0=np.array([2.3, 3.1, 0.3]), res=res, dt=0.1, vrange=[0.0, 3.0], wrange=[-np.pi, np.pi],
+               bounds=[0.0, 1.0])
+    np.savez_compressed(os.path.join(OUT, "ref_state_rollout.npz"), **out)
+
+
 def main():
     from oracle.ref_loader import load_reference
+    if "--only-state-rollout" in sys.argv:
+        Config, TDM_Numba, MPPI_Numba, cuda = load_reference()
+        make_state_rollout_golden(Config, TDM_Numba, MPPI_Numba)
+        return
     if "--only-oversized" in sys.argv:
         Config, TDM_Numba, MPPI_Numba, cuda = load_reference()
         make_oversized_golden(MPPI_Numba, cuda)
@@ -382,6 +435,7 @@ def main():
         solve[mode + "_weights2"] = pl.weights_d.copy_to_host().copy()
         print("solve", mode, "done")
     np.savez_compressed(os.path.join(OUT, "ref_solve.npz"), **solve)
+    make_state_rollout_golden(Config, TDM_Numba, MPPI_Numba)     # get_state_rollout after the first solve
 
 
 if __name__ == "__main__":

@@ -187,6 +187,38 @@ def rollout_costs(mode, lin_grid, ang_grid, lin_bounds, ang_bounds, obstacle_map
     return cost
 
 
+def state_rollouts(mode, V, lin_grid, ang_grid, lin_bounds, ang_bounds, res, xlimits, ylimits, x0, dt,
+                   u_cur, u_prev=None, noise=None, vrange=None, wrange=None):
+    """get_state_rollout's kernels (mppi.py:1194-1351): float32 (V, T+1, 3), no goal test, no costs.
+
+    MODE_STOCHASTIC -- get_state_rollout_across_envs_numba (:1303-1351): u_cur, unclipped and without
+      noise, rolled out on sampled maps 0..V-1.
+    other modes -- get_state_rollout_across_control_noise (:1194-1300) on map 0 (tid == 0 in its one-thread
+      blocks): block 0 rolls out u_cur unclipped, block b > 0 rolls out clip(u_prev + noise[b])."""
+    u_cur = np.asarray(u_cur, dtype=F32)
+    T = u_cur.shape[0]
+    Hg, Wg = lin_grid.shape[1:]
+    zeros = np.zeros((Hg, Wg), dtype=np.int8)
+    far = np.array([1e18, 1e18], dtype=F32)              # never within the (zero) goal tolerance
+    wide = np.array([-np.inf, np.inf], dtype=F32)
+
+    def run(grid_mode, lg, ag, noise_, u_, vr, wr):
+        _, st = rollout_costs(grid_mode, lg, ag, lin_bounds, ang_bounds, zeros, zeros, res, xlimits, ylimits,
+                              vr, wr, far, 1.0, 0.0, 0.0, 0.0, 1.0, [1.0, 1.0], x0, dt, 1.0, noise_, u_,
+                              return_states=True)
+        return st
+    if mode == MODE_STOCHASTIC:
+        st = run(MODE_STOCHASTIC, lin_grid[:V], ang_grid[:V], np.zeros((1, T, 2), dtype=F32), u_cur, wide, wide)
+        return st[0]                                     # (V, T+1, 3)
+    out = np.zeros((V, T + 1, 3), dtype=F32)
+    out[0] = run(MODE_DET_DYN, lin_grid[:1], ang_grid[:1], np.zeros((1, T, 2), dtype=F32), u_cur, wide, wide)[0, 0]
+    if V > 1:
+        st = run(MODE_DET_DYN, lin_grid[:1], ang_grid[:1], np.asarray(noise, dtype=F32)[1:V],
+                 np.asarray(u_prev, dtype=F32), vrange, wrange)
+        out[1:] = st[:, 0]
+    return out
+
+
 def rollout_costs_barebone(obs_pos, obs_r, vrange, wrange, xgoal, obs_cost, goal_tolerance, lambda_weight, u_std,
                            x0, dt, dist_weight, noise, u_cur, return_states=False):
     """The map-free variant of the reference's barebone_mppi_numba.ipynb (cell 3, rollout_numba): nominal

@@ -694,6 +694,48 @@ def test_solve_vs_reference_golden(eng, golden_dir, mode):
     assert abs(float(w.sum()) - 1.0) < 1e-5
 
 
+@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: not yet run on hardware "
+                                        "(the oracle side is pinned in test_oracle_golden.py)")
+@pytest.mark.parametrize("mode", ["tdm", "det", "spd"])
+def test_state_rollout_vs_reference_golden(eng, golden_dir, mode):
+    """get_state_rollout() after the first solve() of the ref_solve.npz scenario against what the reference's
+    own kernels (mppi.py:1194-1351) returned (ref_state_rollout.npz), and against the oracle on the engine's
+    own buffers."""
+    g = load(golden_dir, "ref_solve.npz")
+    s = load(golden_dir, "ref_state_rollout.npz")
+    flags = dict(tdm=dict(use_tdm=True), det=dict(use_det_dynamics=True),
+                 spd=dict(use_nom_dynamics_with_speed_map=True))[mode]
+    cfg = eng.Config(T=float(g["T_s"]), dt=float(g["dt"]), num_grid_samples=int(g["M"]),
+                     num_control_rollouts=int(g["N"]), seed=int(g["seed"]),
+                     max_map_dim=tuple(int(v) for v in g["max_map_dim"]),
+                     tdm_sample_thread_dim=tuple(int(v) for v in g["thread_dim"]),
+                     max_speed_padding=float(g["max_speed_padding"]), num_vis_state_rollouts=5, **flags)
+    H, W = g["obstacle"].shape
+    res = float(g["res"])
+    d = dict(res=res, xlimits=np.array([0.0, W * res]), ylimits=np.array([0.0, H * res]),
+             bin_values=g["bin_values"], bin_values_bounds=np.array([0.0, 1.0]), det_dynamics_cvar_alpha=0.4)
+    lin, ang = eng.TDM_Numba(cfg), eng.TDM_Numba(cfg)
+    lin.set_TDM_from_PMF_grid(g["pmf_lin"], d, g["obstacle"], g["unknown"])
+    ang.set_TDM_from_PMF_grid(g["pmf_ang"], d, g["obstacle"], g["unknown"])
+    pl = eng.MPPI_Numba(cfg)
+    p = dict(dt=0.1, x0=np.array([2.3, 3.1, 0.3]), xgoal=np.array([5.0, 4.5]), goal_tolerance=0.5,
+             v_post_rollout=0.01, cvar_alpha=0.5, alpha_dyn=1.0, dist_weight=1.0, lambda_weight=1.0, num_opt=1,
+             u_std=np.array([2.0, 3.0]), vrange=np.array([0.0, 3.0]), wrange=np.array([-np.pi, np.pi]),
+             obs_penalty=1e5, unknown_penalty=1e2)
+    pl.setup(p, lin, ang)
+    pl.solve()
+    got = pl.get_state_rollout()
+    assert got.shape == s[mode + "_states"].shape
+    m = dict(tdm=MR.MODE_STOCHASTIC, det=MR.MODE_DET_DYN, spd=MR.MODE_SPEED_MAP)[mode]
+    want = MR.state_rollouts(m, got.shape[0], lin.sample_grid_batch_d.copy_to_host(),
+                             ang.sample_grid_batch_d.copy_to_host(), [0.0, 1.0], [0.0, 1.0], res, lin.padded_xlimits,
+                             lin.padded_ylimits, p["x0"], 0.1, pl.u_cur_d.copy_to_host(), pl.u_prev_d.copy_to_host(),
+                             pl.noise_samples_d.copy_to_host(), p["vrange"], p["wrange"])
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)              # same inputs: engine vs oracle
+    np.testing.assert_allclose(got, s[mode + "_states"], rtol=2e-3, atol=2e-3)   # vs the reference's run (its u1
+                                                                                 # differs from ours by ~1e-4)
+
+
 def test_solve_preconditions_and_api_surface(eng, capsys):
     sc = make_scenario("det", N=128, M=1, T=16, H=40, W=40, res=0.5, B=5, seed=9)
     cfg = eng.Config(**sc["cfg"])

@@ -134,6 +134,21 @@ def test_oversized_kernel_mean_matches_reference(golden_dir, gname):
     np.testing.assert_allclose(MR.cvar_reduce(cnm, 1.0), o["over_a10_" + gname], rtol=2e-6)
 
 
+@pytest.mark.parametrize("mode", ["tdm", "det", "spd"])
+def test_state_rollouts_match_reference(golden_dir, mode):
+    """get_state_rollout (mppi.py:545-608, kernels :1194-1351) after a solve of the reference, three modes."""
+    g = load(golden_dir, "ref_state_rollout.npz")
+    m = dict(tdm=MR.MODE_STOCHASTIC, det=MR.MODE_DET_DYN, spd=MR.MODE_SPEED_MAP)[mode]
+    got = MR.state_rollouts(m, int(g[mode + "_V"]), g[mode + "_lin_grid"], g[mode + "_ang_grid"], g["bounds"],
+                            g["bounds"], g["res"], g[mode + "_pxl"], g[mode + "_pyl"], g["x0"], g["dt"],
+                            g[mode + "_u_cur"], g[mode + "_u_prev"], g[mode + "_noise"], g["vrange"], g["wrange"])
+    ref = g[mode + "_states"]
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=2e-6, atol=2e-6)
+    if mode != "tdm":
+        assert not np.allclose(ref[0], ref[1])          # block 0 = optimal sequence, the others are noisy samples
+
+
 def test_near_goal_case_exercises_early_exit(golden_dir):
     g = load(golden_dir, "ref_rollout.npz")
     # a reached rollout has no terminal cost: far smaller than dist/v_post of the others
