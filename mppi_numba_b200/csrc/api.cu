@@ -354,12 +354,15 @@ extern "C" int b200mppi_tdm_set_pmf_collapsed(b200mppi_tdm* t, const int8_t* raw
   const bool speed = t->cfg.mode == B200MPPI_MODE_SPEED_MAP;
   const size_t raw_bytes = (size_t)B * H * W, out_bytes = (size_t)B * Hp * Wp;
   int8_t* raw_d = nullptr; float* bv_d = nullptr; int* bad_d = nullptr;
-  CU(cudaMalloc(&raw_d, raw_bytes));
-  CU(cudaMalloc(&bv_d, (size_t)B * sizeof(float)));
-  CU(cudaMalloc(&bad_d, sizeof(int)));
   std::vector<int8_t> host_out(out_bytes);
   int rc = B200MPPI_OK;
   do {
+    if (cudaMalloc(&raw_d, raw_bytes) != cudaSuccess || cudaMalloc(&bv_d, (size_t)B * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&bad_d, sizeof(int)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      rc = fail(B200MPPI_ENOMEM, "set_pmf_collapsed: cudaMalloc");
+      break;
+    }
     if (out_bytes > t->pmf_cap) { cudaFree(t->pmf); t->pmf = nullptr; if (cudaMalloc(&t->pmf, out_bytes) != cudaSuccess) { rc = fail(B200MPPI_ENOMEM, "set_pmf_collapsed: cudaMalloc"); break; } t->pmf_cap = out_bytes; }
     const int rpitch = round_up(Wp, 16);
     if (speed) {
@@ -435,6 +438,7 @@ extern "C" int b200mppi_tdm_set_masks(b200mppi_tdm* t, const int8_t* obs, const 
 
 extern "C" int b200mppi_tdm_set_risk_map(b200mppi_tdm* t, const int8_t* risk, int32_t rows, int32_t cols) {
   if (!t || !risk) return fail(B200MPPI_EINVAL, "set_risk_map: null argument");
+  if (rows < 1 || cols < 1) return fail(B200MPPI_EINVAL, "set_risk_map: bad shape");
   CU(cudaSetDevice(t->cfg.device));
   int rc = upload_plane(t, &t->risk, &t->risk_cap, risk, rows, cols, round_up(cols, 16));
   if (rc) return rc;
