@@ -174,6 +174,9 @@ __device__ __forceinline__ void xoro_jump(Xoro& s, const ulonglong2* __restrict_
   s.s0 = a0; s.s1 = a1;
 }
 
+// a | (~b & c): one LOP3 (c is a compile-time mask after unrolling -> immediate operand)
+__device__ __forceinline__ uint32_t or_andn(uint32_t a, uint32_t b, uint32_t c) { return a | (~b & c); }
+
 template <int NT, int NW>
 __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const SampleGridsV2Args a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
       const uint32_t* src = reinterpret_cast<const uint32_t*>(a.t[k].cum + (size_t)ri * row_bytes);
       uint32_t* dst = reinterpret_cast<uint32_t*>(s_cum + k * row_bytes_al);
 #pragma unroll 8
-      for (int i = tid; i < row_bytes / 4; i += nthreads) dst[i] = __ldg(src + i);
+      for (int i = tid; i < row_bytes / 4; i += nthreads) dst[i] = __ldg(src + i) | 0x80808080u;   // guard bits, see cell()
     }
     __syncthreads();
     if (active) {
@@ -253,17 +256,14 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
         for (int k = 0; k < NT; ++k) {
           const uint32_t* cw = reinterpret_cast<const uint32_t*>(s_cum + k * row_bytes_al + ci * bpad);
           uint32_t bits = 0;
+          // staged bytes carry bit 7 (guard): (0x80 | cum) - q never borrows across bytes (cum, q <= 127) and
+          // leaves bit 7 CLEAR exactly for the bytes with cum < q.  Word w contributes its four flags at bit
+          // 7-w of each byte: shift first, then one LOP3 does bits | (~z & mask)
           if (NW > 0) {
 #pragma unroll
-            for (int w = 0; w < (NW > 0 ? NW : 1); ++w) {
-              const uint32_t lt = ~((cw[w] | 0x80808080u) - qq) & 0x80808080u;   // bytes with cum < q
-              bits |= lt >> (7 - w);
-            }
+            for (int w = 0; w < (NW > 0 ? NW : 1); ++w) bits = or_andn(bits, (cw[w] - qq) >> (7 - w), 0x80808080u >> (7 - w));
           } else {
-            for (int w = 0; w < nw; ++w) {
-              const uint32_t lt = ~((cw[w] | 0x80808080u) - qq) & 0x80808080u;
-              bits |= lt >> (7 - w);
-            }
+            for (int w = 0; w < nw; ++w) bits = or_andn(bits, (cw[w] - qq) >> (7 - w), 0x80808080u >> (7 - w));
           }
           const int bin = __popc(bits);                       // cum is monotone: #bins below q = first bin >= q
           if (NW > 0 && NW <= 4) {                            // value table in registers: byte-permute lookup
