@@ -256,6 +256,13 @@ int b200mppi_planner_copy_in(b200mppi_planner* pl, int32_t buffer_id, const void
                              size_t bytes);
 int b200mppi_planner_synchronize(b200mppi_planner* pl);
 
+/* Test hook (host only, no GPU needed): the sampler's threshold lookup q(draw) for raw 64-bit xoroshiro draws --
+ * the same inline function and tables the kernel uses (terrain.py:682-684 restated as an integer table, see
+ * csrc/common.cuh::sample_threshold_q).  q_cap = the smallest column total of the PMF (100 for a proper PMF).
+ * B200MPPI_ESTATE if alpha_dyn is not representable (the sampler then uses its generic kernel). */
+int b200mppi_debug_sample_threshold(double alpha_dyn, int32_t q_cap, const uint64_t* draws, int64_t n,
+                                    uint8_t* q_out);
+
 /* Tracing: CUDA-event time of each stage of the last solve/solve_local+finish, milliseconds.
  * Enabled with b200mppi_planner_set_profiling(pl, 1) (adds event records, no syncs). */
 enum {

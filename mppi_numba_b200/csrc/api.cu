@@ -77,7 +77,7 @@ static inline uint64_t mix_sig(uint64_t h, uint64_t v) {
 
 static int tdm_prepare_thresholds(b200mppi_tdm* t, double alpha, cudaStream_t st) {
   if (t->thr_alpha == alpha && t->thr_d) return B200MPPI_OK;
-  uint64_t T[256];
+  uint64_t T[SAMPLE_TABLE_WORDS];
   t->thr_ok = t->pmf_valid && build_sample_thresholds(alpha, t->min_total, T);
   t->thr_alpha = alpha;
   if (!t->thr_d) CU(cudaMalloc(&t->thr_d, sizeof(T)));
@@ -444,6 +444,20 @@ extern "C" int b200mppi_tdm_set_risk_map(b200mppi_tdm* t, const int8_t* risk, in
   if (rc) return rc;
   CU(cudaStreamSynchronize(t->stream));
   t->risk_set = true;
+  return B200MPPI_OK;
+}
+
+// Host-side evaluation of the sampler's threshold lookup (the very function the kernel inlines): lets the
+// CPU test-suite check the bucket tables against the reference's float arithmetic without a GPU.
+extern "C" int b200mppi_debug_sample_threshold(double alpha_dyn, int32_t q_cap, const uint64_t* draws, int64_t n,
+                                               uint8_t* q_out) {
+  if (!draws || !q_out || n < 0) return fail(B200MPPI_EINVAL, "debug_sample_threshold: bad argument");
+  uint64_t T[SAMPLE_TABLE_WORDS];
+  if (!build_sample_thresholds(alpha_dyn, q_cap, T))
+    return fail(B200MPPI_ESTATE, "debug_sample_threshold: alpha_dyn / q_cap not representable by the bucket table "
+                                 "(the sampler falls back to its generic kernel)");
+  const unsigned char* Q = reinterpret_cast<const unsigned char*>(T + 256);
+  for (int64_t i = 0; i < n; ++i) q_out[i] = (uint8_t)sample_threshold_q(draws[i], T, Q);
   return B200MPPI_OK;
 }
 

@@ -187,8 +187,9 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
   const int stage_pitch = (a.cols + 15) & ~15;
   unsigned char* s_cum = smem;                               // [NT][row_bytes_al]
   unsigned char* s_stage = s_cum + NT * row_bytes_al;        // [NT][GM][stage_pitch]
-  uint64_t* s_T = reinterpret_cast<uint64_t*>(s_stage + NT * SG_GM * stage_pitch);   // [256] bucket table
-  unsigned char* s_q = reinterpret_cast<unsigned char*>(s_T + 256);                  // [NT][128]
+  uint64_t* s_T = reinterpret_cast<uint64_t*>(s_stage + NT * SG_GM * stage_pitch);   // [256] bucket thresholds
+  const unsigned char* s_Q = reinterpret_cast<const unsigned char*>(s_T + 256);      // [256] q at bucket start
+  unsigned char* s_q = reinterpret_cast<unsigned char*>(s_T + SAMPLE_TABLE_WORDS);   // [NT][128]
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int tiy = tid % a.ty, mloc = tid / a.ty;
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
   const int m = blockIdx.y * SG_GM + mloc;
   const bool active = (mloc < SG_GM) && (m < a.num_maps);
 
-  for (int i = tid; i < 256; i += nthreads) s_T[i] = a.thresholds[i];
+  for (int i = tid; i < SAMPLE_TABLE_WORDS; i += nthreads) s_T[i] = a.thresholds[i];   // thresholds + the qbase bytes
   for (int i = tid; i < 128; i += nthreads) {
     s_q[i] = (unsigned char)a.t[0].qvals[i];
     if (NT == 2) s_q[128 + i] = (unsigned char)a.t[1].qvals[i];
@@ -247,10 +248,9 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
       // one cell: threshold from the 53-bit draw, then the first bin whose cumulative mass reaches it.
       // Returns the sampled value byte of each TDM; the caller stores them AFTER a group of cells so that
       // the shared-memory loads of the whole group are independent of the byte stores (ILP).
-      auto cell = [&](int ci, uint64_t v, uint32_t (&outv)[NT]) {
-        // bucket of the draw's top 8 bits: q at the bucket start and the single breakpoint inside it
-        const uint64_t e = s_T[(uint32_t)(v >> 45)];
-        const uint32_t q = (uint32_t)(e >> 56) + (v >= (e & 0x00FFFFFFFFFFFFFFULL));
+      auto cell = [&](int ci, uint64_t r, uint32_t (&outv)[NT]) {
+        // bucket of the raw draw's top 8 bits: q at the bucket start and the single breakpoint inside it
+        const uint32_t q = sample_threshold_q(r, s_T, s_Q);
         const uint32_t qq = q * 0x01010101u;
 #pragma unroll
         for (int k = 0; k < NT; ++k) {
@@ -279,12 +279,12 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
       unsigned char* st1 = s_stage + (SG_GM + mloc) * stage_pitch;
       int ci = c0;
       for (; ci + 4 <= c1; ci += 4) {          // 4 draws in stream order, then 4 independent cells (ILP)
-        uint64_t v[4];
+        uint64_t r[4];
         uint32_t o[4][NT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = xoro_next(s) >> 11;
+        for (int j = 0; j < 4; ++j) r[j] = xoro_next(s);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cell(ci + j, v[j], o[j]);
+        for (int j = 0; j < 4; ++j) cell(ci + j, r[j], o[j]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           st0[ci + j] = (unsigned char)o[j][0];
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
       }
       for (; ci < c1; ++ci) {
         uint32_t o[NT];
-        cell(ci, xoro_next(s) >> 11, o);
+        cell(ci, xoro_next(s), o);
         st0[ci] = (unsigned char)o[0];
         if (NT == 2) st1[ci] = (unsigned char)o[NT - 1];
       }
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
 size_t sample_grids_v2_smem(const SampleGridsV2Args& a, int nt) {
   const int row_bytes_al = (a.cols * a.t[0].bpad + 15) & ~15;
   const int stage_pitch = (a.cols + 15) & ~15;
-  return (size_t)nt * row_bytes_al + (size_t)nt * SG_GM * stage_pitch + 256 * 8 + (size_t)nt * 128;
+  return (size_t)nt * row_bytes_al + (size_t)nt * SG_GM * stage_pitch + SAMPLE_TABLE_WORDS * 8 + (size_t)nt * 128;
 }
 
 template <int NT>
@@ -408,7 +408,7 @@ static inline int q_of_v(uint64_t v, double alpha) {
   return (int)(int8_t)(int16_t)c;
 }
 
-bool build_sample_thresholds(double alpha, int q_cap, uint64_t* B /*[256]*/) {
+bool build_sample_thresholds(double alpha, int q_cap, uint64_t* B /*[SAMPLE_TABLE_WORDS]*/) {
   if (!(alpha >= 0.0) || !(alpha * 100.0 <= 127.0)) return false;
   const uint64_t VMAX = (1ULL << 53) - 1;
   const int qmax = q_of_v(VMAX, alpha);
@@ -423,18 +423,32 @@ bool build_sample_thresholds(double alpha, int q_cap, uint64_t* B /*[256]*/) {
     }
     T[k] = hi;
   }
-  // bucket b covers v in [b << 45, (b+1) << 45): entry = q(start) << 56 | first breakpoint above start
-  // (2^53 = "none").  Valid iff at most one breakpoint lies strictly inside each bucket.
+  // bucket b covers the 53-bit draws v in [b << 45, (b+1) << 45), i.e. the RAW draws r = v << 11 | (11 low bits) in
+  // [b << 56, (b+1) << 56): v >= T[k]  <=>  r >= T[k] << 11.  Valid iff at most one breakpoint lies strictly inside
+  // each bucket and it raises q by exactly one.  No breakpoint inside: thr = 0 ("r >= thr" always true), qbase = q-1.
+  unsigned char* Q = reinterpret_cast<unsigned char*>(B + 256);
   for (int b = 0; b < 256; ++b) {
     const uint64_t start = (uint64_t)b << 45, end = start + (1ULL << 45);
     const int qb = q_of_v(start, alpha);
-    uint64_t next = 1ULL << 53;
+    uint64_t next = 0;
     int inside = 0;
     for (int k = 1; k <= qmax; ++k)
       if (T[k] > start && T[k] < end) { if (!inside) next = T[k]; ++inside; }
     if (inside > 1 || qb < 0 || qb > 127) return false;
-    if (inside == 1 && q_of_v(next, alpha) != qb + 1) return false;     // the breakpoint raises q by exactly one
-    B[b] = ((uint64_t)qb << 56) | next;
+    if (inside == 1) {
+      if (q_of_v(next, alpha) != qb + 1) return false;
+      B[b] = next << 11;
+      Q[b] = (unsigned char)qb;
+    } else if (qb > 0) {
+      B[b] = 0;
+      Q[b] = (unsigned char)(qb - 1);
+    } else {
+      // q = 0 over a whole bucket: only v = 0 has q = 0 for alpha > 0 (bucket 0 then holds the breakpoint v = 1),
+      // so this is alpha = 0; "never" needs thr > every r of the bucket, which bucket 255 cannot offer
+      if (b == 255) return false;
+      B[b] = ~0ULL;
+      Q[b] = 0;
+    }
   }
   return true;
 }

@@ -128,3 +128,51 @@ def test_combine_partials_host_matches_oracle_update(libmod):
                                                           libmod.ptr(vr), libmod.ptr(wr), libmod.ptr(out)))
     want, _ = MR.update_useq(lam, costs, noise, vr, wr, u0)
     np.testing.assert_allclose(out, want, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.9, 0.6, 0.3, 0.05, 1.27])
+def test_sampler_threshold_tables_match_reference_arithmetic(libmod, alpha):
+    """The sampler replaces q = int8(ceil(f64(f32((r >> 11) * 2^-53)) * 100 * alpha)) (terrain.py:682-684;
+    numba's uint64_to_unit_float32, random.py:130-154) by a two-table lookup on the raw draw.  The very function
+    the kernel inlines, evaluated on the host (b200mppi_debug_sample_threshold), against the oracle's float
+    arithmetic: random draws, every bucket edge, and both sides of every breakpoint."""
+    from oracle import terrain_ref as TR
+    rng = np.random.default_rng(int(alpha * 1000))
+    r = rng.integers(0, 2 ** 64, 400000, dtype=np.uint64)
+    edges = (np.arange(256, dtype=np.uint64) << np.uint64(56))
+    r = np.concatenate([r, edges, edges - np.uint64(1), edges + np.uint64(1), edges + np.uint64(2047), edges + np.uint64(2048),
+                        np.array([0, 1, 2047, 2048, 2 ** 64 - 1, 2 ** 64 - 2048, 2 ** 64 - 2049], dtype=np.uint64)])
+
+    def oracle_q(raw):
+        u = ((raw >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)).astype(np.float32)
+        return TR.sample_thresholds(u, alpha).astype(np.int64)
+
+    def engine_q(raw):
+        raw = np.ascontiguousarray(raw, dtype=np.uint64)
+        out = np.empty(raw.shape, np.uint8)
+        libmod.check(libmod.lib.b200mppi_debug_sample_threshold(alpha, 127, libmod.ptr(raw), raw.size, libmod.ptr(out)))
+        return out.astype(np.int64)
+    want = oracle_q(r)
+    assert (engine_q(r) == want).all()
+    # both sides of every breakpoint: bisect the oracle on the 53-bit draw v for each q level
+    pts = []
+    for k in range(1, int(want.max()) + 1):
+        lo, hi = 0, 2 ** 53 - 1                       # q(lo) < k <= q(hi)
+        while hi - lo > 1:
+            mid = (lo + hi) // 2
+            if oracle_q(np.array([mid << 11], dtype=np.uint64))[0] >= k:
+                hi = mid
+            else:
+                lo = mid
+        pts += [(hi << 11) - 1, hi << 11, (hi << 11) + 2047, (lo << 11), (lo << 11) + 2047]
+    pts = np.array(pts, dtype=np.uint64)
+    assert (engine_q(pts) == oracle_q(pts)).all()
+
+
+def test_sampler_threshold_tables_refuse_what_they_cannot_represent(libmod):
+    r = np.zeros(4, np.uint64)
+    out = np.empty(4, np.uint8)
+    # q would exceed the smallest column total / alpha beyond the int8 range -> generic kernel
+    assert libmod.lib.b200mppi_debug_sample_threshold(1.0, 50, libmod.ptr(r), 4, libmod.ptr(out)) != 0
+    assert libmod.lib.b200mppi_debug_sample_threshold(1.5, 127, libmod.ptr(r), 4, libmod.ptr(out)) != 0
+    assert "generic" in libmod.lib.b200mppi_last_error().decode()
