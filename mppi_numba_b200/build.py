@@ -27,7 +27,19 @@ def _newer(target, deps):
 
 
 def build_library(force=False, verbose=False):
-    """Compile every .cu under csrc/ and link the shared library.  Returns its path."""
+    """Compile every .cu under csrc/ and link the shared library.  Returns its path.
+    Serialised with a file lock: the ranks of a torchrun launch all call this at start-up, the first one
+    builds (if anything is stale), the others find everything up to date once they hold the lock."""
+    import fcntl
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
     objs = []
     log = []
