@@ -375,38 +375,54 @@ class TDM_Numba(object):
 
 
 class Terrain(object):
-    """Ground-truth traction statistics of one semantic class (simulation helper; the reference's
-    terrain.py:24-66).  ``lin_density`` / ``ang_density`` expose ``sample(n)``."""
+    """Ground-truth traction statistics of one semantic class: the reference's simulation helper
+    (terrain.py:24-66), same constructor and attributes.  ``lin_density`` / ``ang_density`` are duck-typed:
+    they must offer ``sample(n)``; ``mean(samples)``, ``var(samples)`` and ``cvar(alpha, samples=, front=)``
+    (-> (tail mean, threshold), the reference's density.py:25-56) are used when present, numpy otherwise."""
 
-    def __init__(self, name, lin_density, ang_density, cvar_alpha=0.1, cvar_front=True,
-                 num_saved_samples=1e4, rgb=None):
+    def __init__(self, name, rgb, lin_density, ang_density, cvar_alpha=0.1, cvar_front=True, num_saved_samples=1e4):
         self.name = name
-        self.lin_density, self.ang_density = lin_density, ang_density
-        self.cvar_alpha, self.cvar_front = cvar_alpha, cvar_front
-        self.num_saved_samples = int(num_saved_samples)
         self.rgb = rgb
-        self.update_stats()
+        self.lin_density, self.ang_density = lin_density, ang_density
+        self.num_saved_samples = num_saved_samples
+        self.lin_saved_samples = np.asarray(lin_density.sample(int(num_saved_samples)))
+        self.ang_saved_samples = np.asarray(ang_density.sample(int(num_saved_samples)))
+        self.cvar_alpha, self.cvar_front = cvar_alpha, cvar_front
+        for axis in ("lin", "ang"):
+            dens, smp = getattr(self, axis + "_density"), getattr(self, axis + "_saved_samples")
+            mean = dens.mean(smp) if hasattr(dens, "mean") else np.mean(smp)
+            var = dens.var(smp) if hasattr(dens, "var") else np.var(smp)
+            setattr(self, axis + "_mean", mean)
+            setattr(self, axis + "_var", var)
+            setattr(self, axis + "_std", np.sqrt(var))
+        self.update_cvar_alpha(cvar_alpha)
 
     @staticmethod
-    def _tail_mean(samples, alpha, front):
-        s = np.sort(samples)
-        k = max(1, int(math.ceil(alpha * len(s))))
-        return float(np.mean(s[:k] if front else s[-k:]))
+    def _tail(dens, samples, alpha, front):
+        """(mean of the alpha-tail, its percentile threshold): the lower tail if ``front``, else the upper one;
+        samples equal to the threshold are excluded (density.py:41-56)."""
+        if hasattr(dens, "cvar"):
+            return dens.cvar(alpha, samples=samples, front=front)
+        thres = np.percentile(samples, alpha * 100.0 if front else (1.0 - alpha) * 100.0)
+        tail = samples[samples < thres] if front else samples[samples > thres]
+        assert tail.size > 0
+        return np.mean(tail), thres
 
-    def update_stats(self):
-        lin, ang = self.sample_traction(self.num_saved_samples)
-        self.lin_mean, self.ang_mean = float(np.mean(lin)), float(np.mean(ang))
-        self.lin_std, self.ang_std = float(np.std(lin)), float(np.std(ang))
-        self.lin_cvar = self._tail_mean(lin, self.cvar_alpha, self.cvar_front)
-        self.ang_cvar = self._tail_mean(ang, self.cvar_alpha, self.cvar_front)
+    def update_cvar_alpha(self, alpha):
+        assert alpha > 0 and alpha <= 1.0
+        self.cvar_alpha = alpha
+        self.lin_cvar, self.lin_cvar_thres = self._tail(self.lin_density, self.lin_saved_samples, alpha, self.cvar_front)
+        self.ang_cvar, self.ang_cvar_thres = self._tail(self.ang_density, self.ang_saved_samples, alpha, self.cvar_front)
 
     def sample_traction(self, num_samples):
         return self.lin_density.sample(num_samples), self.ang_density.sample(num_samples)
 
     def __repr__(self):
-        return ("Terrain {}: mean=({:.2f}, {:.2f}), std=({:.2f}, {:.2f}), cvar({:.2f})=({:.2f}, {:.2f})"
-                .format(self.name, self.lin_mean, self.ang_mean, self.lin_std, self.ang_std,
-                        self.cvar_alpha, self.lin_cvar, self.ang_cvar))
+        return ("Terrain {} has the following properties for linear and angular tractions.\n"
+                "mean=({:.2f}, {:.2f}), std=({:.2f}, {:.2f}), cvar({:.2f})=({:.2f}, {:.2f}) "
+                "(computed from {} saved samples)").format(
+                    self.name, self.lin_mean, self.ang_mean, self.lin_std, self.ang_std, self.cvar_alpha,
+                    self.lin_cvar, self.ang_cvar, self.num_saved_samples)
 
 
 class TractionGrid(object):

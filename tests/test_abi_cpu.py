@@ -176,3 +176,48 @@ def test_sampler_threshold_tables_refuse_what_they_cannot_represent(libmod):
     assert libmod.lib.b200mppi_debug_sample_threshold(1.0, 50, libmod.ptr(r), 4, libmod.ptr(out)) != 0
     assert libmod.lib.b200mppi_debug_sample_threshold(1.5, 127, libmod.ptr(r), 4, libmod.ptr(out)) != 0
     assert "generic" in libmod.lib.b200mppi_last_error().decode()
+
+
+def test_terrain_helper_mirrors_reference_constructor_and_statistics(libmod):
+    """Terrain (terrain.py:24-66): positional order (name, rgb, lin_density, ang_density), saved samples, mean /
+    var / std, CVaR = mean of the samples strictly below (front) or above the alpha-percentile, and
+    update_cvar_alpha."""
+    from mppi_numba_b200.terrain import Terrain
+
+    class Dens:                                   # duck-typed: only sample()
+        def __init__(self, seed, lo, hi):
+            self.rng, self.lo, self.hi = np.random.default_rng(seed), lo, hi
+
+        def sample(self, n):
+            return self.rng.uniform(self.lo, self.hi, int(n))
+
+    t = Terrain("grass", (0, 255, 0), Dens(1, 0.2, 0.9), Dens(2, 0.1, 0.5), cvar_alpha=0.2, cvar_front=True,
+                num_saved_samples=2e3)
+    assert t.name == "grass" and t.rgb == (0, 255, 0) and t.num_saved_samples == 2e3
+    assert t.lin_saved_samples.shape == (2000,) and t.ang_saved_samples.shape == (2000,)
+    for axis in ("lin", "ang"):
+        smp = getattr(t, axis + "_saved_samples")
+        assert getattr(t, axis + "_mean") == np.mean(smp) and getattr(t, axis + "_var") == np.var(smp)
+        assert getattr(t, axis + "_std") == np.sqrt(np.var(smp))
+        thres = np.percentile(smp, 20.0)
+        assert getattr(t, axis + "_cvar_thres") == thres
+        assert getattr(t, axis + "_cvar") == np.mean(smp[smp < thres])
+    t.update_cvar_alpha(0.5)
+    assert t.cvar_alpha == 0.5 and t.lin_cvar == np.mean(t.lin_saved_samples[t.lin_saved_samples < np.median(t.lin_saved_samples)])
+    lin, ang = t.sample_traction(7)
+    assert lin.shape == (7,) and ang.shape == (7,)
+    assert "grass" in repr(t) and "2000" in repr(t).replace("2000.0", "2000")
+    up = Terrain("rock", None, Dens(3, 0, 1), Dens(4, 0, 1), cvar_alpha=0.1, cvar_front=False)
+    assert up.lin_cvar == np.mean(up.lin_saved_samples[up.lin_saved_samples > np.percentile(up.lin_saved_samples, 90.0)])
+
+    class Full(Dens):                             # a density that brings its own statistics (density.py:25-56)
+        def mean(self, samples=None):
+            return 1.0
+
+        def var(self, samples=None):
+            return 4.0
+
+        def cvar(self, alpha, front=True, samples=None):
+            return 0.25, 0.5
+    f = Terrain("x", None, Full(5, 0, 1), Full(6, 0, 1))
+    assert (f.lin_mean, f.lin_var, f.lin_std, f.lin_cvar, f.lin_cvar_thres) == (1.0, 4.0, 2.0, 0.25, 0.5)
