@@ -361,9 +361,13 @@ class TDM_Numba(object):
         ``TractionGrid`` for the simulated robot (terrain.py:586-608)."""
         lins = np.zeros_like(self.semantic_grid, dtype=float)
         angs = np.zeros_like(self.semantic_grid, dtype=float)
-        ids, counts = np.unique(self.semantic_grid, return_counts=True)
-        for sid, num in zip(ids, counts):
-            lin_s, ang_s = self.id2terrain_fn(sid).sample_traction(int(num))
+        ids, first, counts = np.unique(np.asarray(self.semantic_grid).ravel(), return_index=True, return_counts=True)
+        # classes are visited in order of first appearance (row-major), like the reference's dict walk: with a
+        # shared global RNG behind the densities this keeps the draws of every class identical to the reference's
+        drawn = {}
+        for k in np.argsort(first):
+            drawn[ids[k]] = self.id2terrain_fn(ids[k]).sample_traction(int(counts[k]))
+        for sid, (lin_s, ang_s) in drawn.items():
             mask = self.semantic_grid == sid
             lins[mask] = lin_s
             angs[mask] = ang_s

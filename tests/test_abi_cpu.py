@@ -221,3 +221,28 @@ def test_terrain_helper_mirrors_reference_constructor_and_statistics(libmod):
             return 0.25, 0.5
     f = Terrain("x", None, Full(5, 0, 1), Full(6, 0, 1))
     assert (f.lin_mean, f.lin_var, f.lin_std, f.lin_cvar, f.lin_cvar_thres) == (1.0, 4.0, 2.0, 0.25, 0.5)
+
+
+def test_sample_grids_true_dist_visits_classes_in_first_appearance_order(libmod):
+    """TDM_Numba.sample_grids_true_dist (terrain.py:586-608) is host-only: semantic classes draw from their
+    densities in the order they first appear in the grid (row-major), each cell of a class gets one draw."""
+    import types
+    from mppi_numba_b200.terrain import TDM_Numba, TractionGrid
+    calls = []
+
+    class Terr:
+        def __init__(self, sid):
+            self.sid = sid
+
+        def sample_traction(self, n):
+            calls.append((self.sid, n))
+            return np.full(n, self.sid / 10.0) + np.arange(n) * 1e-3, np.full(n, self.sid / 20.0)
+    sg = np.array([[5, 5, 2], [7, 2, 5], [7, 7, 7]])
+    fake = types.SimpleNamespace(semantic_grid=sg, id2terrain_fn=lambda i: Terr(int(i)))
+    g = TDM_Numba.sample_grids_true_dist(fake)
+    assert isinstance(g, TractionGrid)
+    assert calls == [(5, 3), (2, 2), (7, 4)]
+    lin = g.lin_traction
+    assert np.allclose(lin[sg == 5], 0.5 + np.arange(3) * 1e-3) and np.allclose(lin[sg == 7], 0.7 + np.arange(4) * 1e-3)
+    assert np.allclose(g.ang_traction[sg == 2], 0.1)
+    assert g.get(0.5, 0.5)[0] == lin[0, 0]
