@@ -83,3 +83,91 @@ def test_generator_shards_are_slices_of_the_global_stream():
                 s = X.jump_scalar(*s)
             assert (int(full[n0 * T, 0]), int(full[n0 * T, 1])) == s
             assert n1 > n0
+
+
+# ------------------------------------------------------------------------------------------------
+# Set-up of the peer-memory exchange (MPPI_Numba._connect_peers): every rank exports an IPC handle, the handles
+# are all-gathered, every rank imports them, and ALL ranks must agree on the outcome (one rank failing sends
+# every rank to the collective-library exchange).  Run on two gloo ranks against tests/fake_backend.py.
+def _peer_main(rank, port, out_dir):
+    import contextlib
+    import json
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WS)
+    import __graft_entry__
+    __graft_entry__.build()
+    import mppi_numba_b200 as E
+    import mppi_numba_b200.mppi as M
+    import mppi_numba_b200.terrain as Tm
+    from tests.fake_backend import FakeLib, disarm
+    torch.cuda.device = lambda idx: contextlib.nullcontext()        # no CUDA in this process
+
+    class Lib(FakeLib):
+        fail_export = False
+
+        def b200mppi_planner_p2p_export(self, h, out, n):
+            self.calls.append(("planner_p2p_export", (n,)))
+            if self.fail_export:
+                return -3
+            for i in range(64):
+                out[i] = (rank * 64 + i) & 0xFF
+            return 0
+
+        def b200mppi_planner_p2p_import(self, h, handles, n):
+            self.uploads["p2p_import"] = bytes(bytearray(handles[i] for i in range(n)))
+            self.calls.append(("planner_p2p_import", (n,)))
+            return 0
+
+        def b200mppi_last_error(self):
+            return b"no peer access"
+    fake = Lib()
+    M.lib = Tm.lib = fake
+    cfg = E.Config(T=1.0, dt=0.1, num_grid_samples=4, num_control_rollouts=128, max_map_dim=(20, 20),
+                   max_speed_padding=1.0, use_tdm=True)
+    res = {}
+    try:
+        pl = E.MPPI_Numba(cfg, rank=rank, world_size=WS)
+        created = [c for c in fake.calls if c[0] == "planner_create"][0][1]
+        res["create"] = [created["rank"], created["world_size"], pl.shard_maps, pl.m_local, pl.n_local, pl.n_reduce]
+        # 1. everybody succeeds
+        os.environ.pop("B200MPPI_EXCHANGE", None)
+        res["ok"] = bool(pl._connect_peers())
+        blob = fake.uploads["p2p_import"]
+        res["handles_in_rank_order"] = [blob[0], blob[64]] == [0, 64] and len(blob) == 128
+        # 2. rank 1 cannot export: every rank must fall back
+        fake.fail_export = (rank == 1)
+        fake.uploads.pop("p2p_import", None)
+        res["one_fails"] = bool(pl._connect_peers())
+        res["import_skipped"] = "p2p_import" not in fake.uploads
+        # 3. the same with the exchange forced: an error on every rank
+        os.environ["B200MPPI_EXCHANGE"] = "p2p"
+        try:
+            pl._connect_peers()
+            res["forced"] = "no error"
+        except RuntimeError as e:
+            res["forced"] = str(e)
+        # 4. B200MPPI_EXCHANGE=nccl: no handshake at all
+        os.environ["B200MPPI_EXCHANGE"] = "nccl"
+        n_before = len(fake.calls)
+        res["nccl"] = bool(pl._connect_peers())
+        res["nccl_calls"] = len(fake.calls) - n_before
+    finally:
+        disarm(fake)
+    with open(os.path.join(out_dir, "peer_rank%d.json" % rank), "w") as f:
+        json.dump(res, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_setup_is_agreed_by_all_ranks(tmp_path):
+    import json
+    port = _free_port()
+    mp.spawn(_peer_main, args=(port, str(tmp_path)), nprocs=WS, join=True)
+    r = [json.load(open(os.path.join(str(tmp_path), "peer_rank%d.json" % k))) for k in range(WS)]
+    for k in range(WS):
+        assert r[k]["create"] == [k, WS, True, 2, 128, 64]        # maps sharded: M/ws maps, all N rollouts, N/ws reduced
+        assert r[k]["ok"] is True and r[k]["handles_in_rank_order"]
+        assert r[k]["one_fails"] is False and r[k]["import_skipped"]
+        assert "rank 1: no peer access" in r[k]["forced"]
+        assert r[k]["nccl"] is False and r[k]["nccl_calls"] == 0
