@@ -81,6 +81,13 @@ class FakeLib(object):
         self.calls.append(("planner_set_params", ()))
         return 0
 
+    def b200mppi_planner_set_obstacles(self, h, xy, rad, count):
+        self.uploads["set_obstacles"] = dict(
+            xy=self._bytes(xy, 8 * count, np.float32, (count, 2)) if count else np.zeros((0, 2), np.float32),
+            rad=self._bytes(rad, 4 * count, np.float32, (count,)) if count else np.zeros((0,), np.float32))
+        self.calls.append(("planner_set_obstacles", (count,)))
+        return 0
+
     def b200mppi_planner_set_u(self, h, u):
         self.calls.append(("planner_set_u", ()))
         self.uploads["set_u"] = u
@@ -105,10 +112,11 @@ class FakeLib(object):
 
 def install(monkeypatch):
     """Swap the ctypes library object in the host modules for a FakeLib; returns it."""
+    import mppi_numba_b200.barebone as B
     import mppi_numba_b200.mppi as M
     import mppi_numba_b200.terrain as T
     fake = FakeLib()
-    for mod in (M, T):
+    for mod in (M, T, B):
         monkeypatch.setattr(mod, "lib", fake)
     return fake
 
@@ -117,10 +125,11 @@ def disarm(fake):
     """Objects created against the fake hold fake handles; once the real library is back their __del__ would pass
     those to the real destroy functions.  Clear them (also when a failed test's traceback keeps them alive)."""
     import gc
+    from mppi_numba_b200.barebone import MPPI_Numba as Barebone
     from mppi_numba_b200.mppi import MPPI_Numba
     from mppi_numba_b200.terrain import TDM_Numba
     for obj in gc.get_objects():
-        if type(obj) is MPPI_Numba or type(obj) is TDM_Numba:      # (isinstance would poke lazy module proxies)
+        if type(obj) in (MPPI_Numba, TDM_Numba, Barebone):         # (isinstance would poke lazy module proxies)
             h = getattr(obj, "_handle", None)
             if h is not None and getattr(h, "value", None) in fake.issued:
                 obj._handle = None
