@@ -81,6 +81,35 @@ class FakeLib(object):
         self.calls.append(("planner_set_params", ()))
         return 0
 
+    def b200mppi_tdm_set_pmf_collapsed(self, h, raw, B, H, W, keep_r, keep_c, pad, bv, bb, res, pxl, pyl, alpha,
+                                       pmf_out, risk_out, bad_out):
+        """The device-side collapse + crop + padding of the one-map modes, stood in for by the ORACLE's restatement
+        (oracle/terrain_ref.py) so that the Python wrapper around it can be exercised without a GPU."""
+        from oracle import terrain_ref as TR
+        pmf = self._bytes(raw, B * H * W, np.int8, (B, H, W))
+        bin_values = self._bytes(bv, 4 * B, np.float32, (B,))
+        bounds = self._bytes(bb, 8, np.float32, (2,))
+        speed = risk_out is not None
+        if speed:
+            onehot, risk = TR.risk_traction_map(pmf, bin_values, bounds, alpha)
+        else:
+            onehot = TR.collapse_pmf_det_dynamics(pmf, bin_values, alpha)
+        Hp, Wp = keep_r + 2 * pad, keep_c + 2 * pad
+        out = np.zeros((B, Hp, Wp), dtype=np.int8)
+        out[0] = 100
+        out[:, pad:pad + keep_r, pad:pad + keep_c] = onehot[:, :keep_r, :keep_c]
+        C.memmove(C.cast(pmf_out, C.c_void_p).value, out.ctypes.data, out.nbytes)
+        if speed:
+            rp = np.zeros((Hp, Wp), dtype=np.int8)
+            rp[pad:pad + keep_r, pad:pad + keep_c] = risk[0, :keep_r, :keep_c]
+            C.memmove(C.cast(risk_out, C.c_void_p).value, rp.ctypes.data, rp.nbytes)
+        _deref(bad_out).value = int((pmf.astype(np.int64).sum(0) != 100).sum())
+        self.uploads["set_pmf_collapsed"] = dict(keep=(keep_r, keep_c), pad=pad, alpha=float(alpha), res=float(res),
+                                                 pxl=self._bytes(pxl, 8, np.float32, (2,)),
+                                                 pyl=self._bytes(pyl, 8, np.float32, (2,)))
+        self.calls.append(("tdm_set_pmf_collapsed", (B, H, W)))
+        return 0
+
     def b200mppi_planner_set_obstacles(self, h, xy, rad, count):
         self.uploads["set_obstacles"] = dict(
             xy=self._bytes(xy, 8 * count, np.float32, (count, 2)) if count else np.zeros((0, 2), np.float32),
