@@ -21,6 +21,7 @@ struct SampleGridsArgs {
 };
 void launch_sample_grids(const SampleGridsArgs& a, cudaStream_t st);
 // v2 (staged, integer-threshold, optionally lin+ang fused) sampler -- see sample.cu
+// [emu:begin sampler_args]
 struct SampleTdm {
   int8_t* grid; const int8_t* cum; const uint64_t* states; uint64_t* states_out; const int8_t* qvals; int bpad;
 };
@@ -35,6 +36,7 @@ void build_jump_matrices(const int64_t* ks, int count, uint64_t* out);
 // q(r) of a RAW 64-bit draw r as a two-table lookup over its top 8 bits (see sample_threshold_q in common.cuh):
 // table = thr[256] (u64) followed by qbase[256] (u8).  false if alpha is not representable that way.
 constexpr int SAMPLE_TABLE_WORDS = 256 + 256 / 8;
+// [emu:end sampler_args]
 bool build_sample_thresholds(double alpha, int q_cap, uint64_t* table /*[SAMPLE_TABLE_WORDS]*/);
 bool sample_grids_v2_fits(const SampleGridsV2Args& a, int nt);
 void launch_sample_grids_v2(const SampleGridsV2Args& a, int nt, cudaStream_t st);

@@ -153,6 +153,7 @@ void launch_sample_grids(const SampleGridsArgs& a, cudaStream_t st) {
 //   * NT = 2 samples the linear and angular maps together from ONE stream when both TDMs hold identical
 //     generator states (same seed, same history -- the reference seeds both with cfg.seed, so their
 //     streams are identical): the draw and the threshold are shared.
+// [emu:begin sampler_v2]   (tests/emu_sampler.py compiles the text between these markers for the host)
 constexpr int SG_GM = 8;          // maps per CTA
 
 // GF(2) jump-ahead: the xoroshiro128+ transition is linear, so advancing a state by K draws is a
@@ -323,6 +324,8 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
     if (NT == 2) reinterpret_cast<ulonglong2*>(a.t[1].states_out)[gen] = make_ulonglong2(s.s0, s.s1);
   }
 }
+
+// [emu:end sampler_v2]
 
 size_t sample_grids_v2_smem(const SampleGridsV2Args& a, int nt) {
   const int row_bytes_al = (a.cols * a.t[0].bpad + 15) & ~15;

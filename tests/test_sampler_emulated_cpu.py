@@ -1,0 +1,63 @@
+"""The sampler kernel's REAL source, executed on the host by tests/emu_sampler.py, against the oracle's
+restatement of sample_grids_numba (terrain.py:633-694): sampled maps and advanced generator states bit for bit,
+for the template variants solve() uses (12 bins = 3 words, fused lin+ang), the generic-width variant, row
+segments with GF(2) jump-ahead, partial map groups and ragged tiles."""
+import numpy as np
+import pytest
+
+from oracle import terrain_ref as TR
+from oracle import xoroshiro as X
+from tests.emu_sampler import build, cumulative_table
+from tests.scenarios import random_pmf
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    import __graft_entry__
+    __graft_entry__.build()
+    return build(str(tmp_path_factory.mktemp("emu")))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(__import__("ctypes").c_void_p)
+
+
+@pytest.mark.parametrize("B,nt,segs,alpha,M,shape,tdim", [
+    (12, 2, 1, 1.0, 10, (37, 41), (4, 4)),      # the variant solve() runs at config 5 (<2,3>), partial map group
+    (12, 2, 3, 0.6, 9, (37, 41), (4, 4)),       # row segments: jump-ahead, double-buffered states
+    (12, 1, 2, 0.9, 3, (21, 50), (3, 5)),       # single TDM, ragged tiles (last tile column narrower)
+    (5, 2, 2, 1.0, 8, (19, 23), (2, 4)),        # 5 bins -> 2 words: generic-width variant (NW = 0)
+    (32, 1, 1, 0.3, 2, (12, 18), (2, 2)),       # 32 bins -> 8 words (config 4's PMF width)
+    (4, 2, 4, 1.27, 17, (16, 16), (4, 2)),      # 1 word, largest representable alpha, 3 map groups
+])
+def test_sampler_kernel_source_matches_oracle(emu, B, nt, segs, alpha, M, shape, tdim):
+    rows, cols = shape
+    tx, ty = tdim
+    rng = np.random.default_rng(B * 100 + M)
+    bpad = (B + 3) // 4 * 4
+    bin_values = np.linspace(0, 1, B)
+    bounds = np.array([0.0, 1.0], dtype=np.float32)
+    pmfs = [random_pmf(rng, B, rows, cols) for _ in range(nt)]
+    if alpha > 1.0:                                  # thresholds up to 127: column totals must reach them
+        pmfs = [np.concatenate([p[:-1], (p[-1:] + 27)], axis=0).astype(np.int8) for p in pmfs]
+    grid_rows, pitch = rows + 3, (cols + 5 + 15) // 16 * 16
+    states0 = X.create_states(tx * ty * M, 7)
+    q = np.zeros(128, dtype=np.int8)
+    q[:B] = TR.quantise_bin_values(bin_values, bounds)
+    grids = [np.full((M, grid_rows, pitch), -7, dtype=np.int8) for _ in range(nt)]
+    cums = [cumulative_table(p, bpad) for p in pmfs]
+    st_in = np.ascontiguousarray(states0.copy())
+    st_out = np.zeros_like(st_in)
+    q_cap = int(min(int(np.cumsum(p.astype(np.int64), axis=0)[-1].min()) for p in pmfs))
+    rc = emu.emu_sample_v2(nt, _ptr(grids[0]), _ptr(grids[nt - 1]), _ptr(cums[0]), _ptr(cums[nt - 1]), _ptr(st_in),
+                           _ptr(st_out), _ptr(q), _ptr(q), bpad, rows, cols, grid_rows, pitch, tx, ty, M, segs,
+                           float(alpha), min(q_cap, 127))
+    assert rc == 0
+    for k in range(nt):
+        want = np.full((M, grid_rows, pitch), -7, dtype=np.int8)
+        st = states0.copy()
+        TR.sample_grids(want, pmfs[k], st, bin_values, bounds, alpha, (tx, ty), M)
+        assert (grids[k][:, :rows, :cols] == want[:, :rows, :cols]).all(), "TDM %d" % k
+        assert (grids[k][:, rows:, :] == -7).all()               # nothing written outside the map rows
+        assert (st_out == st).all()                               # generator states advanced exactly alike
+    assert (st_in == states0).all()                               # the input buffer is not modified (double buffer)
