@@ -175,8 +175,9 @@ __device__ __forceinline__ void xoro_jump(Xoro& s, const ulonglong2* __restrict_
   s.s0 = a0; s.s1 = a1;
 }
 
-// a | (~b & c): one LOP3 (c is a compile-time mask after unrolling -> immediate operand)
-__device__ __forceinline__ uint32_t or_andn(uint32_t a, uint32_t b, uint32_t c) { return a | (~b & c); }
+// sampled value looked up from shared memory (false) or from a 16-byte register table with PRMT (true): the
+// register variant costs four more ALU-pipe instructions per cell and map, the shared-memory one a byte load
+constexpr bool SG_VALUES_IN_REGISTERS = false;
 
 template <int NT, int NW>
 __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const SampleGridsV2Args a) {
@@ -199,18 +200,23 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
   const bool active = (mloc < SG_GM) && (m < a.num_maps);
 
   for (int i = tid; i < SAMPLE_TABLE_WORDS; i += nthreads) s_T[i] = a.thresholds[i];   // thresholds + the qbase bytes
+  // value table indexed by ge = number of cumulative bytes >= q (the SIMD compare yields that count directly):
+  // bin = 4*nw - ge, so the table is stored reversed and the lookup is one byte load at s_q[ge]
   for (int i = tid; i < 128; i += nthreads) {
-    s_q[i] = (unsigned char)a.t[0].qvals[i];
-    if (NT == 2) s_q[128 + i] = (unsigned char)a.t[1].qvals[i];
+    const int b = bpad - i;
+    s_q[i] = (b >= 0) ? (unsigned char)a.t[0].qvals[b] : 0;
+    if (NT == 2) s_q[128 + i] = (b >= 0) ? (unsigned char)a.t[1].qvals[b] : 0;
   }
 
-  // value tables for <= 16 bins live in registers (4 x 32-bit per TDM), looked up with PRMT
+  // alternative kept for A/B timing: value tables for <= 16 bins in registers (4 x 32-bit per TDM), PRMT lookup
   uint32_t qreg[NT][4];
+  if (SG_VALUES_IN_REGISTERS) {
 #pragma unroll
-  for (int k = 0; k < NT; ++k) {
-    const int8_t* qv = (NT == 2 && k == 1) ? a.t[1].qvals : a.t[0].qvals;
+    for (int k = 0; k < NT; ++k) {
+      const int8_t* qv = (NT == 2 && k == 1) ? a.t[1].qvals : a.t[0].qvals;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) qreg[k][w] = __ldg(reinterpret_cast<const uint32_t*>(qv) + w);
+      for (int w = 0; w < 4; ++w) qreg[k][w] = __ldg(reinterpret_cast<const uint32_t*>(qv) + w);
+    }
   }
 
   const int ncol = (a.cols + a.ty - 1) / a.ty;
@@ -258,21 +264,22 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
           const uint32_t* cw = reinterpret_cast<const uint32_t*>(s_cum + k * row_bytes_al + ci * bpad);
           uint32_t bits = 0;
           // staged bytes carry bit 7 (guard): (0x80 | cum) - q never borrows across bytes (cum, q <= 127) and
-          // leaves bit 7 CLEAR exactly for the bytes with cum < q.  Word w contributes its four flags at bit
-          // 7-w of each byte: shift first, then one LOP3 does bits | (~z & mask)
+          // leaves bit 7 SET exactly for the bytes with cum >= q.  Word w contributes its four flags at bit
+          // 7-w of each byte: shift, then one LOP3 does bits | (z & mask)
           if (NW > 0) {
 #pragma unroll
-            for (int w = 0; w < (NW > 0 ? NW : 1); ++w) bits = or_andn(bits, (cw[w] - qq) >> (7 - w), 0x80808080u >> (7 - w));
+            for (int w = 0; w < (NW > 0 ? NW : 1); ++w) bits |= ((cw[w] - qq) >> (7 - w)) & (0x80808080u >> (7 - w));
           } else {
-            for (int w = 0; w < nw; ++w) bits = or_andn(bits, (cw[w] - qq) >> (7 - w), 0x80808080u >> (7 - w));
+            for (int w = 0; w < nw; ++w) bits |= ((cw[w] - qq) >> (7 - w)) & (0x80808080u >> (7 - w));
           }
-          const int bin = __popc(bits);                       // cum is monotone: #bins below q = first bin >= q
-          if (NW > 0 && NW <= 4) {                            // value table in registers: byte-permute lookup
+          const int ge = __popc(bits);                        // cum is monotone: first bin >= q  =  4*nw - ge
+          if (SG_VALUES_IN_REGISTERS && NW > 0 && NW <= 4) {
+            const int bin = 4 * NW - ge;
             const uint32_t lo8 = __byte_perm(qreg[k][0], qreg[k][1], bin & 7);
             const uint32_t hi8 = __byte_perm(qreg[k][2], qreg[k][3], bin & 7);
             outv[k] = ((bin & 8) ? hi8 : lo8) & 0xffu;
           } else {
-            outv[k] = s_q[k * 128 + bin];
+            outv[k] = s_q[k * 128 + ge];
           }
         }
       };

@@ -134,13 +134,22 @@ def _region(path, name):
     return m.group(1)
 
 
-def build(out_dir):
-    """Generate + compile the emulator; returns the loaded ctypes library."""
+def build(out_dir, values_in_registers=None):
+    """Generate + compile the emulator; returns the loaded ctypes library.  ``values_in_registers`` overrides the
+    kernel's compile-time switch SG_VALUES_IN_REGISTERS (the A/B variant of the value lookup)."""
+    kernel = _region(os.path.join(CSRC, "sample.cu"), "sampler_v2")
+    tag = ""
+    if values_in_registers is not None:
+        kernel, n = re.subn(r"constexpr bool SG_VALUES_IN_REGISTERS = (true|false);",
+                            "constexpr bool SG_VALUES_IN_REGISTERS = %s;" % ("true" if values_in_registers else "false"),
+                            kernel)
+        assert n == 1
+        tag = "_regs" if values_in_registers else "_smem"
     src = (PRELUDE + _region(os.path.join(CSRC, "kernels.h"), "sampler_args") +
            _region(os.path.join(CSRC, "common.cuh"), "xoro") + _region(os.path.join(CSRC, "common.cuh"), "threshold") +
-           _region(os.path.join(CSRC, "sample.cu"), "sampler_v2") + HARNESS)
-    cpp = os.path.join(out_dir, "sampler_emu.cpp")
-    so = os.path.join(out_dir, "libsampler_emu.so")
+           kernel + HARNESS)
+    cpp = os.path.join(out_dir, "sampler_emu%s.cpp" % tag)
+    so = os.path.join(out_dir, "libsampler_emu%s.so" % tag)
     open(cpp, "w").write(src)
     libdir = os.path.join(ROOT, "mppi_numba_b200")
     cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas", cpp, "-o", so,

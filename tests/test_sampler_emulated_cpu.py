@@ -11,11 +11,12 @@ from tests.emu_sampler import build, cumulative_table
 from tests.scenarios import random_pmf
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
+@pytest.fixture(scope="module", params=["as-built", "values-in-registers"])
+def emu(request, tmp_path_factory):
+    """The kernel as built, and with its compile-time A/B switch flipped (value lookup through a register table)."""
     import __graft_entry__
     __graft_entry__.build()
-    return build(str(tmp_path_factory.mktemp("emu")))
+    return build(str(tmp_path_factory.mktemp("emu")), None if request.param == "as-built" else True)
 
 
 def _ptr(a):
