@@ -206,6 +206,7 @@ void launch_rollout(const RolloutArgs& a, cudaStream_t st) {
 // numel = ceil(M * alpha) LARGEST costs.  One warp per n; the reference's O(M^2) odd-even sort with
 // 2*ceil(M/2) block barriers is replaced by a bitwise radix SELECT of the numel-th largest key done
 // with warp shuffles/ballots: 32 rounds of (compare, warp-sum), no shared memory, no barriers.
+// [emu:begin cvar]   (tests/emu_cvar.py compiles the text between these markers for the host)
 __device__ __forceinline__ uint32_t float_key(float f) {   // order-preserving float -> uint
   const uint32_t b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(CVAR_LARGE_THREADS) cvar_large_kernel(const fl
   }
 }
 
+// [emu:end cvar]
 int cvar_max_maps() { return CVAR_LARGE_MAX_MAPS; }
 
 void launch_cvar(const float* costs_nm, float* costs, int N, int Mc, int chunks, float cvar_alpha, cudaStream_t st) {
