@@ -97,6 +97,7 @@ void launch_cvar(const float* costs_nm, float* costs, int N, int M, int chunks, 
                  cudaStream_t st);
 
 // update_useq_numba (mppi.py:1113-1191) as an online-softmax two-level reduction
+// [emu:begin update_args]
 struct UpdateArgs {
   const float* costs;     // (N)
   const float* noise;     // (N, T, 2)
@@ -108,6 +109,7 @@ struct UpdateArgs {
   int N, T, num_ctas, rows_per_cta;
   float lambda, vrange[2], wrange[2];
 };
+// [emu:end update_args]
 int update_num_ctas(int N);
 void launch_update_partial(const UpdateArgs& a, cudaStream_t st);
 // combine `count` partials (each 2T+2 floats; this rank's own partial is entry `self`) into u and weights

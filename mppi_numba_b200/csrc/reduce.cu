@@ -49,6 +49,7 @@ void launch_sample_noise(uint64_t* states, float* noise, int n_local, int T, flo
 }
 
 // ---------------------------------------------------------------------------------------------
+// [emu:begin update]   (tests/emu_update.py compiles the text between these markers for the host)
 // weight of one rollout, mppi.py:1154:  float32( exp( (-1.0/f64(lambda)) * f64(c - beta) ) )
 __device__ __forceinline__ float softmax_weight(float c, float beta, float lambda) {
   return __double2float_rn(exp((-1.0 / (double)lambda) * (double)fsub(c, beta)));
@@ -216,6 +217,8 @@ __global__ void __launch_bounds__(UPD_THREADS) update_apply_kernel(const UpdateA
     for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) a.weights[r] = a.w_raw[r] * sc;
   }
 }
+
+// [emu:end update]
 
 void launch_update_partial(const UpdateArgs& a, cudaStream_t st) {
   update_partial_kernel<<<a.num_ctas, UPD_THREADS, 0, st>>>(a);
