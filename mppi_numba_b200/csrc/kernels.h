@@ -53,6 +53,7 @@ void launch_sample_noise(uint64_t* states, float* noise, int n_local, int T, flo
                          float std_w, cudaStream_t st);
 
 // rollout kernels (mppi.py:613-1111)
+// [emu:begin rollout_args]
 struct RolloutArgs {
   RolloutParams p;
   int mode;
@@ -68,6 +69,7 @@ struct RolloutArgs {
   const float* obstacles;   // MODE_BAREBONE: (num_obstacles, 3) = x, y, radius
   int num_obstacles;
 };
+// [emu:end rollout_args]
 void launch_rollout(const RolloutArgs& a, cudaStream_t st);
 // windowed (TMA-staged) stochastic rollout kernel -- rollout_win.cu
 struct RolloutWinArgs {
@@ -118,6 +120,7 @@ void launch_update_finish(const UpdateArgs& a, const float* gathered, int count,
 void launch_shift_u(float* u, int T, int shifts, cudaStream_t st);
 
 // visualisation rollouts (mppi.py:1194-1351)
+// [emu:begin vis_args]
 struct VisArgs {
   RolloutParams p;
   int mode, V;
@@ -125,6 +128,7 @@ struct VisArgs {
   const float* noise; const float* u_cur; const float* u_prev;
   float* out;   // (V, T+1, 3)
 };
+// [emu:end vis_args]
 void launch_state_rollout(const VisArgs& a, cudaStream_t st);
 
 // peer-memory exchange of the sharded solve (p2p.cu)

@@ -11,6 +11,7 @@
 
 namespace b200 {
 
+// [emu:begin rollout]
 // ---------------------------------------------------------------------------------------------
 // One state step, shared by every rollout flavour.  Returns the squared goal distance.
 struct StepConst {
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(128) rollout_barebone_kernel(const RolloutArgs
   a.costs[n] = cost;
 }
 
+// [emu:end rollout]
 void launch_rollout(const RolloutArgs& a, cudaStream_t st) {
   const int threads = 128;
   if (a.mode == 3) {
@@ -349,6 +351,7 @@ void launch_cvar(const float* costs_nm, float* costs, int N, int Mc, int chunks,
 // ---------------------------------------------------------------------------------------------
 // Visualisation rollouts (mppi.py:1194-1351).  mode != 0: block 0 rolls out u_cur without noise,
 // block b > 0 rolls out clip(u_prev + eps[b]) ; mode 0: u_cur over the first V sampled maps.
+// [emu:begin vis]
 __global__ void state_rollout_kernel(const VisArgs a) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.V) return;
@@ -399,6 +402,7 @@ __global__ void state_rollout_kernel(const VisArgs a) {
   }
 }
 
+// [emu:end vis]
 void launch_state_rollout(const VisArgs& a, cudaStream_t st) {
   state_rollout_kernel<<<(a.V + 31) / 32, 32, 0, st>>>(a);
 }
