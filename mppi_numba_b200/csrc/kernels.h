@@ -72,6 +72,7 @@ struct RolloutArgs {
 // [emu:end rollout_args]
 void launch_rollout(const RolloutArgs& a, cudaStream_t st);
 // windowed (TMA-staged) stochastic rollout kernel -- rollout_win.cu
+// [emu:begin win_args]
 struct RolloutWinArgs {
   RolloutParams p;
   int WW, WH, wx0, wy0;     // window size / origin in cells
@@ -82,6 +83,7 @@ struct RolloutWinArgs {
   const float* u_cur;
   float* costs_nm;          // (N, M)
 };
+// [emu:end win_args]
 void launch_prepare_rollout(const float* noise, const float* u_cur, float* noiseT, float* ctrl, int N, int T,
                             int npad, float lambda, float std_v, float std_w, const float vrange[2],
                             const float wrange[2], cudaStream_t st);

@@ -29,6 +29,7 @@ namespace b200 {
 // -- identical for all M maps of a control sequence, so computed once here (coalesced per-step loads
 // for lanes = consecutive n) -- and the per-n control cost sum_t lambda*(u_v/s_v^2*e_v + u_w/s_w^2*e_w)
 // (mppi.py:708-710), accumulated in the reference's order t = 0..T-1.
+// [emu:begin prepare]
 __global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __restrict__ noise,
                                                               const float* __restrict__ u_cur,
                                                               double2* __restrict__ noiseT,
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __re
   if (ty == 0 && n0 + tx < N) ctrl[n0 + tx] = acc;
 }
 
+// [emu:end prepare]
 void launch_prepare_rollout(const float* noise, const float* u_cur, float* noiseT, float* ctrl, int N, int T,
                             int npad, float lambda, float std_v, float std_w, const float vrange[2],
                             const float wrange[2], cudaStream_t st) {
@@ -134,15 +136,14 @@ __device__ __forceinline__ double widen(float a) {
 __device__ __forceinline__ float narrow(double a) {
   float r; asm("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(a)); return r;
 }
+// [emu:begin win_kernel]
 // float64 value rounded to float32 precision (round-to-nearest-even at bit 29), kept as float64:
 // == widen(narrow(a)) for every |a| in the float32 normal range, but on the integer pipe instead of a
 // second XU-pipe conversion (f64 conversions issue at half the MUFU rate on sm_100).
 __device__ __forceinline__ double round_to_f32_precision(double a) {
-  const uint32_t lo = (uint32_t)__double2loint(a), hi = (uint32_t)__double2hiint(a);
-  const uint32_t inc = 0x0FFFFFFFu + ((lo >> 29) & 1u);
-  const uint32_t lo2 = lo + inc;
-  const uint32_t hi2 = hi + (lo2 < lo ? 1u : 0u);
-  return __hiloint2double((int)hi2, (int)(lo2 & 0xE0000000u));
+  uint64_t b = ((uint64_t)(uint32_t)__double2hiint(a) << 32) | (uint32_t)__double2loint(a);
+  b += 0x0FFFFFFFull + ((b >> 29) & 1ull);          // 64-bit add: the carry into the high word is the add's own
+  return __hiloint2double((int)(uint32_t)(b >> 32), (int)((uint32_t)b & 0xE0000000u));
 }
 
 // obstacle / unknown penalties (mppi.py:700-701); out of line: taken for ~2 % of the steps, and as
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   }
 }
 
+// [emu:end win_kernel]
 // ---------------------------------------------------------------------------------------------
 // host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

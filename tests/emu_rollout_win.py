@@ -1,0 +1,154 @@
+"""Host emulation of the windowed (TMA-staged) stochastic rollout kernel and its prepare kernel (TEST
+INFRASTRUCTURE; technique of tests/emu_sampler.py).  The kernels' text is lifted from csrc/rollout_win.cu between
+the ``[emu:... prepare]`` / ``[emu:... win_kernel]`` markers.  What stands in for the hardware: a CUtensorMap is a
+plain descriptor (base, dims, pitch, box) and ``tma_load_2d/3d`` copy the box with zero fill outside the tensor
+(what CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE does for integer types); mbarrier calls are no-ops (the copy is done when
+the call returns); shared-space addresses are offsets into one static buffer; ``__fadd_rd`` is a round-down add
+derived from the exact double sum; 1024 std::threads stand for the CTA.  Arithmetic helpers as in
+tests/emu_rollout.py (IEEE meaning; libm for the MUFU approximations)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+from tests.emu_rollout import PRELUDE as ROLLOUT_PRELUDE
+from tests.emu_rollout import _region
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "mppi_numba_b200", "csrc")
+
+EXTRA = r'''
+struct CUtensorMap { const unsigned char* base; int cols, rows, maps, pitch, WW, WH; };
+struct double2 { double x, y; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline int __double2loint(double d) { uint64_t u; std::memcpy(&u, &d, 8); return (int)(uint32_t)u; }
+static inline int __double2hiint(double d) { uint64_t u; std::memcpy(&u, &d, 8); return (int)(uint32_t)(u >> 32); }
+static inline double __hiloint2double(int hi, int lo) {
+  const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double d; std::memcpy(&d, &u, 8); return d;
+}
+static inline float __fadd_rd(float a, float b) {           // add.rm.f32: the double sum of two floats is exact
+  const double s = (double)a + (double)b;
+  float r = (float)s;
+  if ((double)r > s) r = std::nextafterf(r, -INFINITY);
+  return r;
+}
+#define __grid_constant__
+#define __align__(n)
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+alignas(128) unsigned char smem[1 << 18];
+static inline uint32_t smem_u32(const void* p) { return (uint32_t)((const unsigned char*)p - smem); }
+static inline void mbar_init(uint64_t*, int) {}
+static inline void mbar_expect_tx(uint64_t*, uint32_t) {}
+static inline void mbar_wait(uint64_t*, uint32_t) {}
+static inline void tma_box(unsigned char* dst, const CUtensorMap* tm, int c0, int c1, int c2) {
+  for (int y = 0; y < tm->WH; ++y)
+    for (int x = 0; x < tm->WW; ++x) {
+      const int gx = c0 + x, gy = c1 + y;
+      const bool in = gx >= 0 && gx < tm->cols && gy >= 0 && gy < tm->rows && c2 >= 0 && c2 < tm->maps;
+      dst[y * tm->WW + x] = in ? tm->base[((size_t)c2 * tm->rows + gy) * tm->pitch + gx] : 0;
+    }
+}
+static inline void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t*, int c0, int c1, int c2) { tma_box((unsigned char*)dst, tm, c0, c1, c2); }
+static inline void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t*, int c0, int c1) { tma_box((unsigned char*)dst, tm, c0, c1, 0); }
+static inline int lds_s8(uint32_t addr, int imm_plane) { return (int)(int8_t)smem[addr + (uint32_t)imm_plane]; }
+static inline double lds_f64(uint32_t addr) { double v; std::memcpy(&v, smem + addr, 8); return v; }
+static inline double widen(float a) { return (double)a; }
+static inline float narrow(double a) { return (float)a; }
+'''
+
+HARNESS = r'''
+template <class K>
+static void run(K kernel, int threads, unsigned gx, unsigned gy) {
+  for (unsigned by = 0; by < gy; ++by)
+    for (unsigned bx = 0; bx < gx; ++bx) {
+      std::barrier<> bar(threads);
+      g_bar = &bar;
+      std::vector<std::thread> th;
+      for (int t = 0; t < threads; ++t)
+        th.emplace_back([&, t] {
+          threadIdx = {(unsigned)t, 0, 0}; blockIdx = {bx, by, 0}; blockDim = {(unsigned)threads, 1, 1}; gridDim = {gx, gy, 1};
+          kernel();
+        });
+      for (auto& x : th) x.join();
+    }
+}
+static RolloutParams params(const float* f, const int* g, const double* ratios) {
+  RolloutParams p{};
+  p.g.res = f[0]; p.g.inv_res = 1.0f / f[0]; p.g.xlo = f[1]; p.g.ylo = f[2];
+  p.g.rows = g[0]; p.g.cols = g[1]; p.g.grid_rows = g[2]; p.g.grid_cols = g[3]; p.g.grid_pitch = g[4]; p.g.mask_pitch = g[5];
+  p.dt = f[3]; p.x0[0] = f[4]; p.x0[1] = f[5]; p.x0[2] = f[6]; p.xgoal[0] = f[7]; p.xgoal[1] = f[8];
+  p.tol2 = f[9] * f[9]; p.v_post = f[10]; p.lambda = f[11]; p.u_std[0] = f[12]; p.u_std[1] = f[13];
+  p.vrange[0] = f[14]; p.vrange[1] = f[15]; p.wrange[0] = f[16]; p.wrange[1] = f[17];
+  p.obs_cost = f[18]; p.unk_cost = f[19]; p.dist_weight = f[20]; p.lin_lo = f[21]; p.ang_lo = f[22];
+  p.lin_ratio = ratios[0]; p.ang_ratio = ratios[1];
+  p.T = g[6]; p.N = g[7]; p.M = g[8];
+  return p;
+}
+}  // namespace b200
+
+// stage_rollout of csrc/api.cu for MODE_TDM: prepare kernel, window origin, launch geometry of launch_rollout_win.
+// shift_x / shift_y move the window away from the robot (cells) to force the global-memory path.
+extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratios, const int8_t* lin, const int8_t* ang,
+                               const int8_t* obs, const int8_t* unk, const float* noise, const float* u_cur,
+                               float* costs_nm, int shift_x, int shift_y, int* origin_out) {
+  using namespace b200;
+  RolloutWinArgs w{};
+  w.p = params(f, g, ratios);
+  const RolloutParams& p = w.p;
+  const int npad = (p.N + 31) / 32 * 32;
+  std::vector<double2> noiseT((size_t)p.T * npad, double2{0, 0});
+  std::vector<float> ctrl(npad, 0.0f);
+  run([&] { prepare_rollout_kernel(reinterpret_cast<const float2*>(noise), u_cur, noiseT.data(), ctrl.data(), p.N, p.T, npad,
+                                   p.lambda, p.u_std[0] * p.u_std[0], p.u_std[1] * p.u_std[1], p.vrange[0], p.vrange[1],
+                                   p.wrange[0], p.wrange[1]); }, 256, (unsigned)(npad / 32), 1);
+  const int WW = WIN_WW, WH = (win_smem_layout(WIN_WW, 232, p.T).total <= 232448) ? 232 : 224;
+  if (WH != 232) return 1;
+  const int xi0 = (int)std::floor(((double)p.x0[0] - (double)p.g.xlo) / (double)p.g.res);
+  const int yi0 = (int)std::floor(((double)p.x0[1] - (double)p.g.ylo) / (double)p.g.res);
+  const int cx = xi0 - WW / 2 + shift_x;
+  w.WW = WW; w.WH = WH;
+  w.wx0 = (cx >= 0) ? (cx & ~15) : -(((-cx) + 15) & ~15);
+  w.wy0 = yi0 - WH / 2 + shift_y;
+  w.npad = npad;
+  w.lin_grid = lin; w.ang_grid = ang; w.obstacle = obs; w.unknown = unk;
+  w.noiseT = reinterpret_cast<const float*>(noiseT.data()); w.ctrl = ctrl.data(); w.u_cur = u_cur; w.costs_nm = costs_nm;
+  if (origin_out) { origin_out[0] = w.wx0; origin_out[1] = w.wy0; }
+  const CUtensorMap t_lin{(const unsigned char*)lin, p.g.grid_cols, p.g.grid_rows, p.M, p.g.grid_pitch, WW, WH};
+  const CUtensorMap t_ang{(const unsigned char*)ang, p.g.grid_cols, p.g.grid_rows, p.M, p.g.grid_pitch, WW, WH};
+  const CUtensorMap t_obs{(const unsigned char*)obs, p.g.cols, p.g.rows, 1, p.g.mask_pitch, WW, WH};
+  const CUtensorMap t_unk{(const unsigned char*)unk, p.g.cols, p.g.rows, 1, p.g.mask_pitch, WW, WH};
+  const int tiles = (p.N + 1023) / 1024;
+  int ctas_per_map = (tiles + 1) / 2;
+  if (ctas_per_map < 1) ctas_per_map = 1;
+  run([&] { rollout_win_kernel<1024, 232>(w, t_lin, t_ang, t_obs, t_unk); }, 1024, (unsigned)ctas_per_map, (unsigned)p.M);
+  return 0;
+}
+'''
+
+
+def build(out_dir):
+    cell = _region(os.path.join(CSRC, "common.cuh"), "cell_index")
+    cell, n = re.subn(r'int k; asm\("cvt\.rzi\.ftz\.s32\.f32[^;]*;[^;]*;', "int k = (int)res;   /* cvt.rzi */", cell)
+    assert n == 1
+    prep = _region(os.path.join(CSRC, "rollout_win.cu"), "prepare")
+    prep = re.sub(r"(?m)^(\s*)__shared__ ", r"\1static ", prep)
+    kern = _region(os.path.join(CSRC, "rollout_win.cu"), "win_kernel")
+    kern, n = re.subn(r'(?m)^\s*asm volatile\("fence\.[^;]*;[^;]*;\n', "", kern)        # mbarrier / proxy fences
+    assert n == 2, n
+    kern = kern.replace("extern __shared__ __align__(128) unsigned char smem[];", "")
+    prelude = ROLLOUT_PRELUDE.replace("float s_u[4096];", "")
+    src = (prelude + EXTRA + _region(os.path.join(CSRC, "common.cuh"), "params") + cell +
+           _region(os.path.join(CSRC, "kernels.h"), "win_args") + prep + kern + HARNESS)
+    cpp = os.path.join(out_dir, "rollout_win_emu.cpp")
+    so = os.path.join(out_dir, "librollout_win_emu.so")
+    open(cpp, "w").write(src)
+    r = subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+                        "-ffp-contract=off", cpp, "-o", so], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-6000:]
+    lib = C.CDLL(so)
+    P, I = C.c_void_p, C.c_int
+    lib.emu_rollout_win.restype = I
+    lib.emu_rollout_win.argtypes = [P, P, P, P, P, P, P, P, P, P, I, I, P]
+    return lib

@@ -1,0 +1,60 @@
+"""The windowed (TMA-staged) rollout kernel's real source -- the kernel solve() runs in the stochastic mode -- and
+its prepare kernel, executed on the host by tests/emu_rollout_win.py, against the per-(n,m) costs the REFERENCE's
+rollout_numba produced for the same inputs (tests/golden/ref_rollout.npz), with the window around the robot, with
+the window pushed away so that every lookup takes the global-memory path, and against the generic kernel."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests.emu_rollout import build as build_generic
+from tests.emu_rollout_win import build
+from tests.test_rollout_emulated_cpu import _c, _fparams, _p, _ratios
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+F32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("emu_win"))
+    return build(d), build_generic(d)
+
+
+@pytest.mark.parametrize("gname", ["near", "far"])
+def test_windowed_kernel_matches_reference_and_generic_kernel(emu, gname):
+    win, gen = emu
+    g = np.load(os.path.join(GOLDEN, "ref_rollout.npz"))
+    lin, ang = _c(g["lin"], np.int8), _c(g["ang"], np.int8)
+    obs, unk = _c(g["obs"], np.int8), _c(g["unk"], np.int8)
+    noise, u_cur = _c(g["noise"], F32), _c(g["u_cur"], F32)
+    M, R, Cc = lin.shape
+    Hp, Wp = obs.shape
+    N, T = noise.shape[:2]
+    f = _fparams(g["res"], g["xlim"][0], g["ylim"][0], g["dt"], g["x0"], g["xgoal_" + gname], g["goal_tol"], g["v_post"],
+                 g["lam"], g["u_std"], g["vrange"], g["wrange"], g["obs_cost"], g["unk_cost"], g["dist_weight"],
+                 g["lin_bounds"][0], g["ang_bounds"][0])
+    ratios = _ratios(g["lin_bounds"], g["ang_bounds"])
+    geo = _c([Hp, Wp, R, Cc, Cc, Wp, T, N, M], np.int32)
+    ref = g["sto_cnm_" + gname]
+
+    def run_win(sx, sy):
+        out = np.zeros((N, M), F32)
+        origin = np.zeros(2, np.int32)
+        assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur),
+                                   _p(out), sx, sy, _p(origin)) == 0
+        return out, origin
+    inside, origin = run_win(0, 0)
+    assert origin[0] % 16 == 0                                    # TMA: 16-byte aligned inner coordinate
+    assert (np.abs(inside - ref) / np.maximum(np.abs(ref), 1e-6)).max() < 5e-6
+    outside, origin2 = run_win(4000, 4000)                        # window nowhere near the map: global-memory path
+    assert origin2[0] > Cc and origin2[1] > R
+    assert (outside == inside).all()                              # same numbers whatever the source of the bytes
+    partial, _ = run_win(123, 0)                                  # window covers only the left part of the map
+    assert (partial == inside).all()
+    cnm, costs = np.zeros((N, M), F32), np.zeros(N, F32)
+    gen.emu_rollout(0, _p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), None, _p(noise), _p(u_cur), _p(cnm),
+                    _p(costs), None, 0)
+    # the generic kernel adds the control-cost terms one by one, the windowed one adds their pre-summed total: ~1 ulp
+    assert (np.abs(inside - cnm) / np.maximum(np.abs(cnm), 1e-6)).max() < 2e-6
