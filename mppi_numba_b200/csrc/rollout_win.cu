@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   const float xlo = p.g.xlo, ylo = p.g.ylo, res = p.g.res, inv_res = p.g.inv_res;
   const float gx = p.xgoal[0], gy = p.xgoal[1];
   const float MAGIC = 12582912.0f;                          // 1.5 * 2^23
+  const int magic_wx = 0x4B400000 + a.wx0, magic_wy = 0x4B400000 + a.wy0;
   const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
   const int8_t* __restrict__ g_ang = a.ang_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
 
@@ -243,19 +244,19 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const float hy = (yy - 0.5f) - (ky - MAGIC);
       const float lx = fmaf(fabsf(yx), -6.0e-7f, 0.499999f);
       const float ly = fmaf(fabsf(yy), -6.0e-7f, 0.499999f);
-      int xi = __float_as_int(kx) - 0x4B400000;
-      int yi = __float_as_int(ky) - 0x4B400000;
-      if (!(fabsf(hx) < lx && fabsf(hy) < ly)) {
-        xi = cell_index_exact(ax, res);
-        yi = cell_index_exact(ay, res);
+      // window-relative cell straight from the magic-number sums (bits(k) - bits(MAGIC) = floor(y))
+      int wx = __float_as_int(kx) - magic_wx, wy = __float_as_int(ky) - magic_wy;
+      if (!((fabsf(hx) < lx) & (fabsf(hy) < ly))) {           // near a cell edge on either axis: exact sequence
+        wx = cell_index_exact(ax, res) - a.wx0;
+        wy = cell_index_exact(ay, res) - a.wy0;
       }
       // ---- traction / mask lookup: staged window, global memory only for rollouts that left it
-      const int wx = xi - a.wx0, wy = yi - a.wy0;
       int ql, qa, ob, un;
       if ((unsigned)wx < (unsigned)WW && (unsigned)wy < (unsigned)WH) {
         const uint32_t ad = sb_win + (uint32_t)(wy * WW + wx);
         ql = lds_s8(ad, 0); qa = lds_s8(ad, PLANE); ob = lds_s8(ad, 2 * PLANE); un = lds_s8(ad, 3 * PLANE);
       } else {
+        const int xi = wx + a.wx0, yi = wy + a.wy0;
         const int gy2 = min(max(yi < 0 ? yi + p.g.grid_rows : yi, 0), p.g.grid_rows - 1);
         const int gx2 = min(max(xi < 0 ? xi + p.g.grid_cols : xi, 0), p.g.grid_cols - 1);
         const int my = min(max(yi < 0 ? yi + p.g.rows : yi, 0), p.g.rows - 1);
