@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   const float gx = p.xgoal[0], gy = p.xgoal[1];
   const float MAGIC = 12582912.0f;                          // 1.5 * 2^23
   const int magic_wx = 0x4B400000 + a.wx0, magic_wy = 0x4B400000 + a.wy0;
+  const float inv_lo = inv_res * (1.0f - 4.8e-7f), inv_hi = inv_res * (1.0f + 4.8e-7f);
   const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
   const int8_t* __restrict__ g_ang = a.ang_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
 
@@ -235,19 +236,18 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     for (int t = 0; t < p.T; ++t) {
       ep += a.npad;
       const double2 c_next = (t + 1 < p.T) ? __ldg(ep) : c;
-      // ---- cell index of both axes: floor(a/res) by round-down magic-number addition on the FP32 pipe;
-      //      |frac - 0.5| < 0.5 - 5 ulp(y) proves it equals the reference's exact sequence, else run that
+      // ---- cell index of both axes: floor(a/res) by round-down magic-number addition on the FP32 pipe, taken
+      //      at BOTH ends of an interval that contains the exact quotient a/res (relative half-width 4.8e-7,
+      //      about 2.6x the worst rounding error of a * (1/res); the +-1e-30 covers a == 0 and flushed
+      //      denormals).  Equal floors at both ends prove the cell -- it is then what the reference's exact
+      //      sequence (the true floor of a/res) yields; otherwise run that sequence.
       const float ax = fsub(x, xlo), ay = fsub(y, ylo);
-      const float yx = ax * inv_res, yy = ay * inv_res;
-      const float kx = __fadd_rd(yx, MAGIC), ky = __fadd_rd(yy, MAGIC);
-      const float hx = (yx - 0.5f) - (kx - MAGIC);
-      const float hy = (yy - 0.5f) - (ky - MAGIC);
-      const float lx = fmaf(fabsf(yx), -6.0e-7f, 0.499999f);
-      const float ly = fmaf(fabsf(yy), -6.0e-7f, 0.499999f);
-      // window-relative cell straight from the magic-number sums (bits(k) - bits(MAGIC) = floor(y))
+      const float kx = __fadd_rd(fmaf(ax, inv_lo, -1e-30f), MAGIC), kx2 = __fadd_rd(fmaf(ax, inv_hi, 1e-30f), MAGIC);
+      const float ky = __fadd_rd(fmaf(ay, inv_lo, -1e-30f), MAGIC), ky2 = __fadd_rd(fmaf(ay, inv_hi, 1e-30f), MAGIC);
+      // window-relative cell straight from the magic-number sums (bits(k) - bits(MAGIC) = floor)
       int wx = __float_as_int(kx) - magic_wx, wy = __float_as_int(ky) - magic_wy;
-      if (!((fabsf(hx) < lx) & (fabsf(hy) < ly))) {           // near a cell edge on either axis: exact sequence
-        wx = cell_index_exact(ax, res) - a.wx0;
+      if ((__float_as_int(kx) != __float_as_int(kx2)) | (__float_as_int(ky) != __float_as_int(ky2))) {
+        wx = cell_index_exact(ax, res) - a.wx0;             // an integer may lie inside the interval: exact sequence
         wy = cell_index_exact(ay, res) - a.wy0;
       }
       // ---- traction / mask lookup: staged window, global memory only for rollouts that left it

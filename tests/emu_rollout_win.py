@@ -4,7 +4,7 @@ the ``[emu:... prepare]`` / ``[emu:... win_kernel]`` markers.  What stands in fo
 plain descriptor (base, dims, pitch, box) and ``tma_load_2d/3d`` copy the box with zero fill outside the tensor
 (what CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE does for integer types); mbarrier calls are no-ops (the copy is done when
 the call returns); shared-space addresses are offsets into one static buffer; ``__fadd_rd`` is a round-down add
-derived from the exact double sum; 1024 std::threads stand for the CTA.  Arithmetic helpers as in
+derived from the rounded sum and its exact error (TwoSum); 1024 std::threads stand for the CTA.  Arithmetic helpers as in
 tests/emu_rollout.py (IEEE meaning; libm for the MUFU approximations)."""
 import ctypes as C
 import os
@@ -27,11 +27,12 @@ static inline int __double2hiint(double d) { uint64_t u; std::memcpy(&u, &d, 8);
 static inline double __hiloint2double(int hi, int lo) {
   const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double d; std::memcpy(&d, &u, 8); return d;
 }
-static inline float __fadd_rd(float a, float b) {           // add.rm.f32: the double sum of two floats is exact
-  const double s = (double)a + (double)b;
-  float r = (float)s;
-  if ((double)r > s) r = std::nextafterf(r, -INFINITY);
-  return r;
+static inline float __fadd_rd(float a, float b) {           // add.rm.f32 from the round-to-nearest sum + its exact error
+  volatile float s = a + b;                                 // (TwoSum; volatile: no re-association, no excess precision)
+  volatile float bb = s - a;
+  volatile float e1 = a - (s - bb), e2 = b - bb;
+  const float err = e1 + e2;                                // exact: a + b == s + err
+  return (err < 0.0f) ? std::nextafterf(s, -INFINITY) : (float)s;
 }
 #define __grid_constant__
 #define __align__(n)

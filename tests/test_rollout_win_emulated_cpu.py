@@ -58,3 +58,46 @@ def test_windowed_kernel_matches_reference_and_generic_kernel(emu, gname):
                     _p(costs), None, 0)
     # the generic kernel adds the control-cost terms one by one, the windowed one adds their pre-summed total: ~1 ulp
     assert (np.abs(inside - cnm) / np.maximum(np.abs(cnm), 1e-6)).max() < 2e-6
+
+
+def test_two_sided_floor_criterion_never_disagrees_with_the_reference_floor_division():
+    """The windowed kernel takes floor(a/res) from round-down magic-number sums at both ends of the interval
+    [a*inv*(1-4.8e-7) - 1e-30, a*inv*(1+4.8e-7) + 1e-30] and trusts it only when both ends give the same integer.
+    Whenever they do, the integer must be what the reference's float floor-division yields (oracle floor_div_f32,
+    numba real_divmod as compiled): random positions, positions within 1e-5 cells of an edge, exact multiples of the
+    resolution, tiny and denormal offsets, ten resolutions."""
+    from oracle.mppi_ref import floor_div_f32
+    rng = np.random.default_rng(0)
+    MAGIC = F32(12582912.0)
+
+    def fadd_rd(a, b):                       # round-down add from the rounded sum and its exact error (TwoSum)
+        b = np.full_like(a, b)
+        s = (a + b).astype(F32)
+        bb = (s - a).astype(F32)
+        err = ((a - (s - bb).astype(F32)).astype(F32) + (b - bb).astype(F32)).astype(F32)
+        r = s.copy()
+        r[err < 0] = np.nextafter(s[err < 0], F32(-np.inf))
+        return r
+
+    def fma32(a, b, c):
+        return (a.astype(np.longdouble) * np.longdouble(b) + np.longdouble(c)).astype(F32)
+    total = trusted = 0
+    for res in (0.05, 0.1, 0.2, 0.25, 0.5, 1.0, 2.0, 0.3, 0.07, 3.3):
+        r = F32(res)
+        inv = F32(1.0) / r
+        inv_lo, inv_hi = F32(inv * F32(1.0 - 4.8e-7)), F32(inv * F32(1.0 + 4.8e-7))
+        n = 200000
+        k = rng.integers(-300, 2500, n)
+        sets = (rng.uniform(-50, 250, n).astype(F32), (k * np.float64(res) + rng.normal(0, 1e-5, n) * res).astype(F32),
+                (k * np.float64(res)).astype(F32), rng.uniform(-1e-6, 1e-6, n).astype(F32),
+                (rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-37, -5, n)).astype(F32),
+                np.array([0.0, -0.0, 1.2e-38, -1.2e-38], F32))
+        for a in sets:
+            kl = fadd_rd(fma32(a, inv_lo, -1e-30), MAGIC)
+            kh = fadd_rd(fma32(a, inv_hi, 1e-30), MAGIC)
+            same = kl.view(np.int32) == kh.view(np.int32)
+            idx = kl.view(np.int32) - np.int32(0x4B400000)
+            assert (idx[same] == floor_div_f32(a, r)[same]).all(), res
+            total += a.size
+            trusted += int(same.sum())
+    assert trusted > 0.4 * total             # the criterion is not vacuous (random positions pass it ~99.9 % of the time)
