@@ -101,3 +101,31 @@ def test_two_sided_floor_criterion_never_disagrees_with_the_reference_floor_divi
             total += a.size
             trusted += int(same.sum())
     assert trusted > 0.4 * total             # the criterion is not vacuous (random positions pass it ~99.9 % of the time)
+
+
+def test_windowed_kernel_on_a_cell_edge_takes_the_exact_sequence(emu):
+    """A robot standing exactly on a cell edge (a = k*res, the interval around a/res contains the integer k): the
+    two-sided test must refuse and the exact sequence must pick cell k -- an obstacle placed in that cell and
+    nowhere else has to show up in every step's cost, in the windowed and in the generic kernel alike."""
+    win, gen = emu
+    res, T, N, M = F32(0.25), 6, 40, 2
+    R = Cc = 32
+    lin = np.full((M, R, Cc), 50, np.int8)
+    ang = np.full((M, R, Cc), 50, np.int8)
+    obs = np.zeros((R, Cc), np.int8)
+    unk = np.zeros((R, Cc), np.int8)
+    obs[5, 7] = 1
+    xlo, ylo = F32(-1.0), F32(2.0)
+    x0 = [float(F32(xlo + 7 * res)), float(F32(ylo + 5 * res)), 0.3]          # exactly on the lower edges of cell (5, 7)
+    noise, u_cur = np.zeros((N, T, 2), F32), np.zeros((T, 2), F32)             # no motion: every step looks up (5, 7)
+    f = _fparams(res, xlo, ylo, 0.1, x0, [30.0, 30.0], 0.5, 0.01, 1.0, [2, 3], [0, 3], [-np.pi, np.pi], 1e5, 1e2, 1.0, 0.0, 0.0)
+    ratios = _ratios([0, 1], [0, 1])
+    geo = _c([R, Cc, R, Cc, Cc, Cc, T, N, M], np.int32)
+    out = np.zeros((N, M), F32)
+    assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur), _p(out),
+                               0, 0, None) == 0
+    cnm, costs = np.zeros((N, M), F32), np.zeros(N, F32)
+    gen.emu_rollout(0, _p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), None, _p(noise), _p(u_cur), _p(cnm),
+                    _p(costs), None, 0)
+    assert (out == cnm).all()
+    assert (out > T * 1e5).all() and (out < (T + 1) * 1e5).all()          # the obstacle penalty of cell (5, 7), T times
