@@ -232,10 +232,9 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     double x64 = widen(x), y64 = widen(y), th64 = widen(th);   // same values, float64 registers
     float cost = 0.0f, d2 = 1e9f;
     bool reached = false;
-    double2 c = __ldg(ep);                                  // controls are prefetched one step ahead (L2 latency)
+    double2 c = __ldg(ep);                                  // controls of step t (loaded during step t-1, see below)
     for (int t = 0; t < p.T; ++t) {
       ep += a.npad;
-      const double2 c_next = (t + 1 < p.T) ? __ldg(ep) : c;
       // ---- cell index of both axes: floor(a/res) by round-down magic-number addition on the FP32 pipe, taken
       //      at BOTH ends of an interval that contains the exact quotient a/res (relative half-width 4.8e-7,
       //      about 2.6x the worst rounding error of a * (1/res); the +-1e-30 covers a == 0 and flushed
@@ -275,6 +274,9 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const double rx = fma(dv, widen(cs), x64);
       const double ry = fma(dv, widen(sn), y64);
       const double rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), c.y, th64);
+      // `c` is dead from here on: fetch the next step's controls straight into it -- the rest of this step and the
+      // cell lookup of the next one (~70 instructions per warp, 32 warps per SM) cover the L2 latency
+      if (t + 1 < p.T) c = __ldg(ep);
       x = narrow(rx); y = narrow(ry); th = narrow(rt);
       x64 = round_to_f32_precision(rx); y64 = round_to_f32_precision(ry); th64 = round_to_f32_precision(rt);
       // ---- stage cost (mppi.py:696-701)
@@ -283,7 +285,6 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       cost = fadd(cost, ffma(sqrt_approx(d2), p.dist_weight, p.dt));
       if (__builtin_expect((ob | un) != 0, 0)) cost = add_penalties(cost, ob, un, p.obs_cost, p.unk_cost);
       if (d2 <= p.tol2) { reached = true; break; }
-      c = c_next;
     }
     cost = fadd(cost, a.ctrl[n]);                                           // control cost (mppi.py:708-710)
     const double num = (reached ? 0.0 : 1.0) * f2d(sqrt_approx(d2));         // terminal cost (mppi.py:26-28)
