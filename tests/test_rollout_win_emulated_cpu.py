@@ -129,3 +129,39 @@ def test_windowed_kernel_on_a_cell_edge_takes_the_exact_sequence(emu):
                     _p(costs), None, 0)
     assert (out == cnm).all()
     assert (out > T * 1e5).all() and (out < (T + 1) * 1e5).all()          # the obstacle penalty of cell (5, 7), T times
+
+
+def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_oracle(emu):
+    """N = 2100 control sequences = 3 tiles of 1024 on 2 CTAs per map (the second tile of CTA 0 reuses the staged
+    window, the last tile is ragged), 200 x 200 cells of random traction, obstacles and unknown cells, T = 40:
+    windowed kernel == generic kernel (~1 ulp: pre-summed control cost) and both follow the oracle."""
+    from tests.scenarios import make_scenario, oracle_rollout_costs   # noqa: F401  (scenario generator only)
+    from oracle import mppi_ref as MR
+    win, gen = emu
+    rng = np.random.default_rng(5)
+    N, M, T, R, Cc = 2100, 2, 40, 200, 200
+    res = F32(0.1)
+    lin = rng.integers(0, 101, (M, R, Cc)).astype(np.int8)
+    ang = rng.integers(0, 101, (M, R, Cc)).astype(np.int8)
+    obs = (rng.random((R, Cc)) < 0.02).astype(np.int8)
+    unk = (rng.random((R, Cc)) < 0.02).astype(np.int8)
+    noise = (rng.standard_normal((N, T, 2)) * [2, 3]).astype(F32)
+    u_cur = np.stack([rng.uniform(0, 2, T), rng.uniform(-1, 1, T)], 1).astype(F32)
+    x0 = [10.03, 9.97, 0.7]
+    goal = [13.0, 12.0]                                      # within reach: some rollouts exit early
+    f = _fparams(res, 0.0, 0.0, 0.1, x0, goal, 0.5, 0.01, 1.0, [2, 3], [0, 3], [-np.pi, np.pi], 1e5, 1e2, 1.0, 0.0, 0.0)
+    ratios = _ratios([0, 1], [0, 1])
+    geo = _c([R, Cc, R, Cc, Cc, Cc, T, N, M], np.int32)
+    out = np.zeros((N, M), F32)
+    assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur), _p(out),
+                               0, 0, None) == 0
+    cnm, costs = np.zeros((N, M), F32), np.zeros(N, F32)
+    gen.emu_rollout(0, _p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), None, _p(noise), _p(u_cur), _p(cnm),
+                    _p(costs), None, 0)
+    rel = np.abs(out - cnm) / np.maximum(np.abs(cnm), 1e-6)
+    assert rel.max() < 2e-6, rel.max()
+    want = MR.rollout_costs(MR.MODE_STOCHASTIC, lin, ang, [0, 1], [0, 1], obs, unk, res, [0.0, Cc * 0.1], [0.0, R * 0.1],
+                            [0, 3], [-np.pi, np.pi], goal, 0.01, 1e5, 1e2, 0.5, 1.0, [2, 3], x0, 0.1, 1.0, noise, u_cur)
+    r2 = np.abs(out - want) / np.maximum(np.abs(want), 1e-6)
+    assert (r2 < 1e-4).mean() > 0.995 and np.median(r2) < 2e-6          # libm vs numpy sin/cos: a few cell flips at most
+    assert (out < 0.5 * np.median(out)).any()                          # early exits happened
