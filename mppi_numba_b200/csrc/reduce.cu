@@ -16,6 +16,7 @@ namespace b200 {
 // sine branch discarded.  Compiled by Numba this uses libdevice's PRECISE logf/cosf (the helper is
 // jitted without the kernel's fastmath flag) and sqrt.approx.ftz (module-wide NVVM option) --
 // SURVEY.md 2.3; logf/cosf below are the same libdevice routines.
+// [emu:begin noise]   (tests/emu_noise.py compiles the text between these markers for the host)
 __device__ __forceinline__ float xoro_normal(Xoro& s) {
   const float u1 = xoro_unit_f32(xoro_next(s));
   const float u2 = xoro_unit_f32(xoro_next(s));
@@ -39,6 +40,8 @@ __global__ void __launch_bounds__(256) sample_noise_kernel(uint64_t* __restrict_
   noise[g] = e;
   *sp = make_ulonglong2(s.s0, s.s1);
 }
+
+// [emu:end noise]
 
 void launch_sample_noise(uint64_t* states, float* noise, int n_local, int T, float std_v, float std_w,
                          cudaStream_t st) {
