@@ -18,6 +18,7 @@ namespace b200 {
 // ---------------------------------------------------------------------------------------------
 // (B, rows, cols) PMF -> (rows, cols, bpad) running sums, clamped to int8 (comparisons against an
 // int8 threshold are unaffected by the clamp); bins >= B repeat the last sum.
+// [emu:begin build_cum]   (tests/emu_setter.py compiles the marked kernels for the host)
 __global__ void build_cum_kernel(const int8_t* __restrict__ pmf, int8_t* __restrict__ cum, int B, int bpad,
                                  int rows, int cols) {
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
@@ -29,6 +30,7 @@ __global__ void build_cum_kernel(const int8_t* __restrict__ pmf, int8_t* __restr
   }
 }
 
+// [emu:end build_cum]
 void launch_build_cum(const int8_t* pmf, int8_t* cum, int num_bins, int bpad, int rows, int cols,
                       cudaStream_t st) {
   const int cells = rows * cols;
@@ -43,6 +45,7 @@ void launch_build_cum(const int8_t* pmf, int8_t* cum, int num_bins, int bpad, in
 // the one the reference's host code chooses.
 //   mode 1 (use_det_dynamics): all mass on the first bin whose value is >= the statistic
 //   mode 2 (speed map)       : all mass on the last bin, risk = int8(100*(stat-lo)/range)
+// [emu:begin collapse_pad]
 __global__ void collapse_pad_kernel(const int8_t* __restrict__ raw, int8_t* __restrict__ out,
                                     int8_t* __restrict__ risk, int* __restrict__ bad_columns, const float* __restrict__ bin_values,
                                     int B, int H, int W, int keep_r, int keep_c, int pad, int risk_pitch, double alpha,
@@ -85,6 +88,7 @@ __global__ void collapse_pad_kernel(const int8_t* __restrict__ raw, int8_t* __re
   }
 }
 
+// [emu:end collapse_pad]
 void launch_collapse_pad(const int8_t* raw, int8_t* out, int8_t* risk, int* bad_columns, const float* bin_values, int B,
                          int H, int W, int keep_r, int keep_c, int pad, int risk_pitch, double alpha, float lo,
                          float range, int mode, cudaStream_t st) {
