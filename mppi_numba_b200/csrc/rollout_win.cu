@@ -231,7 +231,6 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     float x = p.x0[0], y = p.x0[1], th = p.x0[2];
     double x64 = widen(x), y64 = widen(y), th64 = widen(th);   // same values, float64 registers
     float cost = 0.0f, d2 = 1e9f;
-    bool reached = false;
     double2 c = __ldg(ep);                                  // controls of step t (loaded during step t-1, see below)
     for (int t = 0; t < p.T; ++t) {
       ep += a.npad;
@@ -284,10 +283,13 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       d2 = ffma(dx, dx, fmul(dy, dy));
       cost = fadd(cost, ffma(sqrt_approx(d2), p.dist_weight, p.dt));
       if (__builtin_expect((ob | un) != 0, 0)) cost = add_penalties(cost, ob, un, p.obs_cost, p.unk_cost);
-      if (d2 <= p.tol2) { reached = true; break; }
+      if (d2 <= p.tol2) break;                              // goal reached (mppi.py:703-706)
     }
+    // the loop is left early exactly when d2 <= tol2 and otherwise ends with d2 > tol2 (d2 = 1e9 for T = 0), so the
+    // reference's goal_reached flag is recovered from d2 -- no flag register (and no constant) inside the loop
+    const float not_reached = (d2 <= p.tol2) ? 0.0f : 1.0f;
     cost = fadd(cost, a.ctrl[n]);                                           // control cost (mppi.py:708-710)
-    const double num = (reached ? 0.0 : 1.0) * f2d(sqrt_approx(d2));         // terminal cost (mppi.py:26-28)
+    const double num = f2d(not_reached) * f2d(sqrt_approx(d2));              // terminal cost (mppi.py:26-28)
     cost = fadd(cost, d2f(num / (f2d(p.v_post) + 1e-6)));
     a.costs_nm[(size_t)n * p.M + m] = cost;
   }
