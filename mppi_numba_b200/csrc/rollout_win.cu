@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   const float xlo = p.g.xlo, ylo = p.g.ylo, res = p.g.res, inv_res = p.g.inv_res;
   const float gx = p.xgoal[0], gy = p.xgoal[1];
   const float MAGIC = 12582912.0f;                          // 1.5 * 2^23
-  const int magic_wx = 0x4B400000 + a.wx0, magic_wy = 0x4B400000 + a.wy0;
+  int magic_wx = 0x4B400000 + a.wx0, magic_wy = 0x4B400000 + a.wy0;
+  asm volatile("" : "+r"(magic_wx), "+r"(magic_wy));       // keep the folded constants (else re-derived per step)
   const float inv_lo = inv_res * (1.0f - 4.8e-7f), inv_hi = inv_res * (1.0f + 4.8e-7f);
   const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
   const int8_t* __restrict__ g_ang = a.ang_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
