@@ -62,3 +62,38 @@ def test_sampler_kernel_source_matches_oracle(emu, B, nt, segs, alpha, M, shape,
         assert (grids[k][:, rows:, :] == -7).all()               # nothing written outside the map rows
         assert (st_out == st).all()                               # generator states advanced exactly alike
     assert (st_in == states0).all()                               # the input buffer is not modified (double buffer)
+
+
+def test_sampler_kernel_source_random_configurations(emu):
+    """Fuzz: random map shapes, thread tiles, map counts, bin counts, segment counts, alphas and TDM counts."""
+    rng = np.random.default_rng(2024)
+    for case in range(10):
+        B = int(rng.choice([2, 3, 4, 5, 8, 12, 13, 16, 20, 32]))
+        nt = int(rng.integers(1, 3))
+        tx, ty = int(rng.integers(1, 6)), int(rng.integers(1, 7))
+        rows, cols = int(rng.integers(tx, 40)), int(rng.integers(ty, 44))
+        M = int(rng.integers(1, 20))
+        segs = int(rng.integers(1, 6))
+        alpha = float(rng.choice([1.0, 0.9, 0.5, 0.13, 1.0]))
+        bpad = (B + 3) // 4 * 4
+        bin_values = np.linspace(0, 1, B)
+        bounds = np.array([0.0, 1.0], dtype=np.float32)
+        pmfs = [random_pmf(rng, B, rows, cols) for _ in range(nt)]
+        grid_rows, pitch = rows + int(rng.integers(0, 4)), (cols + int(rng.integers(0, 9)) + 15) // 16 * 16
+        states0 = X.create_states(tx * ty * M, int(rng.integers(1, 1000)))
+        q = np.zeros(128, dtype=np.int8)
+        q[:B] = TR.quantise_bin_values(bin_values, bounds)
+        grids = [np.full((M, grid_rows, pitch), -7, dtype=np.int8) for _ in range(nt)]
+        cums = [cumulative_table(p, bpad) for p in pmfs]
+        st_in = np.ascontiguousarray(states0.copy())
+        st_out = np.zeros_like(st_in)
+        rc = emu.emu_sample_v2(nt, _ptr(grids[0]), _ptr(grids[nt - 1]), _ptr(cums[0]), _ptr(cums[nt - 1]), _ptr(st_in),
+                               _ptr(st_out), _ptr(q), _ptr(q), bpad, rows, cols, grid_rows, pitch, tx, ty, M, segs, alpha, 100)
+        assert rc == 0, case
+        for k in range(nt):
+            want = np.full((M, grid_rows, pitch), -7, dtype=np.int8)
+            st = states0.copy()
+            TR.sample_grids(want, pmfs[k], st, bin_values, bounds, alpha, (tx, ty), M)
+            tag = "case %d: B=%d nt=%d t=(%d,%d) map=(%d,%d) M=%d segs=%d alpha=%g" % (case, B, nt, tx, ty, rows, cols, M, segs, alpha)
+            assert (grids[k][:, :rows, :cols] == want[:, :rows, :cols]).all(), tag
+            assert (st_out == st).all(), tag
