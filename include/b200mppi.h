@@ -273,6 +273,17 @@ int b200mppi_planner_set_profiling(b200mppi_planner* pl, int32_t enable);
 int b200mppi_planner_last_timings(b200mppi_planner* pl, float* ms_out /* [B200MPPI_T_COUNT] */);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int b200mppi_planner_launch_count(b200mppi_planner* pl, int64_t* out);
+/* Reach-box map sampling (MODE_TDM solves only; the reference samples whole maps on every solve,
+ * terrain.py:610-694 called from mppi.py:404-405).  A solve samples only the cells its rollouts can read -- the
+ * box |x - x0| <= dt * max|traction| * S around the robot, S = sum_t |v_t| bounded by T * max|vrange| ("static")
+ * or by the max over this solve's own N clipped control sequences ("dynamic", one 4-byte read-back per solve) --
+ * and advances every generator by the draws of a whole-map walk (GF(2) jump), so costs, u and every RNG state are
+ * those of whole-map sampling.  Readers of the sampled maps outside solve() (get_sample_grids, sample_grid_view,
+ * get_state_rollout, planner_rollout) first complete the maps from the pre-solve states.  Whole maps are sampled
+ * whenever the bound is not airtight (box not strictly inside the map, ill-formed PMF, generic rollout kernel).
+ * Environment: B200MPPI_SAMPLE_BOX = off | static | dynamic (default).
+ * out[5] = { mode used by the last solve (0 whole maps, 1 static, 2 dynamic), row_lo, row_hi, col_lo, col_hi }. */
+int b200mppi_planner_sample_box(b200mppi_planner* pl, int32_t out[5]);
 
 #ifdef __cplusplus
 }

@@ -102,6 +102,7 @@ def _load():
         "b200mppi_planner_set_profiling": (C.c_int, [P, I32]),
         "b200mppi_planner_last_timings": (C.c_int, [P, P]),
         "b200mppi_planner_launch_count": (C.c_int, [P, C.POINTER(I64)]),
+        "b200mppi_planner_sample_box": (C.c_int, [P, C.POINTER(I32 * 5)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError here == ABI drift, fail loudly

@@ -47,7 +47,14 @@ struct b200mppi_tdm {
   uint64_t* states = nullptr; // (num_gen, 2)  current generator states
   uint64_t* states_alt = nullptr;   // double buffer for the segmented sampler
   uint64_t* jump_d = nullptr;       // jump-ahead matrices of the current tile geometry
+  uint64_t* jump_tile_d = nullptr;  // [4][128][2]: whole-tile advance per tile class (sample_tile_draws)
   int jump_segs = 0, jump_seg_rows = 0, jump_rows = 0, jump_cols = 0;
+  // reach-box sampling (solve() only): the sampled maps hold fresh values inside the box of the last solve and
+  // stale ones outside; states_alt still holds the pre-solve generator states, so the whole maps of that very
+  // sampling call can be produced on demand (tdm_complete_grid) -- every reader of `grid` outside solve() does
+  bool grid_partial = false;
+  double partial_alpha = 1.0;
+  float tr_abs_max = 0.0f;          // max |traction| a sampled byte can decode to: max_b |lo + 0.01*(hi-lo)*q_b|
   int64_t num_gen = 0;
   // map
   bool pmf_set = false, masks_set = false, risk_set = false;
@@ -112,6 +119,15 @@ static int tdm_prepare_jump(b200mppi_tdm* t, cudaStream_t st) {
       t->jump_cols == t->cols)
     return B200MPPI_OK;
   if (!t->jump_d) CU(cudaMalloc(&t->jump_d, (size_t)(SAMPLE_MAX_SEGS - 1) * 2 * 256 * sizeof(uint64_t)));
+  if (!t->jump_tile_d) CU(cudaMalloc(&t->jump_tile_d, (size_t)4 * 256 * sizeof(uint64_t)));
+  {
+    int64_t ks[4];
+    sample_tile_draws(t->rows, t->cols, tx, ty, ks);
+    std::vector<uint64_t> h(4 * 256);
+    build_jump_matrices(ks, 4, h.data());
+    CU(cudaMemcpyAsync(t->jump_tile_d, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));            // h is a temporary
+  }
   if (segs > 1) {
     // width classes: 0 = full tile column (ncol cells), 1 = the last, narrower column
     int last_w = t->cols - (ty - 1) * ncol;
@@ -141,20 +157,48 @@ static void fill_v2(const b200mppi_tdm* t, SampleGridsV2Args& a, int slot) {
     a.rows = t->rows; a.cols = t->cols; a.grid_rows = t->cfg.max_map_rows; a.pitch = t->pitch;
     a.tx = t->cfg.tdm_thread_x; a.ty = t->cfg.tdm_thread_y; a.num_maps = t->num_maps;
     a.segs = t->jump_segs; a.seg_rows = t->jump_seg_rows;
+    sample_box_full(a);
+    if (a.ty * a.gm > 256) a.gm = 256 / a.ty;          // wide thread tiles: fewer maps per CTA (0: does not fit)
   }
 }
 
+// Cells [row_lo, row_hi) x [col_lo, col_hi) that the rollouts of the coming solve can read (planner: reach_box).
+struct SampleBox { int row_lo, row_hi, col_lo, col_hi; };
+
+// Restrict a whole-map launch description to the tile rows / row range / tile columns covering `b`.
+static void apply_box(SampleGridsV2Args& a, const SampleBox& b) {
+  const int nrow = (a.rows + a.tx - 1) / a.tx, ncol = (a.cols + a.ty - 1) / a.ty;
+  a.row_lo = b.row_lo; a.row_hi = b.row_hi;
+  a.tix_lo = b.row_lo / nrow;
+  a.tiy_lo = b.col_lo / ncol;
+  a.nact = (b.col_hi - 1) / ncol - a.tiy_lo + 1;
+  int gm = 128 / a.nact;                                // ~4 warps per CTA whatever the number of active tile columns
+  if (gm > SG_GM_MAX) gm = SG_GM_MAX;
+  if (gm > a.num_maps) gm = a.num_maps;
+  if (gm < 1) gm = 1;
+  a.gm = gm;
+  a.write_states = 0;
+}
+
 // One TDM.  Fast staged sampler when the PMF is well-formed, else the generic per-generator kernel.
-static int tdm_sample_on(b200mppi_tdm* t, double alpha_dyn, cudaStream_t st) {
+// box != null (solve() only): sample just that part of every map; generator states advance as for whole maps.
+static int tdm_sample_on(b200mppi_tdm* t, double alpha_dyn, cudaStream_t st, const SampleBox* box = nullptr) {
   if (!t->pmf_set) return fail(B200MPPI_ESTATE, "sample_grids: PMF grid not set");
   int rc = tdm_prepare_thresholds(t, alpha_dyn, st);
   if (rc) return rc;
   if ((rc = tdm_prepare_jump(t, st))) return rc;
   SampleGridsV2Args v2{};
   fill_v2(t, v2, 0);
+  bool boxed = false;
   if (t->thr_ok && sample_grids_v2_fits(v2, 1)) {
+    if (box) {
+      SampleGridsV2Args bx = v2;
+      apply_box(bx, *box);
+      if (sample_grids_v2_fits(bx, 1)) { v2 = bx; boxed = true; }
+    }
     launch_sample_grids_v2(v2, 1, st);
-    std::swap(t->states, t->states_alt);       // the kernel wrote the advanced states to the other buffer
+    if (boxed) launch_advance_states(t->states, t->states_alt, nullptr, t->jump_tile_d, t->rows, t->cols, v2.tx, v2.ty,
+                                     t->num_maps, st);
   } else {
     SampleGridsArgs a{};
     a.grid = t->grid; a.cum = t->cum; a.states = t->states; a.qvals = t->qvals;
@@ -164,15 +208,18 @@ static int tdm_sample_on(b200mppi_tdm* t, double alpha_dyn, cudaStream_t st) {
     a.alpha_dyn = alpha_dyn;
     launch_sample_grids(a, st);
   }
-  t->launches++;
-  tdm_advance_sig(t);
   CHECK_LAUNCH();
+  if (t->thr_ok && sample_grids_v2_fits(v2, 1)) std::swap(t->states, t->states_alt);   // advanced states: other buffer
+  t->launches += boxed ? 2 : 1;
+  t->grid_partial = boxed; t->partial_alpha = alpha_dyn;
+  tdm_advance_sig(t);
   return B200MPPI_OK;
 }
 
 // Both TDMs of a planner.  When their generator states are identical (same seed, same history: the
 // reference seeds both with cfg.seed) ONE pass draws each uniform once and samples both maps.
-static int tdm_sample_pair_on(b200mppi_tdm* l, b200mppi_tdm* g, double alpha_dyn, cudaStream_t st, int64_t* launches) {
+static int tdm_sample_pair_on(b200mppi_tdm* l, b200mppi_tdm* g, double alpha_dyn, cudaStream_t st, int64_t* launches,
+                              const SampleBox* box = nullptr) {
   if (!l->pmf_set || !g->pmf_set) return fail(B200MPPI_ESTATE, "sample_grids: PMF grid not set");
   int rc = tdm_prepare_thresholds(l, alpha_dyn, st);
   if (rc) return rc;
@@ -186,18 +233,46 @@ static int tdm_sample_pair_on(b200mppi_tdm* l, b200mppi_tdm* g, double alpha_dyn
   fill_v2(l, v2, 0);
   fill_v2(g, v2, 1);
   if (same_stream && l->thr_ok && g->thr_ok && sample_grids_v2_fits(v2, 2)) {
+    bool boxed = false;
+    if (box) {
+      SampleGridsV2Args bx = v2;
+      apply_box(bx, *box);
+      if (sample_grids_v2_fits(bx, 2)) { v2 = bx; boxed = true; }
+    }
     launch_sample_grids_v2(v2, 2, st);
+    if (boxed) launch_advance_states(l->states, l->states_alt, g->states_alt, l->jump_tile_d, l->rows, l->cols, v2.tx,
+                                     v2.ty, l->num_maps, st);
+    CHECK_LAUNCH();
     std::swap(l->states, l->states_alt);
     std::swap(g->states, g->states_alt);
+    l->grid_partial = g->grid_partial = boxed;
+    l->partial_alpha = g->partial_alpha = alpha_dyn;
     tdm_advance_sig(l);
     tdm_advance_sig(g);
-    *launches += 1;
-    CHECK_LAUNCH();
+    *launches += boxed ? 2 : 1;
     return B200MPPI_OK;
   }
-  if ((rc = tdm_sample_on(l, alpha_dyn, st))) return rc;
-  if ((rc = tdm_sample_on(g, alpha_dyn, st))) return rc;
-  *launches += 2;
+  if ((rc = tdm_sample_on(l, alpha_dyn, st, box))) return rc;
+  if ((rc = tdm_sample_on(g, alpha_dyn, st, box))) return rc;
+  *launches += (l->grid_partial ? 2 : 1) + (g->grid_partial ? 2 : 1);
+  return B200MPPI_OK;
+}
+
+// The whole maps of the last (boxed) sampling call, on demand: re-walk every tile from the pre-call states the
+// double buffer still holds; the advanced states the walk stores are the ones `states` already holds.
+static int tdm_complete_grid(b200mppi_tdm* t, cudaStream_t st) {
+  if (!t->grid_partial) return B200MPPI_OK;
+  int rc = tdm_prepare_thresholds(t, t->partial_alpha, st);
+  if (rc) return rc;
+  if ((rc = tdm_prepare_jump(t, st))) return rc;
+  SampleGridsV2Args v2{};
+  fill_v2(t, v2, 0);
+  v2.t[0].states = t->states_alt; v2.t[0].states_out = t->states;
+  if (!t->thr_ok || !sample_grids_v2_fits(v2, 1)) return fail(B200MPPI_ESTATE, "complete_grid: sampler state changed");
+  launch_sample_grids_v2(v2, 1, st);
+  CHECK_LAUNCH();
+  t->launches++;
+  t->grid_partial = false;
   return B200MPPI_OK;
 }
 
@@ -269,7 +344,7 @@ extern "C" int b200mppi_tdm_destroy(b200mppi_tdm* t) {
   if (!t) return B200MPPI_OK;
   cudaSetDevice(t->cfg.device);
   cudaFree(t->grid); cudaFree(t->states); cudaFree(t->pmf); cudaFree(t->cum); cudaFree(t->qvals);
-  cudaFree(t->obstacle); cudaFree(t->unknown); cudaFree(t->risk); cudaFree(t->thr_d); cudaFree(t->states_alt); cudaFree(t->jump_d);
+  cudaFree(t->obstacle); cudaFree(t->unknown); cudaFree(t->risk); cudaFree(t->thr_d); cudaFree(t->states_alt); cudaFree(t->jump_d); cudaFree(t->jump_tile_d);
   if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
   delete t;
   return B200MPPI_OK;
@@ -326,6 +401,13 @@ extern "C" int b200mppi_tdm_set_pmf(b200mppi_tdm* t, const int8_t* pmf, int32_t 
     q[b] = (int8_t)(int16_t)std::trunc(v);
   }
   CU(cudaMemcpyAsync(t->qvals, q, 128, cudaMemcpyHostToDevice, t->stream));
+  {
+    const double ratio = 0.01 * (double)range;            // as the rollout kernels decode a byte (mppi.py:674-684)
+    double mx = 0.0;
+    for (int b = 0; b < B; ++b) mx = std::fmax(mx, std::fabs((double)bounds[0] + ratio * (double)q[b]));
+    t->tr_abs_max = (float)mx;
+  }
+  t->grid_partial = false;                                // a new PMF: nothing left to complete
   launch_build_cum(t->pmf, t->cum, B, bpad, rows, cols, t->stream);
   t->launches++;
   CHECK_LAUNCH();
@@ -402,11 +484,23 @@ extern "C" int b200mppi_tdm_set_bin_quantisation(b200mppi_tdm* t, const int8_t* 
   CU(cudaSetDevice(t->cfg.device));
   CU(cudaMemcpyAsync(t->qvals, qvals, (size_t)n, cudaMemcpyHostToDevice, t->stream));
   CU(cudaStreamSynchronize(t->stream));
+  {
+    const double ratio = 0.01 * (double)(float)(t->bounds[1] - t->bounds[0]);
+    double mx = 0.0;
+    for (int b = 0; b < n; ++b) mx = std::fmax(mx, std::fabs((double)t->bounds[0] + ratio * (double)qvals[b]));
+    t->tr_abs_max = (float)mx;
+  }
   return B200MPPI_OK;
 }
 
 extern "C" int b200mppi_tdm_sample_grid_view(b200mppi_tdm* t, void** ptr, int32_t* pitch) {
   if (!t) return fail(B200MPPI_EINVAL, "null tdm");
+  if (t->grid_partial) {                      // a raw view must show whole maps
+    CU(cudaSetDevice(t->cfg.device));
+    const int rc = tdm_complete_grid(t, t->stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(t->stream));
+  }
   if (ptr) *ptr = t->grid;
   if (pitch) *pitch = t->pitch;
   return B200MPPI_OK;
@@ -478,6 +572,7 @@ extern "C" int b200mppi_tdm_get_sample_grids(b200mppi_tdm* t, int8_t* out, size_
   if (!t || !out) return fail(B200MPPI_EINVAL, "null argument");
   if (bytes != tdm_grid_bytes(t)) return fail(B200MPPI_EINVAL, "get_sample_grids: size mismatch");
   CU(cudaSetDevice(t->cfg.device));
+  { const int rc = tdm_complete_grid(t, t->stream); if (rc) return rc; }
   CU(cudaMemcpy2DAsync(out, t->cfg.max_map_cols, t->grid, t->pitch, t->cfg.max_map_cols,
                        (size_t)t->num_maps * t->cfg.max_map_rows, cudaMemcpyDeviceToHost, t->stream));
   CU(cudaStreamSynchronize(t->stream));
@@ -488,6 +583,7 @@ extern "C" int b200mppi_tdm_set_sample_grids(b200mppi_tdm* t, const int8_t* in, 
   if (!t || !in) return fail(B200MPPI_EINVAL, "null argument");
   if (bytes != tdm_grid_bytes(t)) return fail(B200MPPI_EINVAL, "set_sample_grids: size mismatch");
   CU(cudaSetDevice(t->cfg.device));
+  t->grid_partial = false;                    // every cell is overwritten
   CU(cudaMemcpy2DAsync(t->grid, t->pitch, in, t->cfg.max_map_cols, t->cfg.max_map_cols,
                        (size_t)t->num_maps * t->cfg.max_map_rows, cudaMemcpyHostToDevice, t->stream));
   CU(cudaStreamSynchronize(t->stream));
@@ -509,6 +605,7 @@ extern "C" int b200mppi_tdm_get_rng_states(b200mppi_tdm* t, uint64_t* out, size_
 extern "C" int b200mppi_tdm_set_rng_states(b200mppi_tdm* t, const uint64_t* in, size_t bytes) {
   if (!t || !in || bytes != (size_t)t->num_gen * 16) return fail(B200MPPI_EINVAL, "set_rng_states: bad argument");
   CU(cudaSetDevice(t->cfg.device));
+  { const int rc = tdm_complete_grid(t, t->stream); if (rc) return rc; }   // completion needs the states it replaces
   CU(cudaMemcpyAsync(t->states, in, bytes, cudaMemcpyHostToDevice, t->stream));
   CU(cudaStreamSynchronize(t->stream));
   // content-derived signature: two TDMs given identical states compare equal again
@@ -536,7 +633,14 @@ struct b200mppi_planner {
   uint64_t* states = nullptr;
   float* noiseT = nullptr; float* ctrl = nullptr; int npad = 0;   // windowed rollout kernel inputs
   alignas(64) unsigned char tmaps[4][128];
+  const void* tmap_key[6] = {};  // what the cached tensor maps were encoded for (grids, masks, geometry)
   bool use_win = true;
+  // reach-box sampling: 0 = whole maps every solve, 1 = box from the speed limit, 2 = box from this solve's
+  // own clipped controls (max_n sum_t |v|, reduced by the prepare kernel into reach_d and read back mid-solve)
+  int box_mode = 2;
+  float* reach_d = nullptr;
+  bool prepared = false;         // noiseT / ctrl hold this iteration's controls
+  int32_t last_box[5] = {};      // b200mppi_planner_sample_box
   float* h_u = nullptr;        // pinned staging for the T x 2 result (+ one int: exchange status)
   // peer-memory exchange (p2p.cu): ONE allocation per planner so that one IPC handle describes it:
   // [ receive buffer (ws, N/ws, M/ws) | gather buffers 2 x (ws, 2T+2) | cost flags | partial flags | counter | status ]
@@ -642,6 +746,13 @@ static int planner_init(b200mppi_planner* p, const b200mppi_config* cfg) {
   CU(cudaMalloc(&p->noiseT, (size_t)p->T * p->npad * 2 * sizeof(double)));
   CU(cudaMalloc(&p->ctrl, (size_t)p->npad * sizeof(float)));
   p->use_win = getenv("B200MPPI_NO_WINDOW") == nullptr;
+  CU(cudaMalloc(&p->reach_d, 256));
+  CU(cudaMemsetAsync(p->reach_d, 0, 256, p->stream));
+  if (const char* e = getenv("B200MPPI_SAMPLE_BOX")) {
+    if (!strcmp(e, "off") || !strcmp(e, "0")) p->box_mode = 0;
+    else if (!strcmp(e, "static")) p->box_mode = 1;
+    else p->box_mode = 2;
+  }
   p->num_ctas = update_num_ctas(p->n_red);
   p->rows_per_cta = (p->n_red + p->num_ctas - 1) / p->num_ctas;
   p->num_ctas = (p->n_red + p->rows_per_cta - 1) / p->rows_per_cta;
@@ -694,7 +805,7 @@ extern "C" int b200mppi_planner_destroy(b200mppi_planner* p) {
   cudaFree(p->noise); cudaFree(p->u_cur); cudaFree(p->u_prev); cudaFree(p->costs); cudaFree(p->weights);
   cudaFree(p->w_raw); cudaFree(p->costs_nm); cudaFree(p->cta_partials); cudaFree(p->rank_partial);
   cudaFree(p->state_rollout); cudaFree(p->states); cudaFree(p->noiseT); cudaFree(p->ctrl); cudaFree(p->costs_x);
-  cudaFree(p->obstacles);
+  cudaFree(p->obstacles); cudaFree(p->reach_d);
   for (int s = 0; s < P2P_MAX_PEERS; ++s)
     if (p->peer_ipc[s] && p->peer_x[s]) cudaIpcCloseMemHandle(p->peer_x[s]);
   cudaFree(p->xbuf);
@@ -740,6 +851,7 @@ extern "C" int b200mppi_planner_set_u(b200mppi_planner* p, const float* u) {
   std::memcpy(p->h_u, u, (size_t)p->T * 2 * sizeof(float));
   CU(cudaMemcpyAsync(p->u_cur, p->h_u, (size_t)p->T * 2 * sizeof(float), cudaMemcpyHostToDevice, p->stream));
   CU(cudaStreamSynchronize(p->stream));
+  p->prepared = false;
   return B200MPPI_OK;
 }
 
@@ -756,17 +868,51 @@ extern "C" int b200mppi_planner_shift_u(b200mppi_planner* p, int32_t shifts) {
   if (!p) return fail(B200MPPI_EINVAL, "null planner");
   CU(cudaSetDevice(p->cfg.device));
   launch_shift_u(p->u_cur, p->T, shifts, p->stream);
+  p->prepared = false;
   p->launches++;
   CHECK_LAUNCH();
   return B200MPPI_OK;
 }
 
 // ---- stages
+static bool planner_uses_window(const b200mppi_planner* p) {
+  if (p->cfg.mode != B200MPPI_MODE_TDM || !p->use_win) return false;
+  int WW, WH; size_t smem;
+  rollout_win_geometry(p->T, &WW, &WH, &smem);
+  return smem <= 232448;
+}
+
+// control noise, and (windowed stochastic rollouts) the transposed clipped controls + per-n control cost + the
+// reach statistic max_n sum_t |v| of this iteration
 static int stage_noise(b200mppi_planner* p) {
-  launch_sample_noise(p->states, p->noise, p->n_local, p->T, p->prm.u_std[0], p->prm.u_std[1], p->stream);
+  launch_sample_noise(p->states, p->noise, p->n_local, p->T, p->prm.u_std[0], p->prm.u_std[1], p->reach_d, p->stream);
   p->launches++;
   CHECK_LAUNCH();
+  p->prepared = false;
+  if (planner_uses_window(p)) {
+    launch_prepare_rollout(p->noise, p->u_cur, p->noiseT, p->ctrl, p->reach_d, p->n_local, p->T, p->npad,
+                           p->prm.lambda_weight, p->prm.u_std[0], p->prm.u_std[1], p->prm.vrange, p->prm.wrange, p->stream);
+    p->launches++;
+    CHECK_LAUNCH();
+    p->prepared = true;
+  }
   return B200MPPI_OK;
+}
+
+// tensor maps of the windowed rollout: encoded once per (buffers, geometry) -- the window origin is a launch coordinate
+static bool planner_tensor_maps(b200mppi_planner* p, int WW, int WH) {
+  const b200mppi_tdm* l = p->lin; const b200mppi_tdm* g = p->ang;
+  const void* key[6] = {l->grid, g->grid, l->obstacle, l->unknown,
+                        (const void*)(((size_t)l->mask_rows << 40) ^ ((size_t)l->mask_cols << 20) ^ (size_t)l->mask_pitch),
+                        (const void*)(((size_t)WW << 40) ^ ((size_t)WH << 20) ^ (size_t)l->num_maps)};
+  if (!std::memcmp(key, p->tmap_key, sizeof(key))) return true;
+  const bool ok =
+      make_u8_tensor_map(p->tmaps[0], l->grid, 3, l->cfg.max_map_cols, l->cfg.max_map_rows, l->num_maps, l->pitch, WW, WH) &&
+      make_u8_tensor_map(p->tmaps[1], g->grid, 3, g->cfg.max_map_cols, g->cfg.max_map_rows, g->num_maps, g->pitch, WW, WH) &&
+      make_u8_tensor_map(p->tmaps[2], l->obstacle, 2, l->mask_cols, l->mask_rows, 1, l->mask_pitch, WW, WH) &&
+      make_u8_tensor_map(p->tmaps[3], l->unknown, 2, l->mask_cols, l->mask_rows, 1, l->mask_pitch, WW, WH);
+  if (ok) std::memcpy(p->tmap_key, key, sizeof(key)); else std::memset(p->tmap_key, 0, sizeof(key));
+  return ok;
 }
 
 static int stage_rollout(b200mppi_planner* p) {
@@ -780,21 +926,19 @@ static int stage_rollout(b200mppi_planner* p) {
   a.obstacles = p->obstacles; a.num_obstacles = p->num_obstacles;
   a.noise = p->noise; a.u_cur = p->u_cur; a.costs_nm = p->costs_nm; a.costs = p->costs;
   bool done = false;
-  if (p->cfg.mode == B200MPPI_MODE_TDM && p->use_win) {
+  if (planner_uses_window(p)) {
     // stochastic mode: TMA-staged map windows (rollout_win.cu); window centred on the robot's cell
     int WW, WH; size_t smem;
     rollout_win_geometry(p->T, &WW, &WH, &smem);
     const b200mppi_tdm* l = p->lin; const b200mppi_tdm* g = p->ang;
-    const bool ok = smem <= 232448 &&
-        make_u8_tensor_map(p->tmaps[0], l->grid, 3, l->cfg.max_map_cols, l->cfg.max_map_rows, l->num_maps, l->pitch, WW, WH) &&
-        make_u8_tensor_map(p->tmaps[1], g->grid, 3, g->cfg.max_map_cols, g->cfg.max_map_rows, g->num_maps, g->pitch, WW, WH) &&
-        make_u8_tensor_map(p->tmaps[2], l->obstacle, 2, l->mask_cols, l->mask_rows, 1, l->mask_pitch, WW, WH) &&
-        make_u8_tensor_map(p->tmaps[3], l->unknown, 2, l->mask_cols, l->mask_rows, 1, l->mask_pitch, WW, WH);
-    if (ok) {
-      launch_prepare_rollout(p->noise, p->u_cur, p->noiseT, p->ctrl, p->n_local, p->T, p->npad, p->prm.lambda_weight,
-                             p->prm.u_std[0], p->prm.u_std[1], p->prm.vrange, p->prm.wrange, p->stream);
-      p->launches++;
-      CHECK_LAUNCH();
+    if (planner_tensor_maps(p, WW, WH)) {
+      if (!p->prepared) {                       // noise came from outside (set_noise): derive the controls now
+        launch_prepare_rollout(p->noise, p->u_cur, p->noiseT, p->ctrl, p->reach_d, p->n_local, p->T, p->npad,
+                               p->prm.lambda_weight, p->prm.u_std[0], p->prm.u_std[1], p->prm.vrange, p->prm.wrange, p->stream);
+        p->launches++;
+        CHECK_LAUNCH();
+      }
+      p->prepared = false;                      // u_cur changes with the update that follows
       RolloutWinArgs w{};
       w.p = a.p;
       w.WW = WW; w.WH = WH;
@@ -840,6 +984,7 @@ static int stage_update_finish(b200mppi_planner* p, const float* gathered, int c
   UpdateArgs u{};
   fill_update_args(p, u, nullptr);
   launch_update_finish(u, gathered, count, p->stream);
+  p->prepared = false;                        // u_cur moved
   p->launches++;
   CHECK_LAUNCH();
   if (p->cfg.mode != B200MPPI_MODE_TDM)   // self.u_prev_d = self.u_cur_d (alias, mppi.py:292,362)
@@ -865,24 +1010,89 @@ extern "C" int b200mppi_planner_set_obstacles(b200mppi_planner* p, const float* 
   return B200MPPI_OK;
 }
 
+// Cells the rollouts of this solve can read.  A rollout moves at most |traction| * |v| * dt per step, so it stays
+// within R = dt * max|traction| * S of x0, S = sum_t |v_t| -- bounded by T * max|vrange| (static box) or, when the maps
+// are sampled once for ONE set of controls (num_opt = 1), by the max over the N control sequences actually drawn
+// (reach_d, reduced by the prepare kernel: one 4-byte read-back + stream sync per solve buys the smaller box).
+// False (whole maps) whenever the bound is not airtight: the box would leave the map (out-of-map indices wrap),
+// traction bytes not under the sampler's control, non-finite inputs.
+static bool planner_reach_box(b200mppi_planner* p, SampleBox* box, int* how, int* err) {
+  *err = B200MPPI_OK;
+  *how = 1;
+  if (p->box_mode == 0 || !planner_uses_window(p)) return false;
+  const b200mppi_tdm* l = p->lin;
+  const b200mppi_params& q = p->prm;
+  double S = (double)p->T * std::fmax(std::fabs((double)q.vrange[0]), std::fabs((double)q.vrange[1]));
+  if (p->box_mode == 2 && q.num_opt == 1 && p->prepared) {
+    float* h = p->h_u + (size_t)p->T * 2 + 2;
+    if (cudaMemcpyAsync(h, p->reach_d, sizeof(float), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
+        cudaStreamSynchronize(p->stream) != cudaSuccess) {
+      *err = fail(B200MPPI_ECUDA, std::string("reach read-back: ") + cudaGetErrorString(cudaGetLastError()));
+      return false;
+    }
+    if (!((double)*h <= S)) return false;              // NaN or beyond the speed limit: not a usable bound
+    S = (double)*h;
+    *how = 2;
+  }
+  // 1.0002: cos/sin.approx may exceed 1 by ~1e-6, float32 rounding of the state adds ~1e-7 per step; + one cell below
+  const double R = (double)q.dt * (double)l->tr_abs_max * S * 1.0002;
+  if (!(R >= 0.0) || !std::isfinite(R)) return false;
+  const double res = (double)l->res;
+  const double fx0 = ((double)q.x0[0] - R - (double)l->pxl[0]) / res, fx1 = ((double)q.x0[0] + R - (double)l->pxl[0]) / res;
+  const double fy0 = ((double)q.x0[1] - R - (double)l->pyl[0]) / res, fy1 = ((double)q.x0[1] + R - (double)l->pyl[0]) / res;
+  if (!(fx0 > 2.0 && fy0 > 2.0 && fx1 < (double)l->cols - 3.0 && fy1 < (double)l->rows - 3.0)) return false;
+  box->col_lo = (int)std::floor(fx0) - 1; box->col_hi = (int)std::floor(fx1) + 3;      // [lo, hi)
+  box->row_lo = (int)std::floor(fy0) - 1; box->row_hi = (int)std::floor(fy1) + 3;
+  return true;
+}
+
 static int stage_sample_tdms(b200mppi_planner* p) {
   if (p->cfg.mode == B200MPPI_MODE_BAREBONE) return B200MPPI_OK;      // no maps
   // det / speed-map solves call sample_grids() with the default alpha_dyn = 1.0 (mppi.py:248-249,322-323)
   const double alpha = p->cfg.mode == B200MPPI_MODE_TDM ? p->prm.alpha_dyn : 1.0;
-  return tdm_sample_pair_on(p->lin, p->ang, alpha, p->stream, &p->launches);
+  SampleBox box;
+  int err;
+  int how = 0;
+  const bool boxed = planner_reach_box(p, &box, &how, &err);
+  if (err) return err;
+  const int rc = tdm_sample_pair_on(p->lin, p->ang, alpha, p->stream, &p->launches, boxed ? &box : nullptr);
+  const bool used = boxed && p->lin->grid_partial;        // the sampler may still have fallen back to whole maps
+  p->last_box[0] = used ? how : 0;
+  p->last_box[1] = used ? box.row_lo : 0; p->last_box[2] = used ? box.row_hi : p->lin->rows;
+  p->last_box[3] = used ? box.col_lo : 0; p->last_box[4] = used ? box.col_hi : p->lin->cols;
+  return rc;
 }
 
 static void collect_timings(b200mppi_planner* p) {
-  // ev: 0 start, 1 after sampling, 2 after noise, 3 after rollout, 4 after cvar, 5 after update (last iteration)
+  // ev: 0 solve start, 6 iteration start, 1 after noise (+ controls), 7 before / 2 after map sampling (first iteration),
+  //     3 after rollout, 4 after cvar, 5 after update (last iteration)
   if (!p->profiling) return;
   float ms = 0;
   auto dt = [&](int a, int b) { ms = 0; cudaEventElapsedTime(&ms, p->ev[a], p->ev[b]); return ms; };
-  p->last_ms[B200MPPI_T_SAMPLE_GRIDS] = dt(0, 1);
-  p->last_ms[B200MPPI_T_NOISE] = dt(1, 2);
-  p->last_ms[B200MPPI_T_ROLLOUT] = dt(2, 3);
+  const bool one = p->prm.num_opt <= 1;                   // the sampling of a multi-iteration solve precedes ev[6]
+  p->last_ms[B200MPPI_T_SAMPLE_GRIDS] = dt(7, 2);
+  p->last_ms[B200MPPI_T_NOISE] = dt(6, 1);
+  p->last_ms[B200MPPI_T_ROLLOUT] = dt(one ? 2 : 1, 3);
   p->last_ms[B200MPPI_T_CVAR] = dt(3, 4);
   p->last_ms[B200MPPI_T_UPDATE] = dt(4, 5);
   p->last_ms[B200MPPI_T_TOTAL] = dt(0, 5);
+}
+
+// one optimisation iteration up to the per-(n,m) costs: noise (+ controls) -> [first iteration: maps] -> rollouts.
+// The noise comes first because the map sampler is sized by the reach of the controls it yields (planner_reach_box).
+static int iteration_rollouts(b200mppi_planner* p, bool first) {
+  int rc;
+  if (p->profiling) cudaEventRecord(p->ev[6], p->stream);
+  if ((rc = stage_noise(p))) return rc;
+  if (p->profiling) cudaEventRecord(p->ev[1], p->stream);
+  if (first) {
+    if (p->profiling) cudaEventRecord(p->ev[7], p->stream);
+    if ((rc = stage_sample_tdms(p))) return rc;
+    if (p->profiling) cudaEventRecord(p->ev[2], p->stream);
+  }
+  if ((rc = stage_rollout(p))) return rc;
+  if (p->profiling) cudaEventRecord(p->ev[4], p->stream);
+  return B200MPPI_OK;
 }
 
 extern "C" int b200mppi_planner_solve(b200mppi_planner* p, float* u_out) {
@@ -892,16 +1102,9 @@ extern "C" int b200mppi_planner_solve(b200mppi_planner* p, float* u_out) {
   if (rc) return rc;
   CU(cudaSetDevice(p->cfg.device));
   if (p->profiling) cudaEventRecord(p->ev[0], p->stream);
-  rc = stage_sample_tdms(p);
-  if (rc) return rc;
-  if (p->profiling) cudaEventRecord(p->ev[1], p->stream);
+  if (p->prm.num_opt <= 0 && (rc = stage_sample_tdms(p))) return rc;     // the reference samples before its loop
   for (int k = 0; k < p->prm.num_opt; ++k) {
-    const bool last = (k == p->prm.num_opt - 1);
-    if (p->profiling && !last) cudaEventRecord(p->ev[1], p->stream);
-    if ((rc = stage_noise(p))) return rc;
-    if (p->profiling) cudaEventRecord(p->ev[2], p->stream);
-    if ((rc = stage_rollout(p))) return rc;
-    if (p->profiling) cudaEventRecord(p->ev[4], p->stream);
+    if ((rc = iteration_rollouts(p, k == 0))) return rc;
     if ((rc = stage_update_partial(p, nullptr))) return rc;
     if ((rc = stage_update_finish(p, p->rank_partial, 1))) return rc;
     if (p->profiling) cudaEventRecord(p->ev[5], p->stream);
@@ -918,13 +1121,8 @@ extern "C" int b200mppi_planner_solve_local(b200mppi_planner* p, int32_t first_i
   int rc = planner_check_ready(p);
   if (rc) return rc;
   CU(cudaSetDevice(p->cfg.device));
-  if (p->profiling) cudaEventRecord(p->ev[0], p->stream);
-  if (first_iteration && (rc = stage_sample_tdms(p))) return rc;
-  if (p->profiling) cudaEventRecord(p->ev[1], p->stream);
-  if ((rc = stage_noise(p))) return rc;
-  if (p->profiling) cudaEventRecord(p->ev[2], p->stream);
-  if ((rc = stage_rollout(p))) return rc;
-  if (p->profiling) cudaEventRecord(p->ev[4], p->stream);
+  if (p->profiling && first_iteration) cudaEventRecord(p->ev[0], p->stream);
+  if ((rc = iteration_rollouts(p, first_iteration != 0))) return rc;
   if (p->shard_maps) return B200MPPI_OK;                     // costs_nm is the all-to-all send buffer
   if ((rc = stage_update_partial(p, nullptr))) return rc;
   return B200MPPI_OK;
@@ -1178,6 +1376,10 @@ extern "C" int b200mppi_planner_rollout(b200mppi_planner* p) {
   int rc = planner_check_ready(p);
   if (rc) return rc;
   CU(cudaSetDevice(p->cfg.device));
+  if (p->cfg.mode != B200MPPI_MODE_BAREBONE) {            // the maps of the last solve may be boxed
+    if ((rc = tdm_complete_grid(p->lin, p->stream))) return rc;
+    if ((rc = tdm_complete_grid(p->ang, p->stream))) return rc;
+  }
   if ((rc = stage_rollout(p))) return rc;
   CU(cudaStreamSynchronize(p->stream));
   return B200MPPI_OK;
@@ -1223,7 +1425,11 @@ extern "C" int b200mppi_planner_get_state_rollout(b200mppi_planner* p, float* ou
   VisArgs a{};
   fill_rollout_params(p, a.p);
   a.mode = p->cfg.mode; a.V = V;
-  if (p->cfg.mode != B200MPPI_MODE_BAREBONE) { a.lin_grid = p->lin->grid; a.ang_grid = p->ang->grid; }
+  if (p->cfg.mode != B200MPPI_MODE_BAREBONE) {
+    if ((rc = tdm_complete_grid(p->lin, p->stream))) return rc;   // the optimal sequence may leave the last solve's box
+    if ((rc = tdm_complete_grid(p->ang, p->stream))) return rc;
+    a.lin_grid = p->lin->grid; a.ang_grid = p->ang->grid;
+  }
   a.noise = p->noise; a.u_cur = p->u_cur; a.u_prev = p->u_prev; a.out = p->state_rollout;
   launch_state_rollout(a, p->stream);
   p->launches++;
@@ -1272,6 +1478,7 @@ extern "C" int b200mppi_planner_copy_in(b200mppi_planner* p, int32_t id, const v
   if (rc) return rc;
   if (!src || bytes != b) return fail(B200MPPI_EINVAL, "copy_in: size mismatch");
   CU(cudaSetDevice(p->cfg.device));
+  p->prepared = false;
   CU(cudaMemcpyAsync(d, src, b, cudaMemcpyHostToDevice, p->stream));
   CU(cudaStreamSynchronize(p->stream));
   return B200MPPI_OK;
@@ -1297,6 +1504,12 @@ extern "C" int b200mppi_planner_set_profiling(b200mppi_planner* p, int32_t enabl
 extern "C" int b200mppi_planner_last_timings(b200mppi_planner* p, float* ms) {
   if (!p || !ms) return fail(B200MPPI_EINVAL, "null argument");
   for (int i = 0; i < B200MPPI_T_COUNT; ++i) ms[i] = p->last_ms[i];
+  return B200MPPI_OK;
+}
+
+extern "C" int b200mppi_planner_sample_box(b200mppi_planner* p, int32_t out[5]) {
+  if (!p || !out) return fail(B200MPPI_EINVAL, "null argument");
+  for (int i = 0; i < 5; ++i) out[i] = p->last_box[i];
   return B200MPPI_OK;
 }
 

@@ -31,7 +31,17 @@ struct SampleGridsV2Args {
   const uint64_t* jump;         // device, [(segs-1)*2][128][2]: A^(s*seg_rows*width) for width class 0 / 1
   int rows, cols, grid_rows, pitch, tx, ty, num_maps;
   int segs, seg_rows;           // row segments per generator tile (jump-ahead split), rows per segment
+  // reach box (sample_box_full() = the whole map): only rows [row_lo, row_hi) of tile rows [tix_lo, ...) and tile
+  // columns [tiy_lo, tiy_lo + nact) are sampled; gm maps per CTA; write_states: the last segment of every
+  // generator stores its advanced state (whole-map walks only -- a boxed launch leaves the states to
+  // advance_states_kernel, which jumps every generator over its whole tile)
+  int gm, tix_lo, tiy_lo, nact, row_lo, row_hi, write_states;
 };
+constexpr int SG_GM = 8;          // maps per CTA of a whole-map launch
+constexpr int SG_GM_MAX = 32;
+inline void sample_box_full(SampleGridsV2Args& a) {
+  a.gm = SG_GM; a.tix_lo = 0; a.tiy_lo = 0; a.nact = a.ty; a.row_lo = 0; a.row_hi = a.rows; a.write_states = 1;
+}
 void build_jump_matrices(const int64_t* ks, int count, uint64_t* out);
 // q(r) of a RAW 64-bit draw r as a two-table lookup over its top 8 bits (see sample_threshold_q in common.cuh):
 // table = thr[256] (u64) followed by qbase[256] (u8).  false if alpha is not representable that way.
@@ -40,6 +50,12 @@ constexpr int SAMPLE_TABLE_WORDS = 256 + 256 / 8;
 bool build_sample_thresholds(double alpha, int q_cap, uint64_t* table /*[SAMPLE_TABLE_WORDS]*/);
 bool sample_grids_v2_fits(const SampleGridsV2Args& a, int nt);
 void launch_sample_grids_v2(const SampleGridsV2Args& a, int nt, cudaStream_t st);
+// tile classes of a generator: (full | last) tile height x (full | last) tile width -> draws per whole-map walk
+void sample_tile_draws(int rows, int cols, int tx, int ty, int64_t ks[4]);
+// states_out[g] = states[g] advanced by the draws of a whole-map walk of generator g's tile (GF(2) jump with
+// `mats` = [4][128][2] u64, the matrices of sample_tile_draws' four counts); out1 may be null
+void launch_advance_states(const uint64_t* states, uint64_t* out0, uint64_t* out1, const uint64_t* mats, int rows,
+                           int cols, int tx, int ty, int num_maps, cudaStream_t st);
 // builds the (rows, cols, bpad) cumulative table from the (B, rows, cols) PMF
 void launch_build_cum(const int8_t* pmf, int8_t* cum, int num_bins, int bpad, int rows, int cols,
                       cudaStream_t st);
@@ -49,8 +65,9 @@ void launch_collapse_pad(const int8_t* raw, int8_t* out, int8_t* risk, int* bad_
                          float range, int mode, cudaStream_t st);
 
 // sample_noise_numba (mppi.py:1354-1370): generators (n_global*T + t); writes noise (N,T,2).
+// `reach` (may be null): a device float the kernel zeroes for the prepare kernel's max-reduction
 void launch_sample_noise(uint64_t* states, float* noise, int n_local, int T, float std_v,
-                         float std_w, cudaStream_t st);
+                         float std_w, float* reach, cudaStream_t st);
 
 // rollout kernels (mppi.py:613-1111)
 // [emu:begin rollout_args]
@@ -84,8 +101,9 @@ struct RolloutWinArgs {
   float* costs_nm;          // (N, M)
 };
 // [emu:end win_args]
-void launch_prepare_rollout(const float* noise, const float* u_cur, float* noiseT, float* ctrl, int N, int T,
-                            int npad, float lambda, float std_v, float std_w, const float vrange[2],
+// reach (may be null): *reach = max(*reach, max_n sum_t |clipped v[n,t]|) -- bounds how far a rollout can travel
+void launch_prepare_rollout(const float* noise, const float* u_cur, float* noiseT, float* ctrl, float* reach, int N,
+                            int T, int npad, float lambda, float std_v, float std_w, const float vrange[2],
                             const float wrange[2], cudaStream_t st);
 bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int rows, int maps, int pitch,
                         int WW, int WH);

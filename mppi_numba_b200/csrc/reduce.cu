@@ -28,9 +28,10 @@ __device__ __forceinline__ float xoro_normal(Xoro& s) {
 // contiguous in g, so loads/stores are fully coalesced 16 B / 8 B per lane.
 __global__ void __launch_bounds__(256) sample_noise_kernel(uint64_t* __restrict__ states,
                                                            float2* __restrict__ noise, int64_t count,
-                                                           float std_v, float std_w) {
+                                                           float std_v, float std_w, float* __restrict__ reach) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= count) return;
+  if (g == 0 && reach) *reach = 0.0f;          // the prepare kernel that follows max-reduces into it
   ulonglong2* sp = reinterpret_cast<ulonglong2*>(states) + g;
   const ulonglong2 raw = *sp;
   Xoro s{raw.x, raw.y};
@@ -44,11 +45,11 @@ __global__ void __launch_bounds__(256) sample_noise_kernel(uint64_t* __restrict_
 // [emu:end noise]
 
 void launch_sample_noise(uint64_t* states, float* noise, int n_local, int T, float std_v, float std_w,
-                         cudaStream_t st) {
+                         float* reach, cudaStream_t st) {
   const int64_t count = (int64_t)n_local * T;
   const int threads = 256;
   sample_noise_kernel<<<(unsigned)((count + threads - 1) / threads), threads, 0, st>>>(
-      states, reinterpret_cast<float2*>(noise), count, std_v, std_w);
+      states, reinterpret_cast<float2*>(noise), count, std_v, std_w, reach);
 }
 
 // ---------------------------------------------------------------------------------------------

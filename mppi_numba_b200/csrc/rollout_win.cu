@@ -33,13 +33,14 @@ namespace b200 {
 __global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __restrict__ noise,
                                                               const float* __restrict__ u_cur,
                                                               double2* __restrict__ noiseT,
-                                                              float* __restrict__ ctrl, int N, int T, int npad,
+                                                              float* __restrict__ ctrl, float* __restrict__ reach,
+                                                              int N, int T, int npad,
                                                               float lambda, float sv2, float sw2, float v_lo,
                                                               float v_hi, float w_lo, float w_hi) {
   __shared__ float2 tile[32][33];
   const int n0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
-  float acc = 0.0f;
+  float acc = 0.0f, vsum = 0.0f;
   for (int t0 = 0; t0 < T; t0 += 32) {
     for (int r = ty; r < 32; r += 8) {                         // rows = n, cols = t  (coalesced along t)
       const int n = n0 + r, t = t0 + tx;
@@ -65,19 +66,30 @@ __global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __re
         const float a = div_approx(u_cur[2 * (t0 + j)], sv2);
         const float b = div_approx(u_cur[2 * (t0 + j) + 1], sw2);
         acc = ffma(ffma(a, e.x, fmul(b, e.y)), lambda, acc);
+        // reach statistic: sum_t |v| of the clipped speed command (rounded up: it is used as an upper bound)
+        vsum = __fadd_ru(vsum, fabsf(fmaxf(v_lo, fminf(v_hi, fadd(u_cur[2 * (t0 + j)], e.x)))));
       }
     }
     __syncthreads();
   }
-  if (ty == 0 && n0 + tx < N) ctrl[n0 + tx] = acc;
+  if (ty == 0) {
+    if (n0 + tx < N) ctrl[n0 + tx] = acc; else vsum = 0.0f;
+    if (reach) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) vsum = fmaxf(vsum, __shfl_xor_sync(0xffffffffu, vsum, o));
+      // non-negative floats order like their bit patterns; a NaN (sign clear) compares above every number and
+      // makes the host fall back to the static bound
+      if (tx == 0) atomicMax(reinterpret_cast<unsigned int*>(reach), __float_as_uint(vsum));
+    }
+  }
 }
 
 // [emu:end prepare]
-void launch_prepare_rollout(const float* noise, const float* u_cur, float* noiseT, float* ctrl, int N, int T,
-                            int npad, float lambda, float std_v, float std_w, const float vrange[2],
+void launch_prepare_rollout(const float* noise, const float* u_cur, float* noiseT, float* ctrl, float* reach, int N,
+                            int T, int npad, float lambda, float std_v, float std_w, const float vrange[2],
                             const float wrange[2], cudaStream_t st) {
   prepare_rollout_kernel<<<npad / 32, 256, 0, st>>>(reinterpret_cast<const float2*>(noise), u_cur,
-                                                   reinterpret_cast<double2*>(noiseT), ctrl, N, T, npad, lambda,
+                                                   reinterpret_cast<double2*>(noiseT), ctrl, reach, N, T, npad, lambda,
                                                    std_v * std_v, std_w * std_w, vrange[0], vrange[1], wrange[0],
                                                    wrange[1]);
 }
@@ -347,15 +359,20 @@ int rollout_win_threads() { return WIN_THREADS; }
 cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, const void* tm_ang, const void* tm_obs,
                                const void* tm_unk, cudaStream_t st) {
   const WinSmem L = win_smem_layout(a.WW, a.WH, a.p.T);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rollout_win_kernel<WIN_THREADS, 232>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_MAX_SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(rollout_win_kernel<WIN_THREADS, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               WIN_MAX_SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
+  {
+    // the opt-in is per device (per-context function): a process may run planners on several GPUs
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(rollout_win_kernel<WIN_THREADS, 232>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_MAX_SMEM);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(rollout_win_kernel<WIN_THREADS, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 WIN_MAX_SMEM);
+      if (e != cudaSuccess) return e;
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   if (a.WW != WIN_WW || (a.WH != 232 && a.WH != 224) || L.total > WIN_MAX_SMEM) return cudaErrorInvalidValue;
   const int tiles = (a.p.N + WIN_THREADS - 1) / WIN_THREADS;

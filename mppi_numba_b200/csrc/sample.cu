@@ -8,6 +8,7 @@
 // if no bin reaches q the cell keeps its previous content.  The table of cumulative PMFs is built
 // once per set_pmf (cell-major, so one cell's bins are contiguous) instead of re-summing B strided
 // int8 loads per cell per map as the reference does.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -158,8 +159,6 @@ void launch_sample_grids(const SampleGridsArgs& a, cudaStream_t st) {
 //     generator states (same seed, same history -- the reference seeds both with cfg.seed, so their
 //     streams are identical): the draw and the threshold are shared.
 // [emu:begin sampler_v2]   (tests/emu_sampler.py compiles the text between these markers for the host)
-constexpr int SG_GM = 8;          // maps per CTA
-
 // GF(2) jump-ahead: the xoroshiro128+ transition is linear, so advancing a state by K draws is a
 // 128x128 bit-matrix product.  `mat` holds the 128 columns (2 x u64 each) of A^K.
 __device__ __forceinline__ void xoro_jump(Xoro& s, const ulonglong2* __restrict__ mat) {
@@ -184,24 +183,32 @@ __device__ __forceinline__ void xoro_jump(Xoro& s, const ulonglong2* __restrict_
 constexpr bool SG_VALUES_IN_REGISTERS = false;
 
 template <int NT, int NW>
-__global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const SampleGridsV2Args a) {
+__global__ void __launch_bounds__(256) sample_grids_v2_kernel(const SampleGridsV2Args a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int nw = (NW > 0) ? NW : a.t[0].bpad / 4;
   const int bpad = nw * 4;
-  const int row_bytes = a.cols * bpad;                       // one row of the cumulative table
+  const int ncol = (a.cols + a.ty - 1) / a.ty;
+  const int nrow = (a.rows + a.tx - 1) / a.tx;
+  // staged column window [cs0, cs1): the active tile columns, start rounded down to 16 cells (16-byte stores)
+  const int cfirst = min(a.tiy_lo * ncol, a.cols);
+  const int cs0 = cfirst & ~15;
+  const int cs1 = min((a.tiy_lo + a.nact) * ncol, a.cols);
+  const int wcols = cs1 - cs0;
+  const int row_bytes = wcols * bpad;                        // the window's slice of one cumulative-table row
   const int row_bytes_al = (row_bytes + 15) & ~15;
-  const int stage_pitch = (a.cols + 15) & ~15;
+  const int stage_pitch = (wcols + 15) & ~15;
+  const int gm = a.gm;
   unsigned char* s_cum = smem;                               // [NT][row_bytes_al]
-  unsigned char* s_stage = s_cum + NT * row_bytes_al;        // [NT][GM][stage_pitch]
-  uint64_t* s_T = reinterpret_cast<uint64_t*>(s_stage + NT * SG_GM * stage_pitch);   // [256] bucket thresholds
+  unsigned char* s_stage = s_cum + NT * row_bytes_al;        // [NT][gm][stage_pitch]
+  uint64_t* s_T = reinterpret_cast<uint64_t*>(s_stage + NT * gm * stage_pitch);   // [256] bucket thresholds
   const unsigned char* s_Q = reinterpret_cast<const unsigned char*>(s_T + 256);      // [256] q at bucket start
   unsigned char* s_q = reinterpret_cast<unsigned char*>(s_T + SAMPLE_TABLE_WORDS);   // [NT][128]
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int tiy = tid % a.ty, mloc = tid / a.ty;
-  const int tix = blockIdx.x / a.segs, seg = blockIdx.x % a.segs;
-  const int m = blockIdx.y * SG_GM + mloc;
-  const bool active = (mloc < SG_GM) && (m < a.num_maps);
+  const int tiy = a.tiy_lo + tid % a.nact, mloc = tid / a.nact;
+  const int tix = a.tix_lo + blockIdx.x / a.segs, seg = blockIdx.x % a.segs;
+  const int m = blockIdx.y * gm + mloc;
+  const bool active = (mloc < gm) && (m < a.num_maps);
 
   for (int i = tid; i < SAMPLE_TABLE_WORDS; i += nthreads) s_T[i] = a.thresholds[i];   // thresholds + the qbase bytes
   // value table indexed by ge = number of cumulative bytes >= q (the SIMD compare yields that count directly):
@@ -223,8 +230,6 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
     }
   }
 
-  const int ncol = (a.cols + a.ty - 1) / a.ty;
-  const int nrow = (a.rows + a.tx - 1) / a.tx;
   const int t0 = min(tix * nrow, a.rows), t1 = min(t0 + nrow, a.rows);          // the generator's tile rows
   const int c0 = min(tiy * ncol, a.cols), c1 = min(c0 + ncol, a.cols);
   // this CTA's row segment of the tile.  A generator's stream is split into `segs` consecutive row
@@ -244,12 +249,17 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
       xoro_jump(s, reinterpret_cast<const ulonglong2*>(a.jump) + ((size_t)(seg - 1) * 2 + cls) * 128);
     }
   }
+  // rows of this segment inside the reach box (CTA-uniform); the draws of the segment's rows above the box are
+  // consumed without sampling (one xoroshiro step per cell), rows below it are simply not walked
+  const int rs0 = max(r0, a.row_lo), rs1 = min(r1, a.row_hi);
+  if (active && rs0 < rs1)
+    for (int64_t i = (int64_t)(rs0 - r0) * wc; i > 0; --i) xoro_next(s);
 
-  for (int ri = r0; ri < r1; ++ri) {
+  for (int ri = rs0; ri < rs1; ++ri) {
     __syncthreads();                                          // previous row's stage fully drained
 #pragma unroll
     for (int k = 0; k < NT; ++k) {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(a.t[k].cum + (size_t)ri * row_bytes);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(a.t[k].cum + ((size_t)ri * a.cols + cs0) * bpad);
       uint32_t* dst = reinterpret_cast<uint32_t*>(s_cum + k * row_bytes_al);
 #pragma unroll 8
       for (int i = tid; i < row_bytes / 4; i += nthreads) dst[i] = __ldg(src + i) | 0x80808080u;   // guard bits, see cell()
@@ -265,7 +275,7 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
         const uint32_t qq = q * 0x01010101u;
 #pragma unroll
         for (int k = 0; k < NT; ++k) {
-          const uint32_t* cw = reinterpret_cast<const uint32_t*>(s_cum + k * row_bytes_al + ci * bpad);
+          const uint32_t* cw = reinterpret_cast<const uint32_t*>(s_cum + k * row_bytes_al + (ci - cs0) * bpad);
           uint32_t bits = 0;
           // staged bytes carry bit 7 (guard): (0x80 | cum) - q never borrows across bytes (cum, q <= 127) and
           // leaves bit 7 SET exactly for the bytes with cum >= q.  Word w contributes its four flags at bit
@@ -287,8 +297,8 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
           }
         }
       };
-      unsigned char* st0 = s_stage + mloc * stage_pitch;
-      unsigned char* st1 = s_stage + (SG_GM + mloc) * stage_pitch;
+      unsigned char* st0 = s_stage + mloc * stage_pitch - cs0;          // indexed by the map column
+      unsigned char* st1 = s_stage + (gm + mloc) * stage_pitch - cs0;
       int ci = c0;
       for (; ci + 4 <= c1; ci += 4) {          // 4 draws in stream order, then 4 independent cells (ILP)
         uint64_t r[4];
@@ -311,43 +321,92 @@ __global__ void __launch_bounds__(SG_GM * 32) sample_grids_v2_kernel(const Sampl
       }
     }
     __syncthreads();
-    // coalesced write-back of the GM x NT staged rows: 16-byte chunks, byte tail
-    const int chunks = (a.cols + 15) / 16;
-    const int maps_here = min(SG_GM, a.num_maps - (int)blockIdx.y * SG_GM);
+    // coalesced write-back of the gm x NT staged rows: 16-byte chunks, bytes at the ragged ends of the window
+    const int chunks = (wcols + 15) / 16;
+    const int maps_here = min(gm, a.num_maps - (int)blockIdx.y * gm);
     for (int idx = tid; idx < NT * maps_here * chunks; idx += nthreads) {
       const int ch = idx % chunks;
       const int km = idx / chunks;
       const int k = km / maps_here, ml = km % maps_here;
-      const unsigned char* srow = s_stage + (k * SG_GM + ml) * stage_pitch + ch * 16;
+      const unsigned char* srow = s_stage + (k * gm + ml) * stage_pitch + ch * 16;
       int8_t* gbase = (NT == 2 && k == 1) ? a.t[1].grid : a.t[0].grid;
-      int8_t* grow = gbase + ((size_t)(blockIdx.y * SG_GM + ml) * a.grid_rows + ri) * a.pitch + ch * 16;
-      if (ch * 16 + 16 <= a.cols) {
+      int8_t* grow = gbase + ((size_t)(blockIdx.y * gm + ml) * a.grid_rows + ri) * a.pitch + cs0 + ch * 16;
+      const int lo = max(cfirst - (cs0 + ch * 16), 0), hi = min(cs1 - (cs0 + ch * 16), 16);
+      if (lo == 0 && hi == 16) {
         *reinterpret_cast<uint4*>(grow) = *reinterpret_cast<const uint4*>(srow);
       } else {
-        for (int b = 0; b < a.cols - ch * 16; ++b) grow[b] = (int8_t)srow[b];
+        for (int b = lo; b < hi; ++b) grow[b] = (int8_t)srow[b];
       }
     }
   }
   // states are double-buffered (another segment of the same generator may still have to read the old
   // state): exactly one segment per generator writes the new state
-  if (active && seg == last_seg) {
+  if (a.write_states && active && seg == last_seg) {
     reinterpret_cast<ulonglong2*>(a.t[0].states_out)[gen] = make_ulonglong2(s.s0, s.s1);
     if (NT == 2) reinterpret_cast<ulonglong2*>(a.t[1].states_out)[gen] = make_ulonglong2(s.s0, s.s1);
   }
 }
 
+// whole-tile advance of every generator (box mode: the sampler walks only part of each tile, so the states a
+// whole-map walk would leave behind are produced by ONE GF(2) jump per generator).  Tile classes as sample_tile_draws.
+__global__ void __launch_bounds__(128) advance_states_kernel(const ulonglong2* __restrict__ in, ulonglong2* __restrict__ out0,
+                                                             ulonglong2* __restrict__ out1, const ulonglong2* __restrict__ mats,
+                                                             int rows, int cols, int tx, int ty, int num_maps) {
+  const int64_t gen = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gen >= (int64_t)tx * ty * num_maps) return;
+  const int tix = (int)(gen / ((int64_t)ty * num_maps)), tiy = (int)(gen % ty);
+  const int ncol = (cols + ty - 1) / ty, nrow = (rows + tx - 1) / tx;
+  const int t0 = min(tix * nrow, rows), t1 = min(t0 + nrow, rows);
+  const int c0 = min(tiy * ncol, cols), c1 = min(c0 + ncol, cols);
+  const ulonglong2 raw = in[gen];
+  Xoro s{raw.x, raw.y};
+  if (t1 > t0 && c1 > c0) xoro_jump(s, mats + (((t1 - t0 == nrow) ? 0 : 2) + ((c1 - c0 == ncol) ? 0 : 1)) * 128);
+  out0[gen] = make_ulonglong2(s.s0, s.s1);
+  if (out1) out1[gen] = make_ulonglong2(s.s0, s.s1);
+}
+
 // [emu:end sampler_v2]
 
-size_t sample_grids_v2_smem(const SampleGridsV2Args& a, int nt) {
-  const int row_bytes_al = (a.cols * a.t[0].bpad + 15) & ~15;
-  const int stage_pitch = (a.cols + 15) & ~15;
-  return (size_t)nt * row_bytes_al + (size_t)nt * SG_GM * stage_pitch + SAMPLE_TABLE_WORDS * 8 + (size_t)nt * 128;
+void launch_advance_states(const uint64_t* states, uint64_t* out0, uint64_t* out1, const uint64_t* mats, int rows,
+                           int cols, int tx, int ty, int num_maps, cudaStream_t st) {
+  const int64_t total = (int64_t)tx * ty * num_maps;
+  advance_states_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+      reinterpret_cast<const ulonglong2*>(states), reinterpret_cast<ulonglong2*>(out0),
+      reinterpret_cast<ulonglong2*>(out1), reinterpret_cast<const ulonglong2*>(mats), rows, cols, tx, ty, num_maps);
 }
+
+// draws of a whole-map walk per tile class: [0] full x full, [1] full height x last width, [2] last height x full
+// width, [3] last x last ("last" = the one ragged, non-empty tile row / column; equal to "full" if none is ragged)
+void sample_tile_draws(int rows, int cols, int tx, int ty, int64_t ks[4]) {
+  const int nrow = (rows + tx - 1) / tx, ncol = (cols + ty - 1) / ty;
+  int last_h = rows % nrow ? rows % nrow : nrow;
+  int last_w = cols % ncol ? cols % ncol : ncol;
+  ks[0] = (int64_t)nrow * ncol; ks[1] = (int64_t)nrow * last_w;
+  ks[2] = (int64_t)last_h * ncol; ks[3] = (int64_t)last_h * last_w;
+}
+
+static int v2_window_cols(const SampleGridsV2Args& a) {
+  const int ncol = (a.cols + a.ty - 1) / a.ty;
+  const int cfirst = std::min(a.tiy_lo * ncol, a.cols);
+  const int cs1 = std::min((a.tiy_lo + a.nact) * ncol, a.cols);
+  return cs1 - (cfirst & ~15);
+}
+
+size_t sample_grids_v2_smem(const SampleGridsV2Args& a, int nt) {
+  const int wcols = v2_window_cols(a);
+  const int row_bytes_al = (wcols * a.t[0].bpad + 15) & ~15;
+  const int stage_pitch = (wcols + 15) & ~15;
+  return (size_t)nt * row_bytes_al + (size_t)nt * a.gm * stage_pitch + SAMPLE_TABLE_WORDS * 8 + (size_t)nt * 128;
+}
+
+static int v2_threads(const SampleGridsV2Args& a) { return ((a.nact * a.gm + 31) / 32) * 32; }
 
 template <int NT>
 static void launch_v2_nt(const SampleGridsV2Args& a, cudaStream_t st) {
-  const dim3 grid(a.tx * a.segs, (a.num_maps + SG_GM - 1) / SG_GM);
-  const int threads = ((a.ty * SG_GM + 31) / 32) * 32;
+  const int nrow = (a.rows + a.tx - 1) / a.tx;
+  const int tix_hi = std::min(a.tx - 1, (std::max(a.row_hi, a.row_lo + 1) - 1) / nrow);     // last tile row with box rows
+  const dim3 grid((tix_hi - a.tix_lo + 1) * a.segs, (a.num_maps + a.gm - 1) / a.gm);
+  const int threads = v2_threads(a);
   const size_t smem = sample_grids_v2_smem(a, NT);
   const int nw = a.t[0].bpad / 4;
   auto go = [&](auto kern) {
@@ -361,7 +420,8 @@ static void launch_v2_nt(const SampleGridsV2Args& a, cudaStream_t st) {
 }
 
 bool sample_grids_v2_fits(const SampleGridsV2Args& a, int nt) {
-  return a.ty * SG_GM <= 1024 && a.t[0].bpad <= 32 && sample_grids_v2_smem(a, nt) <= 200 * 1024 &&
+  return a.gm >= 1 && a.gm <= SG_GM_MAX && a.nact >= 1 && a.tiy_lo >= 0 && a.tiy_lo + a.nact <= a.ty &&
+         v2_threads(a) <= 256 && a.t[0].bpad <= 32 && sample_grids_v2_smem(a, nt) <= 200 * 1024 &&
          (nt == 1 || a.t[0].bpad == a.t[1].bpad);
 }
 

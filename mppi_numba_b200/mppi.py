@@ -359,6 +359,15 @@ class MPPI_Numba(object):
         check(lib.b200mppi_planner_last_timings(self._handle, ms))
         return dict(zip(_lib.T_NAMES, [float(v) for v in ms]))
 
+    def sample_box(self):
+        """How the last solve() sampled the traction maps: ``(mode, row_lo, row_hi, col_lo, col_hi)`` with mode
+        0 = whole maps (what the reference does every solve), 1 / 2 = only the cells its rollouts could reach
+        (bound from the speed limit / from this solve's own clipped controls); results are identical either way
+        (include/b200mppi.h, b200mppi_planner_sample_box)."""
+        out = (C.c_int32 * 5)()
+        check(lib.b200mppi_planner_sample_box(self._handle, C.byref(out)))
+        return tuple(int(v) for v in out)
+
     def launch_count(self):
         n = C.c_int64()
         check(lib.b200mppi_planner_launch_count(self._handle, C.byref(n)))

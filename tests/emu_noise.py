@@ -31,11 +31,11 @@ static inline float xoro_unit_f32(uint64_t x) { return (float)((double)(x >> 11)
 
 HARNESS = r'''
 }  // namespace b200
-extern "C" void emu_sample_noise(uint64_t* states, float* noise, long long count, float std_v, float std_w) {
+extern "C" void emu_sample_noise(uint64_t* states, float* noise, long long count, float std_v, float std_w, float* reach) {
   blockDim = {256, 1, 1};
   for (long long g = 0; g < (count + 255) / 256 * 256; ++g) {
     blockIdx = {(unsigned)(g / 256), 0, 0}; threadIdx = {(unsigned)(g % 256), 0, 0};
-    b200::sample_noise_kernel(states, reinterpret_cast<float2*>(noise), count, std_v, std_w);
+    b200::sample_noise_kernel(states, reinterpret_cast<float2*>(noise), count, std_v, std_w, reach);
   }
 }
 '''
@@ -50,5 +50,5 @@ def build(out_dir):
     assert r.returncode == 0, r.stderr[-4000:]
     lib = C.CDLL(so)
     lib.emu_sample_noise.restype = None
-    lib.emu_sample_noise.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float]
+    lib.emu_sample_noise.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_void_p]
     return lib

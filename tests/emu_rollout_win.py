@@ -34,6 +34,25 @@ static inline float __fadd_rd(float a, float b) {           // add.rm.f32 from t
   const float err = e1 + e2;                                // exact: a + b == s + err
   return (err < 0.0f) ? std::nextafterf(s, -INFINITY) : (float)s;
 }
+static inline float __fadd_ru(float a, float b) {           // add.rp.f32, same construction
+  volatile float s = a + b;
+  volatile float bb = s - a;
+  volatile float e1 = a - (s - bb), e2 = b - bb;
+  const float err = e1 + e2;
+  return (err > 0.0f) ? std::nextafterf(s, INFINITY) : (float)s;
+}
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline unsigned atomicMax(unsigned* p, unsigned v) { const unsigned o = *p; if (v > o) *p = v; return o; }   // blocks run one by one
+static std::barrier<> g_w0(32);                             // the prepare kernel's warp 0 (its only shuffling warp)
+static float g_w0buf[32];
+static inline float __shfl_xor_sync(unsigned, float v, int o) {
+  const int lane = threadIdx.x & 31;
+  g_w0buf[lane] = v;
+  g_w0.arrive_and_wait();
+  const float r = g_w0buf[lane ^ o];
+  g_w0.arrive_and_wait();
+  return r;
+}
 #define __grid_constant__
 #define __align__(n)
 #undef __launch_bounds__
@@ -93,7 +112,7 @@ static RolloutParams params(const float* f, const int* g, const double* ratios) 
 // shift_x / shift_y move the window away from the robot (cells) to force the global-memory path.
 extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratios, const int8_t* lin, const int8_t* ang,
                                const int8_t* obs, const int8_t* unk, const float* noise, const float* u_cur,
-                               float* costs_nm, int shift_x, int shift_y, int* origin_out) {
+                               float* costs_nm, int shift_x, int shift_y, int* origin_out, float* reach_out) {
   using namespace b200;
   RolloutWinArgs w{};
   w.p = params(f, g, ratios);
@@ -101,7 +120,8 @@ extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratio
   const int npad = (p.N + 31) / 32 * 32;
   std::vector<double2> noiseT((size_t)p.T * npad, double2{0, 0});
   std::vector<float> ctrl(npad, 0.0f);
-  run([&] { prepare_rollout_kernel(reinterpret_cast<const float2*>(noise), u_cur, noiseT.data(), ctrl.data(), p.N, p.T, npad,
+  float reach = 0.0f;
+  run([&] { prepare_rollout_kernel(reinterpret_cast<const float2*>(noise), u_cur, noiseT.data(), ctrl.data(), &reach, p.N, p.T, npad,
                                    p.lambda, p.u_std[0] * p.u_std[0], p.u_std[1] * p.u_std[1], p.vrange[0], p.vrange[1],
                                    p.wrange[0], p.wrange[1]); }, 256, (unsigned)(npad / 32), 1);
   const int WW = WIN_WW, WH = (win_smem_layout(WIN_WW, 232, p.T).total <= 232448) ? 232 : 224;
@@ -116,6 +136,7 @@ extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratio
   w.lin_grid = lin; w.ang_grid = ang; w.obstacle = obs; w.unknown = unk;
   w.noiseT = reinterpret_cast<const float*>(noiseT.data()); w.ctrl = ctrl.data(); w.u_cur = u_cur; w.costs_nm = costs_nm;
   if (origin_out) { origin_out[0] = w.wx0; origin_out[1] = w.wy0; }
+  if (reach_out) *reach_out = reach;
   const CUtensorMap t_lin{(const unsigned char*)lin, p.g.grid_cols, p.g.grid_rows, p.M, p.g.grid_pitch, WW, WH};
   const CUtensorMap t_ang{(const unsigned char*)ang, p.g.grid_cols, p.g.grid_rows, p.M, p.g.grid_pitch, WW, WH};
   const CUtensorMap t_obs{(const unsigned char*)obs, p.g.cols, p.g.rows, 1, p.g.mask_pitch, WW, WH};
@@ -151,5 +172,5 @@ def build(out_dir):
     lib = C.CDLL(so)
     P, I = C.c_void_p, C.c_int
     lib.emu_rollout_win.restype = I
-    lib.emu_rollout_win.argtypes = [P, P, P, P, P, P, P, P, P, P, I, I, P]
+    lib.emu_rollout_win.argtypes = [P, P, P, P, P, P, P, P, P, P, I, I, P, P]
     return lib

@@ -77,10 +77,12 @@ static void run(const SampleGridsV2Args& a, int threads, unsigned gx, unsigned g
 
 // nt TDMs (1 or 2) sampled from the generator states `states` (numba layout, gen = tix*(ty*M)+m*ty+tiy).
 // cum: (nt)(rows, cols, bpad) int8 running sums; grids: (nt)(M, grid_rows, pitch); qvals: (nt)(128).
+// box = {row_lo, row_hi, col_lo, col_hi} (cells) or null: with a box the launch is restricted as apply_box (api.cu)
+// does it and the states come from advance_states_kernel -- what tdm_sample_pair_on does for a boxed solve.
 extern "C" int emu_sample_v2(int nt, int8_t* grid0, int8_t* grid1, const int8_t* cum0, const int8_t* cum1,
                              const uint64_t* states, uint64_t* states_out, const int8_t* qv0, const int8_t* qv1, int bpad,
                              int rows, int cols, int grid_rows, int pitch, int tx, int ty, int num_maps, int segs,
-                             double alpha, int q_cap) {
+                             double alpha, int q_cap, const int* box) {
   using namespace b200;
   SampleGridsV2Args a{};
   std::vector<uint64_t> out2(states_out ? 0 : 1);
@@ -111,8 +113,25 @@ extern "C" int emu_sample_v2(int nt, int8_t* grid0, int8_t* grid1, const int8_t*
   }
   a.rows = rows; a.cols = cols; a.grid_rows = grid_rows; a.pitch = pitch; a.tx = tx; a.ty = ty; a.num_maps = num_maps;
   a.segs = segs; a.seg_rows = seg_rows;
-  const int threads = ((ty * SG_GM + 31) / 32) * 32;
-  const unsigned gx = (unsigned)(tx * segs), gy = (unsigned)((num_maps + SG_GM - 1) / SG_GM);
+  sample_box_full(a);
+  if (a.ty * a.gm > 256) a.gm = 256 / a.ty;
+  int tix_hi = tx - 1;
+  if (box) {                           // apply_box (api.cu)
+    a.row_lo = box[0]; a.row_hi = box[1];
+    a.tix_lo = box[0] / nrow;
+    a.tiy_lo = box[2] / ncol;
+    a.nact = (box[3] - 1) / ncol - a.tiy_lo + 1;
+    int gm = 128 / a.nact;
+    if (gm > SG_GM_MAX) gm = SG_GM_MAX;
+    if (gm > num_maps) gm = num_maps;
+    if (gm < 1) gm = 1;
+    a.gm = gm;
+    a.write_states = 0;
+    tix_hi = std::min(tx - 1, (std::max(a.row_hi, a.row_lo + 1) - 1) / nrow);       // launch_v2_nt (sample.cu)
+  }
+  const int threads = ((a.nact * a.gm + 31) / 32) * 32;
+  if (threads > 256 || a.gm < 1) return 3;
+  const unsigned gx = (unsigned)((tix_hi - a.tix_lo + 1) * segs), gy = (unsigned)((num_maps + a.gm - 1) / a.gm);
   const int nw = bpad / 4;
   if (nt == 1) {
     if (nw == 3) run<1, 3>(a, threads, gx, gy); else if (nw == 8) run<1, 8>(a, threads, gx, gy);
@@ -120,6 +139,22 @@ extern "C" int emu_sample_v2(int nt, int8_t* grid0, int8_t* grid1, const int8_t*
   } else {
     if (nw == 3) run<2, 3>(a, threads, gx, gy); else if (nw == 8) run<2, 8>(a, threads, gx, gy);
     else if (nw == 1) run<2, 1>(a, threads, gx, gy); else run<2, 0>(a, threads, gx, gy);
+  }
+  if (box) {                           // launch_advance_states (sample.cu), one thread at a time
+    int64_t ks[4];
+    const int nr = (rows + tx - 1) / tx, nc = (cols + ty - 1) / ty;           // sample_tile_draws
+    const int last_h = rows % nr ? rows % nr : nr, last_w = cols % nc ? cols % nc : nc;
+    ks[0] = (int64_t)nr * nc; ks[1] = (int64_t)nr * last_w; ks[2] = (int64_t)last_h * nc; ks[3] = (int64_t)last_h * last_w;
+    std::vector<uint64_t> mats(4 * 256);
+    build_jump_matrices(ks, 4, mats.data());
+    const int64_t total = (int64_t)tx * ty * num_maps;
+    blockDim = {128, 1, 1}; gridDim = {(unsigned)((total + 127) / 128), 1, 1};
+    for (int64_t g = 0; g < (int64_t)gridDim.x * 128; ++g) {
+      blockIdx = {(unsigned)(g / 128), 0, 0}; threadIdx = {(unsigned)(g % 128), 0, 0};
+      advance_states_kernel(reinterpret_cast<const ulonglong2*>(states), reinterpret_cast<ulonglong2*>(states_out),
+                            nt == 2 ? reinterpret_cast<ulonglong2*>(alt.data()) : nullptr,
+                            reinterpret_cast<const ulonglong2*>(mats.data()), rows, cols, tx, ty, num_maps);
+    }
   }
   if (nt == 2 && std::memcmp(alt.data(), states_out, alt.size() * 8) != 0) return 2;   // both TDMs advance alike
   return 0;
@@ -159,7 +194,7 @@ def build(out_dir, values_in_registers=None):
     lib = C.CDLL(so)
     P = C.c_void_p
     lib.emu_sample_v2.restype = C.c_int
-    lib.emu_sample_v2.argtypes = [C.c_int, P, P, P, P, P, P, P, P] + [C.c_int] * 9 + [C.c_double, C.c_int]
+    lib.emu_sample_v2.argtypes = [C.c_int, P, P, P, P, P, P, P, P] + [C.c_int] * 9 + [C.c_double, C.c_int, P]
     return lib
 
 

@@ -19,6 +19,6 @@ def test_noise_kernel_source_matches_reference(tmp_path):
     for key in ("noise1", "noise2"):
         noise = np.zeros((N, T, 2), np.float32)
         emu.emu_sample_noise(states.ctypes.data_as(C.c_void_p), noise.ctypes.data_as(C.c_void_p), N * T,
-                             np.float32(g["u_std"][0]), np.float32(g["u_std"][1]))
+                             np.float32(g["u_std"][0]), np.float32(g["u_std"][1]), None)
         np.testing.assert_allclose(noise, g[key], rtol=3e-6, atol=2e-6)
     assert (states == np.ascontiguousarray(g["states2"]).view(np.uint64).reshape(-1, 2)).all()

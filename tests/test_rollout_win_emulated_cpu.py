@@ -42,8 +42,9 @@ def test_windowed_kernel_matches_reference_and_generic_kernel(emu, gname):
     def run_win(sx, sy):
         out = np.zeros((N, M), F32)
         origin = np.zeros(2, np.int32)
+        reach = np.zeros(1, F32)
         assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur),
-                                   _p(out), sx, sy, _p(origin)) == 0
+                                   _p(out), sx, sy, _p(origin), _p(reach)) == 0
         return out, origin
     inside, origin = run_win(0, 0)
     assert origin[0] % 16 == 0                                    # TMA: 16-byte aligned inner coordinate
@@ -123,7 +124,7 @@ def test_windowed_kernel_on_a_cell_edge_takes_the_exact_sequence(emu):
     geo = _c([R, Cc, R, Cc, Cc, Cc, T, N, M], np.int32)
     out = np.zeros((N, M), F32)
     assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur), _p(out),
-                               0, 0, None) == 0
+                               0, 0, None, None) == 0
     cnm, costs = np.zeros((N, M), F32), np.zeros(N, F32)
     gen.emu_rollout(0, _p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), None, _p(noise), _p(u_cur), _p(cnm),
                     _p(costs), None, 0)
@@ -153,8 +154,12 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
     ratios = _ratios([0, 1], [0, 1])
     geo = _c([R, Cc, R, Cc, Cc, Cc, T, N, M], np.int32)
     out = np.zeros((N, M), F32)
+    reach = np.zeros(1, F32)
     assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur), _p(out),
-                               0, 0, None) == 0
+                               0, 0, None, _p(reach)) == 0
+    # the reach statistic of the prepare kernel: max_n sum_t |clip(u_v + e_v)|, never below the exact sum
+    vsum = np.abs(np.clip(u_cur[None, :, 0] + noise[:, :, 0], 0, 3).astype(np.float64)).sum(1).max()
+    assert vsum <= float(reach[0]) <= vsum * (1 + 1e-5)
     cnm, costs = np.zeros((N, M), F32), np.zeros(N, F32)
     gen.emu_rollout(0, _p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), None, _p(noise), _p(u_cur), _p(cnm),
                     _p(costs), None, 0)

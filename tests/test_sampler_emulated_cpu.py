@@ -52,7 +52,7 @@ def test_sampler_kernel_source_matches_oracle(emu, B, nt, segs, alpha, M, shape,
     q_cap = int(min(int(np.cumsum(p.astype(np.int64), axis=0)[-1].min()) for p in pmfs))
     rc = emu.emu_sample_v2(nt, _ptr(grids[0]), _ptr(grids[nt - 1]), _ptr(cums[0]), _ptr(cums[nt - 1]), _ptr(st_in),
                            _ptr(st_out), _ptr(q), _ptr(q), bpad, rows, cols, grid_rows, pitch, tx, ty, M, segs,
-                           float(alpha), min(q_cap, 127))
+                           float(alpha), min(q_cap, 127), None)
     assert rc == 0
     for k in range(nt):
         want = np.full((M, grid_rows, pitch), -7, dtype=np.int8)
@@ -88,7 +88,7 @@ def test_sampler_kernel_source_random_configurations(emu):
         st_in = np.ascontiguousarray(states0.copy())
         st_out = np.zeros_like(st_in)
         rc = emu.emu_sample_v2(nt, _ptr(grids[0]), _ptr(grids[nt - 1]), _ptr(cums[0]), _ptr(cums[nt - 1]), _ptr(st_in),
-                               _ptr(st_out), _ptr(q), _ptr(q), bpad, rows, cols, grid_rows, pitch, tx, ty, M, segs, alpha, 100)
+                               _ptr(st_out), _ptr(q), _ptr(q), bpad, rows, cols, grid_rows, pitch, tx, ty, M, segs, alpha, 100, None)
         assert rc == 0, case
         for k in range(nt):
             want = np.full((M, grid_rows, pitch), -7, dtype=np.int8)
@@ -97,3 +97,53 @@ def test_sampler_kernel_source_random_configurations(emu):
             tag = "case %d: B=%d nt=%d t=(%d,%d) map=(%d,%d) M=%d segs=%d alpha=%g" % (case, B, nt, tx, ty, rows, cols, M, segs, alpha)
             assert (grids[k][:, :rows, :cols] == want[:, :rows, :cols]).all(), tag
             assert (st_out == st).all(), tag
+
+
+def test_sampler_kernel_source_boxed_launch(emu):
+    """Reach-box launches (solve() only): inside the box the maps are those of a whole-map walk, outside the box
+    nothing is written, and advance_states_kernel leaves every generator exactly where the whole-map walk does --
+    random boxes, tiles, segment counts, map counts (maps per CTA follow the number of active tile columns)."""
+    rng = np.random.default_rng(77)
+    for case in range(14):
+        B = int(rng.choice([3, 5, 12, 12, 32]))
+        nt = int(rng.integers(1, 3))
+        tx, ty = int(rng.integers(1, 7)), int(rng.integers(1, 9))
+        rows, cols = int(rng.integers(max(tx, 6), 60)), int(rng.integers(max(ty, 6), 70))
+        M = int(rng.integers(1, 40))
+        segs = int(rng.integers(1, 6))
+        alpha = float(rng.choice([1.0, 0.7, 0.25]))
+        r_lo = int(rng.integers(0, rows - 1)); r_hi = int(rng.integers(r_lo + 1, rows + 1))
+        c_lo = int(rng.integers(0, cols - 1)); c_hi = int(rng.integers(c_lo + 1, cols + 1))
+        box = np.array([r_lo, r_hi, c_lo, c_hi], dtype=np.int32)
+        bpad = (B + 3) // 4 * 4
+        bin_values = np.linspace(0, 1, B)
+        bounds = np.array([0.0, 1.0], dtype=np.float32)
+        pmfs = [random_pmf(rng, B, rows, cols) for _ in range(nt)]
+        grid_rows, pitch = rows + int(rng.integers(0, 3)), (cols + int(rng.integers(0, 9)) + 15) // 16 * 16
+        states0 = X.create_states(tx * ty * M, int(rng.integers(1, 1000)))
+        q = np.zeros(128, dtype=np.int8)
+        q[:B] = TR.quantise_bin_values(bin_values, bounds)
+        grids = [np.full((M, grid_rows, pitch), -7, dtype=np.int8) for _ in range(nt)]
+        cums = [cumulative_table(p, bpad) for p in pmfs]
+        st_in = np.ascontiguousarray(states0.copy())
+        st_out = np.zeros_like(st_in)
+        rc = emu.emu_sample_v2(nt, _ptr(grids[0]), _ptr(grids[nt - 1]), _ptr(cums[0]), _ptr(cums[nt - 1]), _ptr(st_in),
+                               _ptr(st_out), _ptr(q), _ptr(q), bpad, rows, cols, grid_rows, pitch, tx, ty, M, segs, alpha, 100,
+                               _ptr(box))
+        tag = "case %d: B=%d nt=%d t=(%d,%d) map=(%d,%d) M=%d segs=%d alpha=%g box=%s" % (
+            case, B, nt, tx, ty, rows, cols, M, segs, alpha, box.tolist())
+        assert rc == 0, tag
+        nrow, ncol = -(-rows // tx), -(-cols // ty)
+        # what a boxed launch may touch: the box rows x the tile columns covering the box columns
+        tc_lo, tc_hi = (c_lo // ncol) * ncol, min((((c_hi - 1) // ncol) + 1) * ncol, cols)
+        for k in range(nt):
+            want = np.full((M, grid_rows, pitch), -7, dtype=np.int8)
+            st = states0.copy()
+            TR.sample_grids(want, pmfs[k], st, bin_values, bounds, alpha, (tx, ty), M)
+            assert (grids[k][:, r_lo:r_hi, c_lo:c_hi] == want[:, r_lo:r_hi, c_lo:c_hi]).all(), tag
+            inside = np.zeros((grid_rows, pitch), bool)
+            inside[r_lo:r_hi, tc_lo:tc_hi] = True
+            assert (grids[k][:, inside] == want[:, inside]).all(), tag
+            assert (grids[k][:, ~inside] == -7).all(), tag
+            assert (st_out == st).all(), tag
+        assert (st_in == states0).all()
