@@ -178,11 +178,13 @@ int b200mppi_planner_solve(b200mppi_planner* pl, float* u_out);
 /* Multi-GPU, MODE_TDM (the M sampled maps are sharded: rank r owns maps [r*M/ws, (r+1)*M/ws), samples
  * only those -- bit-identical to the same maps of a single-rank run -- and rolls out ALL N control
  * sequences on them):
- *   solve_local  : [first_iteration: sample this rank's maps] noise, rollouts -> B200MPPI_BUF_COSTS_NM
- *                  (N, M/ws) float32 = the send buffer of an all-to-all (block d -> rank d: rows
- *                  [d*N/ws, (d+1)*N/ws)).
+ *   solve_local  : noise, [first_iteration: sample this rank's maps], rollouts -> the device buffer
+ *                  B200MPPI_BUF_COSTS_NM, map-major and already split by destination: (ws, M/ws, N/ws) float32,
+ *                  block d = this rank's maps x the control sequences [d*N/ws, (d+1)*N/ws) that rank d reduces --
+ *                  the send buffer of an all-to-all with equal contiguous blocks.
  *   solve_reduce : CVaR over all M maps for this rank's N/ws control sequences from the received buffer
- *                  (world_size, N/ws, M/ws) float32, then this rank's softmax partial (2T+2 float32).
+ *                  (ws, M/ws, N/ws) float32 (block g = rank g's maps; i.e. the map-major (M, N/ws) array), then
+ *                  this rank's softmax partial (2T+2 float32).
  *   solve_finish : as below.
  * Multi-GPU, deterministic modes (one map): the N control sequences are sharded, no solve_reduce. */
 int b200mppi_planner_solve_reduce(b200mppi_planner* pl, const float* exchanged_costs_dev);
@@ -204,7 +206,10 @@ int b200mppi_planner_solve_finish(b200mppi_planner* pl, const float* gathered_pa
  *   p2p_import        : `handles` = the world_size exported handles in rank order (the caller all-gathers them
  *                       once, with any transport); opens the peers' buffers.
  *   p2p_connect_local : same for planners living in THIS process (peers[s] = rank s; devices may differ).
- *   p2p_push          : after solve_local (MODE_TDM): block d of the (N, M/ws) costs -> rank d, then signal.
+ *   p2p_push          : after solve_local (MODE_TDM): block d of the staged costs -> rank d, then signal.  A no-op
+ *                       when the windowed rollout kernel ran: with peers connected it stores every cost straight
+ *                       into the receive buffer of the rank that reduces it and raises the flags itself (the
+ *                       all-to-all is the rollout kernel's epilogue).
  *   p2p_reduce        : wait for every rank's block, CVaR + softmax partial (as solve_reduce), store the
  *                       partial into every rank's gather buffer, signal.
  *   p2p_finish        : wait for every rank's partial, combine (as solve_finish); u_out may be NULL.
@@ -243,7 +248,11 @@ enum {
   B200MPPI_BUF_U_CUR = 1,     /* float32 (T, 2)            u_cur_d                    */
   B200MPPI_BUF_COSTS = 2,     /* float32 (N_local)         costs_d (NOT clobbered)    */
   B200MPPI_BUF_WEIGHTS = 3,   /* float32 (N_local)         weights_d (normalised)     */
-  B200MPPI_BUF_COSTS_NM = 4,  /* float32 (N_local, M)      per-(n,m) costs, MODE_TDM  */
+  B200MPPI_BUF_COSTS_NM = 4,  /* float32 per-(n,m) costs, MODE_TDM.  copy_out / copy_in: the logical (N_local, M_local)
+                               * array [n][m].  Device buffer (planner_buffer): MAP-MAJOR (M, N) -- row m = all control
+                               * sequences on sampled map m -- and for a map-sharded planner (ws, M/ws, N/ws) blocks by
+                               * destination rank (see solve_local); not written when the rollout kernel stores
+                               * straight into the peers (p2p_push) */
   B200MPPI_BUF_RNG = 5,       /* uint64  (N_local*T, 2)    rng_states_d               */
   B200MPPI_BUF_PARTIAL = 6,   /* float32 (2T+2)            this rank's softmax partial*/
   B200MPPI_BUF_U_PREV = 7,    /* float32 (T, 2)            u_prev_d                   */

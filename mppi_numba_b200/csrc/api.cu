@@ -640,6 +640,7 @@ struct b200mppi_planner {
   int box_mode = 2;
   float* reach_d = nullptr;
   bool prepared = false;         // noiseT / ctrl hold this iteration's controls
+  bool pushed_direct = false;    // the last rollout kernel stored its costs straight into the peers (and signalled)
   int32_t last_box[5] = {};      // b200mppi_planner_sample_box
   float* h_u = nullptr;        // pinned staging for the T x 2 result (+ one int: exchange status)
   // peer-memory exchange (p2p.cu): ONE allocation per planner so that one IPC handle describes it:
@@ -915,6 +916,23 @@ static bool planner_tensor_maps(b200mppi_planner* p, int WW, int WH) {
   return ok;
 }
 
+// Per-(m, n) costs of this rank's rollouts, map-major (kernels.h, CostDst).
+//   one rank                     : costs_nm = (M, N)
+//   maps sharded, staged exchange: costs_nm = (ws, M/ws, N/ws) -- block d = what rank d will reduce (all-to-all send buffer)
+//   maps sharded, peer memory    : block d = rows [rank*M/ws, ...) of rank d's receive buffer (ws*M/ws, N/ws)   [direct]
+static void fill_cost_dst(b200mppi_planner* p, CostDst& d, bool direct) {
+  d = CostDst{};
+  if (!p->shard_maps) {
+    d.base[0] = p->costs_nm; d.n_per = p->n_local > 0 ? p->n_local : 1; d.ld = p->n_local; d.row0 = 0;
+    return;
+  }
+  const int ws = p->cfg.world_size;
+  d.n_per = p->n_red; d.ld = p->n_red;
+  d.row0 = direct ? p->cfg.rank * p->M : 0;
+  for (int r = 0; r < ws; ++r)
+    d.base[r] = direct ? (float*)p->peer_x[r] : p->costs_nm + (size_t)r * p->M * p->n_red;
+}
+
 static int stage_rollout(b200mppi_planner* p) {
   RolloutArgs a{};
   fill_rollout_params(p, a.p);
@@ -924,7 +942,9 @@ static int stage_rollout(b200mppi_planner* p) {
     a.obstacle = p->lin->obstacle; a.unknown = p->lin->unknown; a.risk = p->lin->risk;
   }
   a.obstacles = p->obstacles; a.num_obstacles = p->num_obstacles;
-  a.noise = p->noise; a.u_cur = p->u_cur; a.costs_nm = p->costs_nm; a.costs = p->costs;
+  a.noise = p->noise; a.u_cur = p->u_cur; a.costs = p->costs;
+  fill_cost_dst(p, a.dst, false);
+  p->pushed_direct = false;
   bool done = false;
   if (planner_uses_window(p)) {
     // stochastic mode: TMA-staged map windows (rollout_win.cu); window centred on the robot's cell
@@ -951,9 +971,20 @@ static int stage_rollout(b200mppi_planner* p) {
       w.wy0 = yi0 - WH / 2;
       w.npad = p->npad;
       w.lin_grid = l->grid; w.ang_grid = g->grid; w.obstacle = l->obstacle; w.unknown = l->unknown;
-      w.noiseT = p->noiseT; w.ctrl = p->ctrl; w.u_cur = p->u_cur; w.costs_nm = p->costs_nm;
+      w.noiseT = p->noiseT; w.ctrl = p->ctrl; w.u_cur = p->u_cur;
+      // sharded + peers connected: the all-to-all is this kernel's epilogue (stores into the peers, then the flags)
+      const bool direct = p->shard_maps && p->p2p_ready;
+      fill_cost_dst(p, w.dst, direct);
+      if (direct) {
+        const int ws = p->cfg.world_size;
+        w.sig.ws = ws; w.sig.rank = p->cfg.rank;
+        w.sig.counter = (unsigned*)(p->xbuf + p->x_counter);
+        w.sig.epoch = ++p->epoch_cost;
+        for (int r = 0; r < ws; ++r) w.sig.peer_flags[r] = (uint32_t*)(p->peer_x[r] + p->x_flags_cost);
+      }
       CU(launch_rollout_win(w, p->tmaps[0], p->tmaps[1], p->tmaps[2], p->tmaps[3], p->stream));
       p->launches++;
+      p->pushed_direct = direct;
       done = true;
     }
   }
@@ -964,7 +995,7 @@ static int stage_rollout(b200mppi_planner* p) {
   }
   if (p->profiling) cudaEventRecord(p->ev[3], p->stream);
   if (p->cfg.mode == B200MPPI_MODE_TDM && !p->shard_maps) {
-    launch_cvar(p->costs_nm, p->costs, p->n_local, p->M, 1, p->prm.cvar_alpha, p->stream);
+    launch_cvar(p->costs_nm, p->costs, p->n_local, p->n_local, p->M, p->prm.cvar_alpha, p->stream);
     p->launches++;
     CHECK_LAUNCH();
   }
@@ -1132,8 +1163,9 @@ extern "C" int b200mppi_planner_solve_reduce(b200mppi_planner* p, const float* e
   if (!p || !exchanged_dev) return fail(B200MPPI_EINVAL, "solve_reduce: null argument");
   if (!p->shard_maps) return fail(B200MPPI_ESTATE, "solve_reduce: only for MODE_TDM with world_size > 1");
   CU(cudaSetDevice(p->cfg.device));
-  // exchanged_dev: (world_size, N/ws, M_local) -- chunk g holds rank g's maps for THIS rank's n-slice
-  launch_cvar(exchanged_dev, p->costs, p->n_red, p->M, p->cfg.world_size, p->prm.cvar_alpha, p->stream);
+  // exchanged_dev: (world_size, M_local, N/ws) -- block g holds rank g's maps for THIS rank's control sequences,
+  // i.e. the map-major (M_total, N/ws) array of a one-rank solve restricted to them
+  launch_cvar(exchanged_dev, p->costs, p->n_red, p->n_red, p->M_total, p->prm.cvar_alpha, p->stream);
   p->launches++;
   CHECK_LAUNCH();
   if (p->profiling) cudaEventRecord(p->ev[4], p->stream);
@@ -1250,6 +1282,7 @@ extern "C" int b200mppi_planner_p2p_push(b200mppi_planner* p) {
   int rc = p2p_check(p, "p2p_push");
   if (rc) return rc;
   if (!p->shard_maps) return fail(B200MPPI_ESTATE, "p2p_push: only MODE_TDM shards the maps");
+  if (p->pushed_direct) return B200MPPI_OK;      // the rollout kernel stored into the peers and raised the flags itself
   P2PPushArgs a{};
   a.costs_nm = p->costs_nm;
   a.ws = p->cfg.world_size; a.rank = p->cfg.rank; a.n_red = p->n_red; a.Mc = p->M;
@@ -1272,7 +1305,7 @@ extern "C" int b200mppi_planner_p2p_reduce(b200mppi_planner* p) {
   int* status = (int*)(p->xbuf + p->x_status);
   if (p->shard_maps) {
     launch_p2p_wait((const uint32_t*)(p->xbuf + p->x_flags_cost), ws, p->epoch_cost, p->p2p_timeout_ns, status, p->stream);
-    launch_cvar((const float*)p->xbuf, p->costs, p->n_red, p->M, ws, p->prm.cvar_alpha, p->stream);
+    launch_cvar((const float*)p->xbuf, p->costs, p->n_red, p->n_red, p->M_total, p->prm.cvar_alpha, p->stream);
     p->launches += 2;
     CHECK_LAUNCH();
     if (p->profiling) cudaEventRecord(p->ev[4], p->stream);
@@ -1392,7 +1425,7 @@ extern "C" int b200mppi_planner_cvar(b200mppi_planner* p) {
   if (p->M > cvar_max_maps()) return fail(B200MPPI_EINVAL, "cvar: num_grid_samples exceeds the CVaR kernel's limit (16384)");
   CU(cudaSetDevice(p->cfg.device));
   if (p->shard_maps) return fail(B200MPPI_ESTATE, "cvar: maps are sharded, use solve_reduce");
-  launch_cvar(p->costs_nm, p->costs, p->n_local, p->M, 1, p->prm.cvar_alpha, p->stream);
+  launch_cvar(p->costs_nm, p->costs, p->n_local, p->n_local, p->M, p->prm.cvar_alpha, p->stream);
   p->launches++;
   CHECK_LAUNCH();
   CU(cudaStreamSynchronize(p->stream));
@@ -1461,12 +1494,34 @@ extern "C" int b200mppi_planner_buffer(b200mppi_planner* p, int32_t id, void** p
   return B200MPPI_OK;
 }
 
+// B200MPPI_BUF_COSTS_NM through copy_out / copy_in is the LOGICAL array (n_local, M_local), element [n][m] -- the
+// device buffer is map-major and, for a map-sharded planner, split into per-destination blocks (fill_cost_dst):
+// logical [n][m]  <->  block n / n_per, row m, column n % n_per.
+static void costs_logical(const b200mppi_planner* p, const float* dev_layout, float* logical, bool to_logical) {
+  const int N = p->n_local, M = p->M;
+  const int n_per = p->shard_maps ? p->n_red : N;
+  for (int n = 0; n < N; ++n) {
+    const int blk = n / n_per, c = n - blk * n_per;
+    for (int m = 0; m < M; ++m) {
+      const size_t di = ((size_t)blk * M + m) * n_per + c, li = (size_t)n * M + m;
+      if (to_logical) logical[li] = dev_layout[di]; else const_cast<float*>(dev_layout)[di] = logical[li];
+    }
+  }
+}
+
 extern "C" int b200mppi_planner_copy_out(b200mppi_planner* p, int32_t id, void* dst, size_t bytes) {
   void* d; size_t b;
   int rc = b200mppi_planner_buffer(p, id, &d, &b);
   if (rc) return rc;
   if (!dst || bytes != b) return fail(B200MPPI_EINVAL, "copy_out: size mismatch");
   CU(cudaSetDevice(p->cfg.device));
+  if (id == B200MPPI_BUF_COSTS_NM) {
+    std::vector<float> tmp(b / sizeof(float));
+    CU(cudaMemcpyAsync(tmp.data(), d, b, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    costs_logical(p, tmp.data(), (float*)dst, true);
+    return B200MPPI_OK;
+  }
   CU(cudaMemcpyAsync(dst, d, b, cudaMemcpyDeviceToHost, p->stream));
   CU(cudaStreamSynchronize(p->stream));
   return B200MPPI_OK;
@@ -1479,6 +1534,13 @@ extern "C" int b200mppi_planner_copy_in(b200mppi_planner* p, int32_t id, const v
   if (!src || bytes != b) return fail(B200MPPI_EINVAL, "copy_in: size mismatch");
   CU(cudaSetDevice(p->cfg.device));
   p->prepared = false;
+  if (id == B200MPPI_BUF_COSTS_NM) {
+    std::vector<float> tmp(b / sizeof(float));
+    costs_logical(p, tmp.data(), const_cast<float*>((const float*)src), false);
+    CU(cudaMemcpyAsync(d, tmp.data(), b, cudaMemcpyHostToDevice, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return B200MPPI_OK;
+  }
   CU(cudaMemcpyAsync(d, src, b, cudaMemcpyHostToDevice, p->stream));
   CU(cudaStreamSynchronize(p->stream));
   return B200MPPI_OK;

@@ -69,6 +69,32 @@ void launch_collapse_pad(const int8_t* raw, int8_t* out, int8_t* risk, int* bad_
 void launch_sample_noise(uint64_t* states, float* noise, int n_local, int T, float std_v,
                          float std_w, float* reach, cudaStream_t st);
 
+// Where the per-(map, control sequence) cost of a stochastic rollout goes.  Layout is MAP-MAJOR: row m holds the
+// costs of the control sequences on sampled map m, so the 32 lanes of a warp (consecutive n, same map) store one
+// 128-byte line.  The control sequences are split into blocks of n_per (one block unless the maps are sharded over
+// ranks: block d then belongs to rank d, which reduces those control sequences, and base[d] may point straight into
+// rank d's receive buffer -- the all-to-all of the sharded solve is the rollout kernel's own epilogue).
+// [emu:begin cost_dst]
+constexpr int P2P_MAX_PEERS = 16;
+struct CostDst {
+  float* base[P2P_MAX_PEERS];   // block d: rows = maps, row stride ld, column = n - d*n_per
+  int n_per;                    // control sequences per block
+  int ld;                       // floats per row
+  int row0;                     // row of this rank's map 0 inside a block
+};
+__host__ __device__ __forceinline__ float* cost_ptr(const CostDst& d, int m, int n) {
+  const int b = n / d.n_per;
+  return d.base[b] + (size_t)(d.row0 + m) * d.ld + (n - b * d.n_per);
+}
+// epoch flags raised in every peer once ALL CTAs of the kernel have stored (ws = 0: nothing to signal)
+struct CostSignal {
+  uint32_t* peer_flags[P2P_MAX_PEERS];   // peer d's cost flags [ws]; this rank writes entry `rank`
+  unsigned* counter;                     // local, zero between launches
+  int ws, rank;
+  uint32_t epoch;
+};
+// [emu:end cost_dst]
+
 // rollout kernels (mppi.py:613-1111)
 // [emu:begin rollout_args]
 struct RolloutArgs {
@@ -81,7 +107,7 @@ struct RolloutArgs {
   const int8_t* risk;       // (rows, cols) or null
   const float* noise;       // (N, T, 2)
   const float* u_cur;       // (T, 2)
-  float* costs_nm;          // (N, M)   MODE_TDM
+  CostDst dst;              // MODE_TDM: per-(m, n) costs
   float* costs;             // (N)
   const float* obstacles;   // MODE_BAREBONE: (num_obstacles, 3) = x, y, radius
   int num_obstacles;
@@ -98,7 +124,8 @@ struct RolloutWinArgs {
   const float* noiseT;      // [T][npad] double2: clipped noisy controls (v, w), already widened to f64
   const float* ctrl;        // [npad]
   const float* u_cur;
-  float* costs_nm;          // (N, M)
+  CostDst dst;              // per-(m, n) costs
+  CostSignal sig;           // sharded solve with the peer-memory exchange: flags to raise when the kernel is done
 };
 // [emu:end win_args]
 // reach (may be null): *reach = max(*reach, max_n sum_t |clipped v[n,t]|) -- bounds how far a rollout can travel
@@ -110,13 +137,12 @@ bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int
 void rollout_win_geometry(int T, int* WW, int* WH, size_t* smem);
 cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, const void* tm_ang, const void* tm_obs,
                                const void* tm_unk, cudaStream_t st);
-// CVaR over M (mppi.py:718-755): costs[n] = mean of the ceil(M*alpha) largest of costs_nm[n,:]
-// costs_nm is laid out as `chunks` blocks of (N, M): value j of rollout n lives in block j / M at
-// (n, j % M) -- chunks = 1 is the plain (N, M) buffer; chunks = world_size is the all-to-all result of a
-// map-sharded solve (block g = rank g's maps).  The CVaR is over all chunks*M values.
+// CVaR over M (mppi.py:718-755): costs[n] = mean of the ceil(M*alpha) largest of costs_mn[:, n]
+// costs_mn is map-major: (M, n_cnt) with row stride ld -- the local buffer of a one-rank solve, or the receive buffer
+// of a map-sharded solve (rows g*M/ws .. = rank g's maps): the same kernel, the same values per lane, hence
+// bit-identical CVaR costs whatever the number of ranks.
 int cvar_max_maps();   // largest M the CVaR kernels accept
-void launch_cvar(const float* costs_nm, float* costs, int N, int M, int chunks, float cvar_alpha,
-                 cudaStream_t st);
+void launch_cvar(const float* costs_mn, float* costs, int n_cnt, int ld, int M, float cvar_alpha, cudaStream_t st);
 
 // update_useq_numba (mppi.py:1113-1191) as an online-softmax two-level reduction
 // [emu:begin update_args]
@@ -152,10 +178,9 @@ struct VisArgs {
 void launch_state_rollout(const VisArgs& a, cudaStream_t st);
 
 // peer-memory exchange of the sharded solve (p2p.cu)
-constexpr int P2P_MAX_PEERS = 16;
 struct P2PPushArgs {
-  const float* costs_nm;              // local (N, Mc): block d = rows [d*n_red, (d+1)*n_red)
-  float* peer_recv[P2P_MAX_PEERS];    // peer d's receive buffer (ws, n_red, Mc)
+  const float* costs_nm;              // local staged blocks (ws, Mc, n_red): block d = this rank's maps x rank d's control sequences
+  float* peer_recv[P2P_MAX_PEERS];    // peer d's receive buffer (ws, Mc, n_red): block `rank` is written
   uint32_t* peer_flags[P2P_MAX_PEERS];// peer d's cost flags [ws]
   unsigned* counter;                  // local, zero between launches
   int ws, rank, n_red, Mc;

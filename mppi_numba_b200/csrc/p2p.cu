@@ -14,22 +14,15 @@
 
 namespace b200 {
 
-__device__ __forceinline__ void st_flag_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_flag_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 
-// ---- all-to-all of cost blocks: block d of the local (N, Mc) array = rows [d*n_red, (d+1)*n_red), contiguous
-// n_red*Mc floats, goes to chunk `rank` of peer d's receive buffer (ws, n_red, Mc).  grid = (ctas_per_peer, ws).
+// ---- all-to-all of cost blocks (only for rollouts that did not store straight into the peers -- the generic
+// rollout kernel): block d of the local staged array (ws, Mc, n_red), contiguous n_red*Mc floats, goes to block
+// `rank` of peer d's receive buffer (ws, Mc, n_red).  grid = (ctas_per_peer, ws).
 __global__ void __launch_bounds__(256) p2p_push_kernel(const P2PPushArgs a) {
   const int d = blockIdx.y;
   const size_t block_elems = (size_t)a.n_red * a.Mc;

@@ -73,7 +73,7 @@ __device__ __forceinline__ float ctrl_term(float u0, float u1, float e0, float e
 
 // ---------------------------------------------------------------------------------------------
 // Generic rollout kernel: one thread per (n, m); lanes of a warp = consecutive n on the SAME map.
-// MODE 0: stochastic (costs_nm[n*M+m]);  MODE 1: det dynamics;  MODE 2: nominal + speed map.
+// MODE 0: stochastic (per-(m,n) cost -> a.dst);  MODE 1: det dynamics;  MODE 2: nominal + speed map.
 template <int MODE>
 __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
   const RolloutParams& p = a.p;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
       cost = ffma(ctrl_term(s_u[2 * t], s_u[2 * t + 1], e.x, e.y, sv2, sw2), p.lambda, cost);
     }
     cost = fadd(cost, term_cost(d2, p.v_post, reached));
-    a.costs_nm[(size_t)n * p.M + m] = cost;
+    *cost_ptr(a.dst, m, n) = cost;
   } else {                              // terminal, then control (mppi.py:1004-1009)
     cost = fadd(cost, term_cost(d2, p.v_post, reached));
     for (int t = 0; t < p.T; ++t) {
@@ -220,51 +220,70 @@ __device__ __forceinline__ float key_float(uint32_t k) {   // inverse of float_k
 
 constexpr int CVAR_MAX_PER_LANE = 32;   // warp kernel: M <= 1024 (the reference's one-block limit, mppi.py:199)
 constexpr int CVAR_LARGE_MAX_MAPS = 16384;   // CTA kernel: 64 KB of keys (Config clamps M to 15000, config.py:63)
+constexpr int CVAR_THREADS = 256;
+constexpr int CVAR_TILE_FLOATS = 8192 + 32;  // shared-memory tile of the warp kernel: NB control sequences x (M + 1)
 
-// PER = values held per lane (compile time: the select loop is fully unrolled over them)
+// control sequences per CTA: 32 (one 128-byte line per map row) while the tile fits, fewer for many maps
+__host__ __device__ inline int cvar_block_n(int M) {
+  int nb = 32;
+  while (nb > 1 && nb * (M + 1) > CVAR_TILE_FLOATS) nb >>= 1;
+  return nb;
+}
+
+// costs_mn is map-major (M rows, row stride ld): a CTA loads the M x NB slab of its NB control sequences with
+// coalesced row segments, transposes it through shared memory, then each warp selects for NB/8 of them.
+// PER = values held per lane (compile time: the select loop is fully unrolled over them); value j = map j sits in
+// slot j / 32 of lane j % 32 whatever the number of ranks the maps came from.
 template <int PER>
-__global__ void __launch_bounds__(128) cvar_kernel(const float* __restrict__ costs_nm,
-                                                   float* __restrict__ costs, int N, int Mc, int chunks, int numel) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= N) return;
-  const int M = Mc * chunks;                                  // values per control sequence
-  const size_t chunk_stride = (size_t)N * Mc;
-  const float* row = costs_nm + (size_t)warp * Mc;
-  float v[PER];
-#pragma unroll
-  for (int i = 0; i < PER; ++i) {
-    const int j = i * 32 + lane;
-    v[i] = (j < M) ? row[(size_t)(j / Mc) * chunk_stride + (j % Mc)] : -INFINITY;
+__global__ void __launch_bounds__(CVAR_THREADS) cvar_kernel(const float* __restrict__ costs_mn,
+                                                            float* __restrict__ costs, int n_cnt, int ld, int M, int numel) {
+  __shared__ float s_tile[CVAR_TILE_FLOATS];
+  const int NB = cvar_block_n(M);
+  const int n0 = blockIdx.x * NB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int idx = tid; idx < M * NB; idx += CVAR_THREADS) {
+    const int m = idx / NB, j = idx - m * NB;
+    s_tile[j * (M + 1) + m] = (n0 + j < n_cnt) ? costs_mn[(size_t)m * ld + n0 + j] : 0.0f;
   }
-  float sum = 0.0f;
-  if (numel >= M) {
-#pragma unroll
-    for (int i = 0; i < PER; ++i) if (i * 32 + lane < M) sum += v[i];
-    sum = warp_sum(sum);
-  } else {
-    // find the key of the numel-th largest value
-    uint32_t prefix = 0;
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t cand = prefix | (1u << bit);
-      int cnt = 0;
-#pragma unroll
-      for (int i = 0; i < PER; ++i) cnt += (float_key(v[i]) >= cand) ? 1 : 0;
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt >= numel) prefix = cand;
-    }
-    // sum everything strictly above the k-th key, then add the k-th value for the remaining slots
-    // (all holders of the k-th key hold the same float: the key map is a bijection)
-    int greater = 0;
+  __syncthreads();
+  for (int j = warp; j < NB; j += CVAR_THREADS / 32) {
+    if (n0 + j >= n_cnt) break;                               // warp-uniform
+    const float* row = s_tile + j * (M + 1);
+    float v[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-      if (float_key(v[i]) > prefix) { sum += v[i]; ++greater; }
+      const int k = i * 32 + lane;
+      v[i] = (k < M) ? row[k] : -INFINITY;
     }
-    sum = warp_sum(sum);
-    greater = __reduce_add_sync(0xffffffffu, greater);
-    sum += (float)(numel - greater) * key_float(prefix);
+    float sum = 0.0f;
+    if (numel >= M) {
+#pragma unroll
+      for (int i = 0; i < PER; ++i) if (i * 32 + lane < M) sum += v[i];
+      sum = warp_sum(sum);
+    } else {
+      // find the key of the numel-th largest value
+      uint32_t prefix = 0;
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = prefix | (1u << bit);
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) cnt += (float_key(v[i]) >= cand) ? 1 : 0;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt >= numel) prefix = cand;
+      }
+      // sum everything strictly above the k-th key, then add the k-th value for the remaining slots
+      // (all holders of the k-th key hold the same float: the key map is a bijection)
+      int greater = 0;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        if (float_key(v[i]) > prefix) { sum += v[i]; ++greater; }
+      }
+      sum = warp_sum(sum);
+      greater = __reduce_add_sync(0xffffffffu, greater);
+      sum += (float)(numel - greater) * key_float(prefix);
+    }
+    if (lane == 0) costs[n0 + j] = (float)((double)sum / (double)numel);
   }
-  if (lane == 0) costs[warp] = (float)((double)sum / (double)numel);
 }
 
 // M > 1024 (the reference switches to rollout_oversized_numba, mppi.py:199-203, 760-913, whose "sort" swaps
@@ -273,18 +292,14 @@ __global__ void __launch_bounds__(128) cvar_kernel(const float* __restrict__ cos
 // sequence, the M keys in shared memory, the same bitwise radix select with a CTA-wide count per bit.
 constexpr int CVAR_LARGE_THREADS = 256;
 
-__global__ void __launch_bounds__(CVAR_LARGE_THREADS) cvar_large_kernel(const float* __restrict__ costs_nm,
-                                                                        float* __restrict__ costs, int N, int Mc,
-                                                                        int chunks, int numel) {
+__global__ void __launch_bounds__(CVAR_LARGE_THREADS) cvar_large_kernel(const float* __restrict__ costs_mn,
+                                                                        float* __restrict__ costs, int n_cnt, int ld,
+                                                                        int M, int numel) {
   extern __shared__ uint32_t s_keys[];
   __shared__ int s_cnt[2][CVAR_LARGE_THREADS / 32];
   __shared__ float s_sum[CVAR_LARGE_THREADS / 32];
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int M = Mc * chunks;
-  const size_t chunk_stride = (size_t)N * Mc;
-  const float* row = costs_nm + (size_t)n * Mc;
-  for (int j = tid; j < M; j += CVAR_LARGE_THREADS)
-    s_keys[j] = float_key(row[(size_t)(j / Mc) * chunk_stride + (j % Mc)]);
+  for (int j = tid; j < M; j += CVAR_LARGE_THREADS) s_keys[j] = float_key(costs_mn[(size_t)j * ld + n]);
   __syncthreads();
   uint32_t prefix = 0;
   int greater_total = 0;
@@ -324,8 +339,7 @@ __global__ void __launch_bounds__(CVAR_LARGE_THREADS) cvar_large_kernel(const fl
 // [emu:end cvar]
 int cvar_max_maps() { return CVAR_LARGE_MAX_MAPS; }
 
-void launch_cvar(const float* costs_nm, float* costs, int N, int Mc, int chunks, float cvar_alpha, cudaStream_t st) {
-  const int M = Mc * chunks;
+void launch_cvar(const float* costs_mn, float* costs, int n_cnt, int ld, int M, float cvar_alpha, cudaStream_t st) {
   int numel = (int)ceil((double)M * (double)cvar_alpha);    // mppi.py:744 (float32 alpha, f64 product)
   if (numel < 1) numel = 1;
   if (numel > M) numel = M;
@@ -333,19 +347,18 @@ void launch_cvar(const float* costs_nm, float* costs, int N, int Mc, int chunks,
     const size_t smem = (size_t)M * sizeof(uint32_t);
     cudaFuncSetAttribute(cvar_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,   // per device
                          CVAR_LARGE_MAX_MAPS * (int)sizeof(uint32_t));
-    cvar_large_kernel<<<(unsigned)N, CVAR_LARGE_THREADS, smem, st>>>(costs_nm, costs, N, Mc, chunks, numel);
+    cvar_large_kernel<<<(unsigned)n_cnt, CVAR_LARGE_THREADS, smem, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
     return;
   }
-  const int threads = 128;
-  const int warps_per_block = threads / 32;
-  const unsigned blocks = (unsigned)((N + warps_per_block - 1) / warps_per_block);
+  const int nb = cvar_block_n(M);
+  const unsigned blocks = (unsigned)((n_cnt + nb - 1) / nb);
   const int per = (M + 31) / 32;
-  if (per <= 1) cvar_kernel<1><<<blocks, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
-  else if (per <= 2) cvar_kernel<2><<<blocks, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
-  else if (per <= 4) cvar_kernel<4><<<blocks, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
-  else if (per <= 8) cvar_kernel<8><<<blocks, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
-  else if (per <= 16) cvar_kernel<16><<<blocks, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
-  else cvar_kernel<32><<<blocks, threads, 0, st>>>(costs_nm, costs, N, Mc, chunks, numel);
+  if (per <= 1) cvar_kernel<1><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
+  else if (per <= 2) cvar_kernel<2><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
+  else if (per <= 4) cvar_kernel<4><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
+  else if (per <= 8) cvar_kernel<8><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
+  else if (per <= 16) cvar_kernel<16><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
+  else cvar_kernel<32><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -19,6 +19,9 @@
 // A rollout that leaves the window reads the maps from global memory instead (same values).
 #include <cuda.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace b200 {
@@ -175,13 +178,20 @@ __host__ __device__ inline WinSmem win_smem_layout(int WW, int WH, int T) {
   const int planes = (4 * s.plane + 127) & ~127;
   s.off_lut = planes;                              // 2 x 256 doubles
   s.off_u = s.off_lut + 2 * 256 * 8;               // 2T floats
-  s.off_bar = (s.off_u + 2 * T * 4 + 15) & ~15;
+  s.off_bar = (s.off_u + 2 * T * 4 + 15) & ~15;       // mbarrier (8 bytes) + the chunk counter
   s.total = s.off_bar + 16;
   return s;
 }
 
 constexpr int WIN_WW = 240;       // window width in cells (inner TMA box extent: 240 B, multiple of 16)
 
+// Work distribution: PERSISTENT grid, one CTA per SM.  The work list is the map-major sequence of 32-rollout chunks
+// (map m, control sequences [32c, 32c + 32)); CTA b owns the contiguous share [b*total/G, (b+1)*total/G) of it --
+// every SM gets the same number of chunks whatever M and N are (a (tiles, M) grid of one-tile CTAs quantises: 256
+// tile units on 148 SMs at 8 GPUs = two rounds where 1.73 would do).  A share spans one to a few maps: per map the
+// CTA stages that map's window once (thread 0 issues the TMA loads after the CTA has left the previous window), then
+// its warps pull chunks from a shared-memory counter until the map's part of the share is done -- warps whose
+// rollouts reached the goal early simply take the next chunk.
 template <int THREADS, int WH>
 __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWinArgs a,
                                                                  const __grid_constant__ CUtensorMap tm_lin,
@@ -197,18 +207,15 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   double* s_lutA = s_lutL + 256;
   float* s_u = reinterpret_cast<float*>(smem + L.off_u);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  int* s_next = reinterpret_cast<int*>(bar + 1);             // chunk counter of the current map
 
-  const int tid = threadIdx.x;
-  const int m = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int cpm = a.npad >> 5;                               // chunks per map
+  const long long total = (long long)p.M * cpm;
+  const long long w_lo = total * blockIdx.x / gridDim.x, w_hi = total * (blockIdx.x + 1) / gridDim.x;
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(bar, 4u * (uint32_t)PLANE);
-    tma_load_3d(smem, &tm_lin, bar, a.wx0, a.wy0, m);
-    tma_load_3d(smem + PLANE, &tm_ang, bar, a.wx0, a.wy0, m);
-    tma_load_2d(smem + 2 * PLANE, &tm_obs, bar, a.wx0, a.wy0);
-    tma_load_2d(smem + 3 * PLANE, &tm_unk, bar, a.wx0, a.wy0);
   }
   // traction tables: (lo + ratio*q) * dt exactly as the reference evaluates it (fma.rn.f64, mul.f64)
   const double dt64 = f2d(p.dt);
@@ -218,8 +225,6 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     s_lutA[i] = fma(p.ang_ratio, q, f2d(p.ang_lo)) * dt64;
   }
   for (int i = tid; i < 2 * p.T; i += THREADS) s_u[i] = a.u_cur[i];
-  __syncthreads();
-  mbar_wait(bar, 0);
 
   uint32_t sb_win = smem_u32(smem);
   uint32_t sb_lutL = smem_u32(s_lutL) + 128 * 8;     // index by the signed int8 value directly
@@ -234,18 +239,44 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   int magic_wx = 0x4B400000 + a.wx0, magic_wy = 0x4B400000 + a.wy0;
   asm volatile("" : "+r"(magic_wx), "+r"(magic_wy));       // keep the folded constants (else re-derived per step)
   const float inv_lo = inv_res * (1.0f - 4.8e-7f), inv_hi = inv_res * (1.0f + 4.8e-7f);
-  const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
-  const int8_t* __restrict__ g_ang = a.ang_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
 
-  for (int tile = blockIdx.x; tile * THREADS < p.N; tile += gridDim.x) {
-    const int n = tile * THREADS + tid;
-    if (n >= p.N) break;
+  uint32_t phase = 0;
+  for (long long w = w_lo; w < w_hi;) {
+    const int m = (int)(w / cpm);
+    const int c_lo = (int)(w - (long long)m * cpm);
+    const int c_hi = (int)min((long long)cpm, w_hi - (long long)m * cpm);       // this map's part of the share
+    w += c_hi - c_lo;
+    __syncthreads();                                        // every warp has left the previous window (and the tables are written)
+    if (tid == 0) {
+      *s_next = c_lo;
+      // order the CTA's generic-proxy reads of the previous window before the async-proxy writes of the next one
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar, 4u * (uint32_t)PLANE);
+      tma_load_3d(smem, &tm_lin, bar, a.wx0, a.wy0, m);
+      tma_load_3d(smem + PLANE, &tm_ang, bar, a.wx0, a.wy0, m);
+      tma_load_2d(smem + 2 * PLANE, &tm_obs, bar, a.wx0, a.wy0);
+      tma_load_2d(smem + 3 * PLANE, &tm_unk, bar, a.wx0, a.wy0);
+    }
+    __syncthreads();                                        // s_next visible
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
+    const int8_t* __restrict__ g_ang = a.ang_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
+
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(s_next, 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= c_hi) break;
+      const int n = (c << 5) + lane;
+      const bool live = n < p.N;                            // ragged last chunk (n is padded to whole warps): such lanes
+      const int Tn = live ? p.T : 0;                        // run zero steps and store nothing, but stay with their warp
     const double2* __restrict__ ep = reinterpret_cast<const double2*>(a.noiseT) + n;
     float x = p.x0[0], y = p.x0[1], th = p.x0[2];
     double x64 = widen(x), y64 = widen(y), th64 = widen(th);   // same values, float64 registers
     float cost = 0.0f, d2 = 1e9f;
-    double2 c = __ldg(ep);                                  // controls of step t (loaded during step t-1, see below)
-    for (int t = 0; t < p.T; ++t) {
+    double2 c2 = __ldg(ep);                                 // controls of step t (loaded during step t-1, see below)
+    for (int t = 0; t < Tn; ++t) {
       ep += a.npad;
       // ---- cell index of both axes: floor(a/res) by round-down magic-number addition on the FP32 pipe, taken
       //      at BOTH ends of an interval that contains the exact quotient a/res (relative half-width 4.8e-7,
@@ -277,18 +308,18 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
         ob = __ldg(a.obstacle + (size_t)my * p.g.mask_pitch + mx);
         un = __ldg(a.unknown + (size_t)my * p.g.mask_pitch + mx);
       }
-      // ---- noisy clipped control (mppi.py:686-689): `c`, precomputed per (n, t) by the prepare kernel
+      // ---- noisy clipped control (mppi.py:686-689): `c2`, precomputed per (n, t) by the prepare kernel
       // ---- unicycle step (mppi.py:692-694): float64 FMA, one rounding to float32 per component.  The
       //      float64 copies hold the float32-rounded state, so the reference's f2d(x) costs nothing.
-      const double dv = lds_f64(sb_lutL + (uint32_t)(ql * 8)) * c.x;
+      const double dv = lds_f64(sb_lutL + (uint32_t)(ql * 8)) * c2.x;
       const float cs = cos_approx(th);
       const float sn = sin_approx(th);
       const double rx = fma(dv, widen(cs), x64);
       const double ry = fma(dv, widen(sn), y64);
-      const double rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), c.y, th64);
-      // `c` is dead from here on: fetch the next step's controls straight into it -- the rest of this step and the
+      const double rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), c2.y, th64);
+      // `c2` is dead from here on: fetch the next step's controls straight into it -- the rest of this step and the
       // cell lookup of the next one (~70 instructions per warp, 32 warps per SM) cover the L2 latency
-      if (t + 1 < p.T) c = __ldg(ep);
+      if (t + 1 < Tn) c2 = __ldg(ep);
       x = narrow(rx); y = narrow(ry); th = narrow(rt);
       x64 = round_to_f32_precision(rx); y64 = round_to_f32_precision(ry); th64 = round_to_f32_precision(rt);
       // ---- stage cost (mppi.py:696-701)
@@ -304,7 +335,22 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     cost = fadd(cost, a.ctrl[n]);                                           // control cost (mppi.py:708-710)
     const double num = f2d(not_reached) * f2d(sqrt_approx(d2));              // terminal cost (mppi.py:26-28)
     cost = fadd(cost, d2f(num / (f2d(p.v_post) + 1e-6)));
-    a.costs_nm[(size_t)n * p.M + m] = cost;
+    if (live) *cost_ptr(a.dst, m, n) = cost;                // map-major: the warp's 32 lanes store one 128-byte line
+    }
+  }
+  // sharded solve, peer-memory exchange: the costs above went straight into the receive buffers of the ranks that
+  // reduce them; the LAST CTA to get here raises this rank's epoch flag in every peer (p2p.cu has the protocol)
+  if (a.sig.ws > 0) {
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned prev = atomicAdd(a.sig.counter, 1u);
+      if (prev == gridDim.x - 1) {
+        *a.sig.counter = 0;
+        __threadfence_system();
+        for (int q = 0; q < a.sig.ws; ++q) st_flag_sys(a.sig.peer_flags[q] + a.sig.rank, a.sig.epoch);
+      }
+    }
   }
 }
 
@@ -344,6 +390,7 @@ bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int
 }
 
 constexpr int WIN_THREADS = 1024;
+static int win_grid_override = 0;         // B200MPPI_WIN_GRID (tuning / test hook): number of persistent CTAs
 constexpr int WIN_MAX_SMEM = 232448;      // 227 KB: per-block opt-in limit on sm_100
 
 void rollout_win_geometry(int T, int* WW, int* WH, size_t* smem) {
@@ -375,10 +422,23 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
     }
   }
   if (a.WW != WIN_WW || (a.WH != 232 && a.WH != 224) || L.total > WIN_MAX_SMEM) return cudaErrorInvalidValue;
-  const int tiles = (a.p.N + WIN_THREADS - 1) / WIN_THREADS;
-  int ctas_per_map = (tiles + 1) / 2;                 // each CTA reuses its staged window for ~2 tiles of n
-  if (ctas_per_map < 1) ctas_per_map = 1;
-  const dim3 grid(ctas_per_map, a.p.M);
+  // persistent: one CTA per SM (1024 threads and 222 KB of shared memory fill an SM), never more CTAs than chunks
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  static int sm_count[64] = {};
+  if (dev >= 0 && dev < 64) {
+    if (!sm_count[dev]) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count[dev] > 0) sms = sm_count[dev];
+  }
+  static bool env_read = false;
+  if (!env_read) {
+    if (const char* e = getenv("B200MPPI_WIN_GRID")) win_grid_override = atoi(e);
+    env_read = true;
+  }
+  // every SM takes part as soon as there are 8 chunks (256 rollouts) for each; smaller problems use fewer CTAs
+  const long long total = (long long)a.p.M * (a.npad / 32);
+  const int ctas = (int)std::min<long long>(std::max<long long>(total / 8, 1), sms);
+  const dim3 grid(win_grid_override > 0 ? win_grid_override : ctas);
   const CUtensorMap& t0 = *reinterpret_cast<const CUtensorMap*>(tm_lin);
   const CUtensorMap& t1 = *reinterpret_cast<const CUtensorMap*>(tm_ang);
   const CUtensorMap& t2 = *reinterpret_cast<const CUtensorMap*>(tm_obs);

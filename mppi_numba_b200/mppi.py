@@ -77,7 +77,9 @@ class MPPI_Numba(object):
         self.u_prev_d = None
         self.init_device_vars_before_solving()
 
-    def _buffer(self, buf_id, shape, dtype, writable=True):
+    def _buffer(self, buf_id, shape, dtype, writable=True, raw_view=True):
+        """raw_view=False: no ``__cuda_array_interface__`` (the device layout differs from ``shape``: the per-(n,m)
+        costs are stored map-major, copy_to_host() returns the logical (n, m) array)."""
         h = self._handle
 
         def dev_ptr():
@@ -88,7 +90,7 @@ class MPPI_Numba(object):
             self, shape, dtype,
             lambda out: check(lib.b200mppi_planner_copy_out(h, buf_id, ptr(out), out.nbytes)),
             (lambda src: check(lib.b200mppi_planner_copy_in(h, buf_id, ptr(src), src.nbytes))) if writable else None,
-            dev_ptr=dev_ptr)
+            dev_ptr=dev_ptr if raw_view else None)
 
     def init_device_vars_before_solving(self):
         if self.device_var_initialized:
@@ -122,7 +124,7 @@ class MPPI_Numba(object):
         self.u_prev_d = self._u_prev_buf
         self.costs_d = self._buffer(_lib.BUF_COSTS, (self.n_reduce,), np.float32)
         self.weights_d = self._buffer(_lib.BUF_WEIGHTS, (self.n_reduce,), np.float32)
-        self.costs_nm_d = self._buffer(_lib.BUF_COSTS_NM, (self.n_local, M), np.float32)
+        self.costs_nm_d = self._buffer(_lib.BUF_COSTS_NM, (self.n_local, M), np.float32, raw_view=False)
         self.rng_states_d = self._buffer(_lib.BUF_RNG, (self.n_local * T, 2), np.uint64)
         self.partial_d = self._buffer(_lib.BUF_PARTIAL, (2 * T + 2,), np.float32, writable=False)
         self.state_rollout_batch_d = self._buffer(_lib.BUF_STATE_ROLLOUT,
@@ -260,7 +262,9 @@ class MPPI_Numba(object):
         self._partial_t = torch.as_tensor(self.partial_d, device=dev)          # zero-copy view
         self._gathered = torch.empty((self.world_size * (2 * self.num_steps + 2),), dtype=torch.float32, device=dev)
         if self.shard_maps:
-            self._costs_send = torch.as_tensor(self.costs_nm_d, device=dev).reshape(-1)   # (N, M/ws), zero-copy
+            # the device buffer itself: (ws, M/ws, N/ws) blocks by destination rank (include/b200mppi.h), zero-copy
+            raw = self._buffer(_lib.BUF_COSTS_NM, (self.n_local * self.m_local,), np.float32)
+            self._costs_send = torch.as_tensor(raw, device=dev)
             self._costs_recv = torch.empty_like(self._costs_send)                         # (ws, N/ws, M/ws)
 
     def _connect_peers(self):
@@ -311,7 +315,7 @@ class MPPI_Numba(object):
             for k in range(num_opt):
                 check(lib.b200mppi_planner_solve_local(self._handle, 1 if k == 0 else 0))
                 if self.shard_maps:
-                    # exchange 1: per-(n,m) costs, rank d receives rows [d*N/ws, (d+1)*N/ws) of every rank
+                    # exchange 1: per-(m,n) costs, equal contiguous blocks: rank d receives every rank's block d = its control sequences
                     dist.all_to_all_single(self._costs_recv, self._costs_send, group=self.process_group)
                     check(lib.b200mppi_planner_solve_reduce(self._handle, C.c_void_p(self._costs_recv.data_ptr())))
                 # exchange 2: the (2T+2)-float softmax partial of every rank

@@ -75,27 +75,31 @@ static void run(K kernel, int threads, unsigned blocks) {
 }
 }  // namespace b200
 
-// as launch_cvar (csrc/rollout.cu): which kernel, which PER, which grid
-extern "C" int emu_cvar(const float* costs_nm, float* costs, int N, int Mc, int chunks, float cvar_alpha) {
+// as launch_cvar (csrc/rollout.cu): which kernel, which PER, which grid.  costs_nm: the logical (N, M) array; the
+// kernels get the map-major (M, ld) device layout, ld >= N (a row stride larger than the row exercises `ld`).
+extern "C" int emu_cvar(const float* costs_nm, float* costs, int N, int M, int ld, float cvar_alpha) {
   using namespace b200;
-  const int M = Mc * chunks;
+  if (ld < N) return 2;
+  std::vector<float> mn((size_t)M * ld, 12345.0f);
+  for (int n = 0; n < N; ++n)
+    for (int m = 0; m < M; ++m) mn[(size_t)m * ld + n] = costs_nm[(size_t)n * M + m];
   int numel = (int)std::ceil((double)M * (double)cvar_alpha);
   if (numel < 1) numel = 1;
   if (numel > M) numel = M;
   if (M > 32 * CVAR_MAX_PER_LANE) {
     if (M > (1 << 15)) return 1;
-    run([&] { cvar_large_kernel(costs_nm, costs, N, Mc, chunks, numel); }, CVAR_LARGE_THREADS, (unsigned)N);
+    run([&] { cvar_large_kernel(mn.data(), costs, N, ld, M, numel); }, CVAR_LARGE_THREADS, (unsigned)N);
     return 0;
   }
-  const int threads = 128;
-  const unsigned blocks = (unsigned)((N + 3) / 4);
+  const int nb = cvar_block_n(M);
+  const unsigned blocks = (unsigned)((N + nb - 1) / nb);
   const int per = (M + 31) / 32;
-  if (per <= 1) run([&] { cvar_kernel<1>(costs_nm, costs, N, Mc, chunks, numel); }, threads, blocks);
-  else if (per <= 2) run([&] { cvar_kernel<2>(costs_nm, costs, N, Mc, chunks, numel); }, threads, blocks);
-  else if (per <= 4) run([&] { cvar_kernel<4>(costs_nm, costs, N, Mc, chunks, numel); }, threads, blocks);
-  else if (per <= 8) run([&] { cvar_kernel<8>(costs_nm, costs, N, Mc, chunks, numel); }, threads, blocks);
-  else if (per <= 16) run([&] { cvar_kernel<16>(costs_nm, costs, N, Mc, chunks, numel); }, threads, blocks);
-  else run([&] { cvar_kernel<32>(costs_nm, costs, N, Mc, chunks, numel); }, threads, blocks);
+  if (per <= 1) run([&] { cvar_kernel<1>(mn.data(), costs, N, ld, M, numel); }, CVAR_THREADS, blocks);
+  else if (per <= 2) run([&] { cvar_kernel<2>(mn.data(), costs, N, ld, M, numel); }, CVAR_THREADS, blocks);
+  else if (per <= 4) run([&] { cvar_kernel<4>(mn.data(), costs, N, ld, M, numel); }, CVAR_THREADS, blocks);
+  else if (per <= 8) run([&] { cvar_kernel<8>(mn.data(), costs, N, ld, M, numel); }, CVAR_THREADS, blocks);
+  else if (per <= 16) run([&] { cvar_kernel<16>(mn.data(), costs, N, ld, M, numel); }, CVAR_THREADS, blocks);
+  else run([&] { cvar_kernel<32>(mn.data(), costs, N, ld, M, numel); }, CVAR_THREADS, blocks);
   return 0;
 }
 '''

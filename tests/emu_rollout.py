@@ -95,14 +95,19 @@ extern "C" void emu_rollout(int mode, const float* f, const int* g, const double
   RolloutArgs a{};
   a.p = params(f, g, ratios);
   a.mode = mode; a.lin_grid = lin; a.ang_grid = ang; a.obstacle = obs; a.unknown = unk; a.risk = risk;
-  a.noise = noise; a.u_cur = u_cur; a.costs_nm = costs_nm; a.costs = costs; a.obstacles = obstacles;
+  a.noise = noise; a.u_cur = u_cur; a.costs = costs; a.obstacles = obstacles;
   a.num_obstacles = num_obstacles;
+  std::vector<float> mn((size_t)std::max(a.p.M, 1) * std::max(a.p.N, 1), 0.0f);      // map-major device layout (kernels.h, CostDst)
+  a.dst.base[0] = mn.data(); a.dst.n_per = std::max(a.p.N, 1); a.dst.ld = a.p.N; a.dst.row0 = 0;
   const int threads = 128;
   const unsigned gx = (unsigned)((a.p.N + threads - 1) / threads);
   if (mode == 3) run([&] { rollout_barebone_kernel(a); }, threads, gx, 1);
   else if (mode == 0) run([&] { rollout_kernel<0>(a); }, threads, gx, (unsigned)a.p.M);
   else if (mode == 1) run([&] { rollout_kernel<1>(a); }, threads, gx, 1);
   else run([&] { rollout_kernel<2>(a); }, threads, gx, 1);
+  if (mode == 0 && costs_nm)                                      // hand back the logical (N, M) array
+    for (int n = 0; n < a.p.N; ++n)
+      for (int m = 0; m < a.p.M; ++m) costs_nm[(size_t)n * a.p.M + m] = mn[(size_t)m * a.p.N + n];
 }
 
 extern "C" void emu_state_rollout(int mode, int V, const float* f, const int* g, const double* ratios, const int8_t* lin,
@@ -132,7 +137,7 @@ def build(out_dir):
     kernels = _region(os.path.join(CSRC, "rollout.cu"), "rollout") + _region(os.path.join(CSRC, "rollout.cu"), "vis")
     kernels = kernels.replace("extern __shared__ float s_u[];", "")          # the namespace-level s_u of the prelude
     src = (PRELUDE + _region(os.path.join(CSRC, "common.cuh"), "params") + cell +
-           _region(os.path.join(CSRC, "kernels.h"), "rollout_args") + _region(os.path.join(CSRC, "kernels.h"), "vis_args") +
+           _region(os.path.join(CSRC, "kernels.h"), "cost_dst") + _region(os.path.join(CSRC, "kernels.h"), "rollout_args") + _region(os.path.join(CSRC, "kernels.h"), "vis_args") +
            kernels + HARNESS)
     cpp = os.path.join(out_dir, "rollout_emu.cpp")
     so = os.path.join(out_dir, "librollout_emu.so")

@@ -43,16 +43,30 @@ static inline float __fadd_ru(float a, float b) {           // add.rp.f32, same 
 }
 static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 static inline unsigned atomicMax(unsigned* p, unsigned v) { const unsigned o = *p; if (v > o) *p = v; return o; }   // blocks run one by one
-static std::barrier<> g_w0(32);                             // the prepare kernel's warp 0 (its only shuffling warp)
-static float g_w0buf[32];
+struct EmuWarp { std::barrier<> bar{32}; float fbuf[32]; int ibuf[32]; };     // warp collectives: exchange between two warp barriers
+static EmuWarp g_warps[32];
 static inline float __shfl_xor_sync(unsigned, float v, int o) {
+  EmuWarp& w = g_warps[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
-  g_w0buf[lane] = v;
-  g_w0.arrive_and_wait();
-  const float r = g_w0buf[lane ^ o];
-  g_w0.arrive_and_wait();
+  w.fbuf[lane] = v;
+  w.bar.arrive_and_wait();
+  const float r = w.fbuf[lane ^ o];
+  w.bar.arrive_and_wait();
   return r;
 }
+static inline int __shfl_sync(unsigned, int v, int src) {
+  EmuWarp& w = g_warps[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  w.ibuf[lane] = v;
+  w.bar.arrive_and_wait();
+  const int r = w.ibuf[src];
+  w.bar.arrive_and_wait();
+  return r;
+}
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void st_flag_sys(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 #define __grid_constant__
 #define __align__(n)
 #undef __launch_bounds__
@@ -110,9 +124,14 @@ static RolloutParams params(const float* f, const int* g, const double* ratios) 
 
 // stage_rollout of csrc/api.cu for MODE_TDM: prepare kernel, window origin, launch geometry of launch_rollout_win.
 // shift_x / shift_y move the window away from the robot (cells) to force the global-memory path.
+// ctas: number of persistent CTAs (0: launch_rollout_win's own rule for a 148-SM device).
+// dst_blocks: 1 = one map-major (M, N) destination; ws > 1 = the sharded layout, ws separate (ws*M, N/ws) "receive
+// buffers" written at the rows of "rank" 1 (fill_cost_dst with direct = true) plus the epoch flags of CostSignal --
+// checked here; costs_nm always comes back as the logical (N, M) array.
 extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratios, const int8_t* lin, const int8_t* ang,
                                const int8_t* obs, const int8_t* unk, const float* noise, const float* u_cur,
-                               float* costs_nm, int shift_x, int shift_y, int* origin_out, float* reach_out) {
+                               float* costs_nm, int shift_x, int shift_y, int* origin_out, float* reach_out, int ctas,
+                               int dst_blocks) {
   using namespace b200;
   RolloutWinArgs w{};
   w.p = params(f, g, ratios);
@@ -134,17 +153,41 @@ extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratio
   w.wy0 = yi0 - WH / 2 + shift_y;
   w.npad = npad;
   w.lin_grid = lin; w.ang_grid = ang; w.obstacle = obs; w.unknown = unk;
-  w.noiseT = reinterpret_cast<const float*>(noiseT.data()); w.ctrl = ctrl.data(); w.u_cur = u_cur; w.costs_nm = costs_nm;
+  w.noiseT = reinterpret_cast<const float*>(noiseT.data()); w.ctrl = ctrl.data(); w.u_cur = u_cur;
+  const int ws = dst_blocks < 1 ? 1 : dst_blocks;
+  if (p.N % ws) return 4;
+  const int n_per = p.N / ws, rank = ws > 1 ? 1 : 0;
+  std::vector<std::vector<float>> recv(ws, std::vector<float>((size_t)ws * p.M * n_per, -1.0f));
+  std::vector<std::vector<uint32_t>> flags(ws, std::vector<uint32_t>(ws, 0u));
+  unsigned counter = 0;
+  w.dst.n_per = n_per; w.dst.ld = n_per; w.dst.row0 = rank * p.M;
+  for (int d = 0; d < ws; ++d) { w.dst.base[d] = recv[d].data(); w.sig.peer_flags[d] = flags[d].data(); }
+  w.sig.ws = ws > 1 ? ws : 0; w.sig.rank = rank; w.sig.counter = &counter; w.sig.epoch = 7u;
   if (origin_out) { origin_out[0] = w.wx0; origin_out[1] = w.wy0; }
   if (reach_out) *reach_out = reach;
   const CUtensorMap t_lin{(const unsigned char*)lin, p.g.grid_cols, p.g.grid_rows, p.M, p.g.grid_pitch, WW, WH};
   const CUtensorMap t_ang{(const unsigned char*)ang, p.g.grid_cols, p.g.grid_rows, p.M, p.g.grid_pitch, WW, WH};
   const CUtensorMap t_obs{(const unsigned char*)obs, p.g.cols, p.g.rows, 1, p.g.mask_pitch, WW, WH};
   const CUtensorMap t_unk{(const unsigned char*)unk, p.g.cols, p.g.rows, 1, p.g.mask_pitch, WW, WH};
-  const int tiles = (p.N + 1023) / 1024;
-  int ctas_per_map = (tiles + 1) / 2;
-  if (ctas_per_map < 1) ctas_per_map = 1;
-  run([&] { rollout_win_kernel<1024, 232>(w, t_lin, t_ang, t_obs, t_unk); }, 1024, (unsigned)ctas_per_map, (unsigned)p.M);
+  if (ctas <= 0) {                                            // launch_rollout_win (rollout_win.cu)
+    const long long total = (long long)p.M * (npad / 32);
+    ctas = (int)std::min<long long>(std::max<long long>(total / 8, 1), 148);
+  }
+  run([&] { rollout_win_kernel<1024, 232>(w, t_lin, t_ang, t_obs, t_unk); }, 1024, (unsigned)ctas, 1);
+  for (int n = 0; n < p.N; ++n)
+    for (int m = 0; m < p.M; ++m)
+      costs_nm[(size_t)n * p.M + m] = recv[n / n_per][((size_t)rank * p.M + m) * n_per + n % n_per];
+  if (ws > 1) {
+    if (counter != 0) return 5;
+    for (int d = 0; d < ws; ++d)
+      for (int r = 0; r < ws; ++r)
+        if (flags[d][r] != (r == rank ? 7u : 0u)) return 6;           // exactly this rank's flag, in every peer
+    for (int d = 0; d < ws; ++d)                                      // rows of the other "ranks" untouched
+      for (int r = 0; r < ws; ++r)
+        if (r != rank)
+          for (size_t i = 0; i < (size_t)p.M * n_per; ++i)
+            if (recv[d][(size_t)r * p.M * n_per + i] != -1.0f) return 7;
+  }
   return 0;
 }
 '''
@@ -162,7 +205,8 @@ def build(out_dir):
     kern = kern.replace("extern __shared__ __align__(128) unsigned char smem[];", "")
     prelude = ROLLOUT_PRELUDE.replace("float s_u[4096];", "")
     src = (prelude + EXTRA + _region(os.path.join(CSRC, "common.cuh"), "params") + cell +
-           _region(os.path.join(CSRC, "kernels.h"), "win_args") + prep + kern + HARNESS)
+           _region(os.path.join(CSRC, "kernels.h"), "cost_dst") + _region(os.path.join(CSRC, "kernels.h"), "win_args") +
+           prep + kern + HARNESS)
     cpp = os.path.join(out_dir, "rollout_win_emu.cpp")
     so = os.path.join(out_dir, "librollout_win_emu.so")
     open(cpp, "w").write(src)
@@ -172,5 +216,5 @@ def build(out_dir):
     lib = C.CDLL(so)
     P, I = C.c_void_p, C.c_int
     lib.emu_rollout_win.restype = I
-    lib.emu_rollout_win.argtypes = [P, P, P, P, P, P, P, P, P, P, I, I, P, P]
+    lib.emu_rollout_win.argtypes = [P, P, P, P, P, P, P, P, P, P, I, I, P, P, I, I]
     return lib

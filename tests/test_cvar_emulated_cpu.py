@@ -1,6 +1,6 @@
 """The CVaR kernels' real source (warp radix select for M <= 1024, CTA-wide select above), executed on the host
 by tests/emu_cvar.py, against the oracle's sort-based restatement of mppi.py:718-755: ties, negatives, all-equal
-rows, M not a multiple of 32, the alpha edge cases, the chunked layout of the sharded exchange."""
+rows, M not a multiple of 32, the alpha edge cases, the map-major layout with a row stride."""
 import ctypes as C
 
 import numpy as np
@@ -29,20 +29,19 @@ def test_cvar_kernel_source_matches_oracle(emu, M, alpha):
     c[5] = 7.0                                  # all equal
     c[6] = -np.abs(c[6])                        # all negative
     out = np.zeros(N, dtype=np.float32)
-    assert emu.emu_cvar(_ptr(c), _ptr(out), N, M, 1, np.float32(alpha)) == 0
+    assert emu.emu_cvar(_ptr(c), _ptr(out), N, M, N, np.float32(alpha)) == 0
     np.testing.assert_allclose(out, MR.cvar_reduce(c, alpha), rtol=2e-5, atol=2e-4)
 
 
-@pytest.mark.parametrize("M,ws", [(64, 4), (1536, 2)])
-def test_cvar_kernel_chunked_layout_of_the_sharded_exchange(emu, M, ws):
-    """After the all-to-all a rank holds (ws, N/ws, M/ws): chunk g = rank g's maps for this rank's control sequences."""
-    rng = np.random.default_rng(ws)
-    n_red, Mc = 6, M // ws
-    full = rng.normal(50, 20, (n_red, M)).astype(np.float32)
-    chunked = np.ascontiguousarray(full.reshape(n_red, ws, Mc).transpose(1, 0, 2))
-    out = np.zeros(n_red, dtype=np.float32)
-    assert emu.emu_cvar(_ptr(chunked), _ptr(out), n_red, Mc, ws, np.float32(0.3)) == 0
-    one = np.zeros(n_red, dtype=np.float32)
-    assert emu.emu_cvar(_ptr(full), _ptr(one), n_red, M, 1, np.float32(0.3)) == 0
-    assert (out == one).all()                   # same values per lane / slot: bit-identical to the unsharded layout
-    np.testing.assert_allclose(out, MR.cvar_reduce(full, 0.3), rtol=2e-5, atol=2e-4)
+@pytest.mark.parametrize("M,N,ld", [(64, 70, 96), (256, 33, 33), (1000, 19, 40), (1536, 3, 8)])
+def test_cvar_kernel_row_stride_and_ragged_blocks(emu, M, N, ld):
+    """Map-major input with a row stride larger than the row (the receive buffer of a sharded solve is (M, N/ws)
+    with ld = N/ws; a one-rank buffer has ld = N) and control-sequence counts that do not fill the last CTA: the
+    same values reach the same lanes, so the result does not depend on ld, and follows the oracle."""
+    rng = np.random.default_rng(M + N)
+    c = rng.normal(50, 20, (N, M)).astype(np.float32)
+    out, one = np.zeros(N, dtype=np.float32), np.zeros(N, dtype=np.float32)
+    assert emu.emu_cvar(_ptr(c), _ptr(out), N, M, ld, np.float32(0.3)) == 0
+    assert emu.emu_cvar(_ptr(c), _ptr(one), N, M, N, np.float32(0.3)) == 0
+    assert (out == one).all()
+    np.testing.assert_allclose(out, MR.cvar_reduce(c, 0.3), rtol=2e-5, atol=2e-4)

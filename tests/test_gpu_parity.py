@@ -560,7 +560,8 @@ def test_map_sharded_solve_equals_single_rank(eng):
         sends.append(pl.costs_nm_d.copy_to_host())
     parts, keep = [], []
     for d, (pl, lin, ang) in enumerate(ranks):
-        recv = np.ascontiguousarray(np.stack([sends[g][d * N // ws:(d + 1) * N // ws] for g in range(ws)]))
+        # what the all-to-all delivers: block g = rank g's maps x this rank's control sequences, map-major
+        recv = np.ascontiguousarray(np.stack([sends[g][d * N // ws:(d + 1) * N // ws].T for g in range(ws)]))
         t = torch.from_numpy(recv).cuda()
         keep.append(t)
         L.check(L.lib.b200mppi_planner_solve_reduce(pl._handle, C.c_void_p(t.data_ptr())))
