@@ -369,9 +369,7 @@ def time_small_workload(E, torch, name, local, steps, warmup):
     dev = torch.device("cuda", local)
     cfg, lin, ang, pl = make_planner(E, sc, local)
     stream = torch.cuda.Stream(device=dev)
-    check(lib.b200mppi_planner_set_stream(pl._handle, C.c_void_p(stream.cuda_stream)))
-    for t in (lin, ang):
-        check(lib.b200mppi_tdm_set_stream(t._handle, C.c_void_p(stream.cuda_stream)))
+    check(lib.b200mppi_planner_set_stream(pl._handle, C.c_void_p(stream.cuda_stream)))   # solve() samples on this stream too
     N, M, T = sc["N"], (sc["M"] if sc["mode"] == "tdm" else 1), sc["T"]
     for _ in range(max(warmup, 3) + 50):                         # small solves: ~0.1 ms each, warm the clocks too
         u = pl.solve()
@@ -448,9 +446,7 @@ def run_b200(args, sc):
     from mppi_numba_b200._lib import lib, check
     stream = torch.cuda.Stream(device=dev)
     if world == 1:
-        check(lib.b200mppi_planner_set_stream(pl._handle, C.c_void_p(stream.cuda_stream)))
-        for t in (lin, ang):
-            check(lib.b200mppi_tdm_set_stream(t._handle, C.c_void_p(stream.cuda_stream)))
+        check(lib.b200mppi_planner_set_stream(pl._handle, C.c_void_p(stream.cuda_stream)))   # solve() samples on this stream too
     else:
         pl._ensure_exchange()
         stream = pl._stream

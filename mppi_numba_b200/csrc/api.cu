@@ -834,6 +834,9 @@ extern "C" int b200mppi_planner_set_tdms(b200mppi_planner* p, b200mppi_tdm* lin,
     return fail(B200MPPI_EINVAL, "set_tdms: lin/ang allocation shapes differ");
   if (p->cfg.mode == B200MPPI_MODE_TDM && lin->num_maps < p->M)
     return fail(B200MPPI_EINVAL, "set_tdms: TDM holds fewer sampled maps than the planner's num_grid_samples");
+  if (p->shard_maps && (lin->cfg.rank != p->cfg.rank || lin->cfg.world_size != p->cfg.world_size ||
+                        ang->cfg.rank != p->cfg.rank || ang->cfg.world_size != p->cfg.world_size))
+    return fail(B200MPPI_EINVAL, "set_tdms: the TDMs' rank / world_size differ from the planner's (each rank samples its own maps)");
   p->lin = lin; p->ang = ang;
   return B200MPPI_OK;
 }
@@ -966,9 +969,15 @@ static int stage_rollout(b200mppi_planner* p) {
       const int yi0 = (int)std::floor(((double)p->prm.x0[1] - (double)l->pyl[0]) / (double)l->res);
       // TMA: the inner (x) start coordinate must be 16-byte aligned for 1-byte elements (probed on B200:
       // an unaligned c0 raises 'illegal instruction'); floor to a multiple of 16, also for negatives
-      const int cx = xi0 - WW / 2;
-      w.wx0 = (cx >= 0) ? (cx & ~15) : -(((-cx) + 15) & ~15);
-      w.wy0 = yi0 - WH / 2;
+      // The window is kept INSIDE the map (origin clamped, extents cut): a staged cell is then always a map cell, and
+      // every index outside the map takes the global-memory path with the generic kernel's wrap + clamp.
+      int cx = xi0 - WW / 2, cy = yi0 - WH / 2;
+      cx = std::max(0, std::min(cx, l->cols - WW));
+      cy = std::max(0, std::min(cy, l->rows - WH));
+      w.wx0 = cx & ~15;
+      w.wy0 = cy;
+      w.ww = std::min(WW, l->cols - w.wx0);
+      w.wh = std::min(WH, l->rows - w.wy0);
       w.npad = p->npad;
       w.lin_grid = l->grid; w.ang_grid = g->grid; w.obstacle = l->obstacle; w.unknown = l->unknown;
       w.noiseT = p->noiseT; w.ctrl = p->ctrl; w.u_cur = p->u_cur;

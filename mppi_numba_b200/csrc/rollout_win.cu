@@ -16,7 +16,9 @@
 //   * obstacle / unknown penalties are skipped when the mask byte is 0 (x + 0*c == x exactly);
 //   * the control-cost sum over T, identical for all M maps of a control sequence, is computed once
 //     per n by the prepare kernel (rounding differs from the reference's running sum by ~1 ulp).
-// A rollout that leaves the window reads the maps from global memory instead (same values).
+// A rollout that leaves the window reads the maps from global memory instead (same values); the window never
+// extends beyond the map, so out-of-map indices always take that path and wrap / clamp exactly like the generic
+// kernel (rollout.cu: wrap_clamp).
 #include <cuda.h>
 
 #include <algorithm>
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   int magic_wx = 0x4B400000 + a.wx0, magic_wy = 0x4B400000 + a.wy0;
   asm volatile("" : "+r"(magic_wx), "+r"(magic_wy));       // keep the folded constants (else re-derived per step)
   const float inv_lo = inv_res * (1.0f - 4.8e-7f), inv_hi = inv_res * (1.0f + 4.8e-7f);
+  const unsigned uww = (unsigned)a.ww, uwh = (unsigned)a.wh;     // staged AND inside the map (<= WW, WH)
 
   uint32_t phase = 0;
   for (long long w = w_lo; w < w_hi;) {
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       }
       // ---- traction / mask lookup: staged window, global memory only for rollouts that left it
       int ql, qa, ob, un;
-      if ((unsigned)wx < (unsigned)WW && (unsigned)wy < (unsigned)WH) {
+      if ((unsigned)wx < uww && (unsigned)wy < uwh) {
         const uint32_t ad = sb_win + (uint32_t)(wy * WW + wx);
         ql = lds_s8(ad, 0); qa = lds_s8(ad, PLANE); ob = lds_s8(ad, 2 * PLANE); un = lds_s8(ad, 3 * PLANE);
       } else {

@@ -252,9 +252,9 @@ class MPPI_Numba(object):
         assert dist.is_initialized(), "world_size > 1 needs an initialised torch.distributed process group"
         dev = torch.device("cuda", self.device)
         self._stream = torch.cuda.Stream(device=dev)
+        # only the planner works on the exchange stream: solve() samples the TDMs' maps on the PLANNER's stream;
+        # the TDMs keep their own streams for uploads and public sample_grids() calls (and may outlive the planner)
         check(lib.b200mppi_planner_set_stream(self._handle, C.c_void_p(self._stream.cuda_stream)))
-        for tdm in (self.lin_tdm, self.ang_tdm):
-            check(lib.b200mppi_tdm_set_stream(tdm._handle, C.c_void_p(self._stream.cuda_stream)))
         self._p2p = self._connect_peers()
         if self._p2p:
             self._gathered = True          # exchange buffers live inside the library

@@ -147,10 +147,14 @@ extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratio
   if (WH != 232) return 1;
   const int xi0 = (int)std::floor(((double)p.x0[0] - (double)p.g.xlo) / (double)p.g.res);
   const int yi0 = (int)std::floor(((double)p.x0[1] - (double)p.g.ylo) / (double)p.g.res);
-  const int cx = xi0 - WW / 2 + shift_x;
+  int cx = xi0 - WW / 2 + shift_x, cy = yi0 - WH / 2 + shift_y;
+  cx = std::max(0, std::min(cx, p.g.cols - WW));              // stage_rollout (api.cu): the window stays inside the map
+  cy = std::max(0, std::min(cy, p.g.rows - WH));
   w.WW = WW; w.WH = WH;
-  w.wx0 = (cx >= 0) ? (cx & ~15) : -(((-cx) + 15) & ~15);
-  w.wy0 = yi0 - WH / 2 + shift_y;
+  w.wx0 = cx & ~15;
+  w.wy0 = cy;
+  w.ww = std::min(WW, p.g.cols - w.wx0);
+  w.wh = std::min(WH, p.g.rows - w.wy0);
   w.npad = npad;
   w.lin_grid = lin; w.ang_grid = ang; w.obstacle = obs; w.unknown = unk;
   w.noiseT = reinterpret_cast<const float*>(noiseT.data()); w.ctrl = ctrl.data(); w.u_cur = u_cur;

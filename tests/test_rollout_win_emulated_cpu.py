@@ -49,11 +49,9 @@ def test_windowed_kernel_matches_reference_and_generic_kernel(emu, gname):
     inside, origin = run_win(0, 0)
     assert origin[0] % 16 == 0                                    # TMA: 16-byte aligned inner coordinate
     assert (np.abs(inside - ref) / np.maximum(np.abs(ref), 1e-6)).max() < 5e-6
-    outside, origin2 = run_win(4000, 4000)                        # window nowhere near the map: global-memory path
-    assert origin2[0] > Cc and origin2[1] > R
-    assert (outside == inside).all()                              # same numbers whatever the source of the bytes
-    partial, _ = run_win(123, 0)                                  # window covers only the left part of the map
-    assert (partial == inside).all()
+    shifted, origin2 = run_win(4000, -4000)                       # the window is clamped into the map (here: the whole map)
+    assert 0 <= origin2[0] <= max(Cc - 240, 0) and 0 <= origin2[1] <= max(R - 232, 0)
+    assert (shifted == inside).all()                              # same numbers wherever the window sits
     cnm, costs = np.zeros((N, M), F32), np.zeros(N, F32)
     gen.emu_rollout(0, _p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), None, _p(noise), _p(u_cur), _p(cnm),
                     _p(costs), None, 0)
@@ -145,7 +143,7 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
     from oracle import mppi_ref as MR
     win, gen = emu
     rng = np.random.default_rng(5)
-    N, M, T, R, Cc = 2100, 2, 40, 200, 200
+    N, M, T, R, Cc = 2100, 2, 40, 420, 400                  # larger than the 240 x 232 window
     res = F32(0.1)
     lin = rng.integers(0, 101, (M, R, Cc)).astype(np.int8)
     ang = rng.integers(0, 101, (M, R, Cc)).astype(np.int8)
@@ -153,8 +151,8 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
     unk = (rng.random((R, Cc)) < 0.02).astype(np.int8)
     noise = (rng.standard_normal((N, T, 2)) * [2, 3]).astype(F32)
     u_cur = np.stack([rng.uniform(0, 2, T), rng.uniform(-1, 1, T)], 1).astype(F32)
-    x0 = [10.03, 9.97, 0.7]
-    goal = [13.0, 12.0]                                      # within reach: some rollouts exit early
+    x0 = [20.03, 19.97, 0.7]
+    goal = [23.0, 22.0]                                      # within reach: some rollouts exit early
     f = _fparams(res, 0.0, 0.0, 0.1, x0, goal, 0.5, 0.01, 1.0, [2, 3], [0, 3], [-np.pi, np.pi], 1e5, 1e2, 1.0, 0.0, 0.0)
     ratios = _ratios([0, 1], [0, 1])
     geo = _c([R, Cc, R, Cc, Cc, Cc, T, N, M], np.int32)
@@ -175,3 +173,12 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
     r2 = np.abs(out - want) / np.maximum(np.abs(want), 1e-6)
     assert (r2 < 1e-4).mean() > 0.995 and np.median(r2) < 2e-6          # libm vs numpy sin/cos: a few cell flips at most
     assert (out < 0.5 * np.median(out)).any()                          # early exits happened
+    if ctas == 3:
+        # window pushed 110 cells right / 100 up: the robot sits near its edge, many lookups take the global-memory
+        # path (the generic kernel's wrap + clamp) -- same numbers whatever the source of the bytes
+        out2 = np.zeros((N, M), F32)
+        origin = np.zeros(2, np.int32)
+        assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur),
+                                   _p(out2), 110, 100, _p(origin), None, ctas, 1) == 0
+        assert origin[0] % 16 == 0 and origin[0] > 80 + 16 and origin[1] > 80
+        assert (out2 == out).all()
