@@ -639,6 +639,8 @@ struct b200mppi_planner {
   // own clipped controls (max_n sum_t |v|, reduced by the prepare kernel into reach_d and read back mid-solve)
   int box_mode = 2;
   float* reach_d = nullptr;
+  unsigned* upd_counter_d = nullptr;   // ticket counter of update_partial_kernel's last-CTA tail
+  bool bcast_done = false;             // this iteration's rank partial already went to the peers (update tail)
   bool prepared = false;         // noiseT / ctrl hold this iteration's controls
   bool pushed_direct = false;    // the last rollout kernel stored its costs straight into the peers (and signalled)
   int32_t last_box[5] = {};      // b200mppi_planner_sample_box
@@ -749,6 +751,8 @@ static int planner_init(b200mppi_planner* p, const b200mppi_config* cfg) {
   p->use_win = getenv("B200MPPI_NO_WINDOW") == nullptr;
   CU(cudaMalloc(&p->reach_d, 256));
   CU(cudaMemsetAsync(p->reach_d, 0, 256, p->stream));
+  CU(cudaMalloc(&p->upd_counter_d, 256));
+  CU(cudaMemsetAsync(p->upd_counter_d, 0, 256, p->stream));
   if (const char* e = getenv("B200MPPI_SAMPLE_BOX")) {
     if (!strcmp(e, "off") || !strcmp(e, "0")) p->box_mode = 0;
     else if (!strcmp(e, "static")) p->box_mode = 1;
@@ -806,7 +810,7 @@ extern "C" int b200mppi_planner_destroy(b200mppi_planner* p) {
   cudaFree(p->noise); cudaFree(p->u_cur); cudaFree(p->u_prev); cudaFree(p->costs); cudaFree(p->weights);
   cudaFree(p->w_raw); cudaFree(p->costs_nm); cudaFree(p->cta_partials); cudaFree(p->rank_partial);
   cudaFree(p->state_rollout); cudaFree(p->states); cudaFree(p->noiseT); cudaFree(p->ctrl); cudaFree(p->costs_x);
-  cudaFree(p->obstacles); cudaFree(p->reach_d);
+  cudaFree(p->obstacles); cudaFree(p->reach_d); cudaFree(p->upd_counter_d);
   for (int s = 0; s < P2P_MAX_PEERS; ++s)
     if (p->peer_ipc[s] && p->peer_x[s]) cudaIpcCloseMemHandle(p->peer_x[s]);
   cudaFree(p->xbuf);
@@ -1004,32 +1008,56 @@ static int stage_rollout(b200mppi_planner* p) {
   }
   if (p->profiling) cudaEventRecord(p->ev[3], p->stream);
   if (p->cfg.mode == B200MPPI_MODE_TDM && !p->shard_maps) {
-    launch_cvar(p->costs_nm, p->costs, p->n_local, p->n_local, p->M, p->prm.cvar_alpha, p->stream);
+    launch_cvar(p->costs_nm, p->costs, p->n_local, p->n_local, p->M, p->prm.cvar_alpha, FlagWait{}, p->stream);
     p->launches++;
     CHECK_LAUNCH();
   }
   return B200MPPI_OK;
 }
 
-static int stage_update_partial(b200mppi_planner* p, const float* costs) {
-  UpdateArgs u{};
-  fill_update_args(p, u, costs);
-  launch_update_partial(u, p->stream);
-  p->launches += 2;
-  CHECK_LAUNCH();
-  return B200MPPI_OK;
-}
-
-static int stage_update_finish(b200mppi_planner* p, const float* gathered, int count) {
-  UpdateArgs u{};
-  fill_update_args(p, u, nullptr);
-  launch_update_finish(u, gathered, count, p->stream);
+static int after_u_update(b200mppi_planner* p) {
   p->prepared = false;                        // u_cur moved
-  p->launches++;
-  CHECK_LAUNCH();
   if (p->cfg.mode != B200MPPI_MODE_TDM)   // self.u_prev_d = self.u_cur_d (alias, mppi.py:292,362)
     CU(cudaMemcpyAsync(p->u_prev, p->u_cur, (size_t)p->T * 2 * sizeof(float), cudaMemcpyDeviceToDevice, p->stream));
   return B200MPPI_OK;
+}
+
+// CTA partials of this rank's rollouts; the kernel's last CTA merges them into the rank partial and then
+//   UPD_TAIL_APPLY (one rank)      applies the update: the whole update is this one launch,
+//   UPD_TAIL_BCAST (peers connected) pushes the partial to every peer and raises the flags,
+//   UPD_TAIL_RANK                  leaves it in rank_partial for a staged (collective-library) all-gather.
+static int stage_update_partial(b200mppi_planner* p, int tail) {
+  UpdateArgs u{};
+  fill_update_args(p, u, nullptr);
+  UpdateTail tl{};
+  tl.counter = p->upd_counter_d;
+  tl.mode = tail;
+  p->bcast_done = false;
+  if (tail == UPD_TAIL_BCAST) {
+    const int ws = p->cfg.world_size;
+    tl.ws = ws; tl.rank = p->cfg.rank;
+    tl.epoch = ++p->epoch_part;
+    const size_t parity_off = (size_t)(tl.epoch & 1u) * ws * (2 * p->T + 2) * sizeof(float);
+    for (int s = 0; s < ws; ++s) {
+      tl.peer_gather[s] = (float*)(p->peer_x[s] + p->x_gather + parity_off);
+      tl.peer_flags[s] = (uint32_t*)(p->peer_x[s] + p->x_flags_part);
+    }
+    p->bcast_done = true;
+  }
+  launch_update_partial(u, tl, p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
+  if (tail == UPD_TAIL_APPLY) return after_u_update(p);
+  return B200MPPI_OK;
+}
+
+static int stage_update_finish(b200mppi_planner* p, const float* gathered, int count, const FlagWait& fw) {
+  UpdateArgs u{};
+  fill_update_args(p, u, nullptr);
+  launch_update_finish(u, gathered, count, fw, p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
+  return after_u_update(p);
 }
 
 extern "C" int b200mppi_planner_set_obstacles(b200mppi_planner* p, const float* xy, const float* rad, int32_t count) {
@@ -1145,8 +1173,7 @@ extern "C" int b200mppi_planner_solve(b200mppi_planner* p, float* u_out) {
   if (p->prm.num_opt <= 0 && (rc = stage_sample_tdms(p))) return rc;     // the reference samples before its loop
   for (int k = 0; k < p->prm.num_opt; ++k) {
     if ((rc = iteration_rollouts(p, k == 0))) return rc;
-    if ((rc = stage_update_partial(p, nullptr))) return rc;
-    if ((rc = stage_update_finish(p, p->rank_partial, 1))) return rc;
+    if ((rc = stage_update_partial(p, UPD_TAIL_APPLY))) return rc;
     if (p->profiling) cudaEventRecord(p->ev[5], p->stream);
   }
   CU(cudaMemcpyAsync(p->h_u, p->u_cur, (size_t)p->T * 2 * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
@@ -1163,8 +1190,8 @@ extern "C" int b200mppi_planner_solve_local(b200mppi_planner* p, int32_t first_i
   CU(cudaSetDevice(p->cfg.device));
   if (p->profiling && first_iteration) cudaEventRecord(p->ev[0], p->stream);
   if ((rc = iteration_rollouts(p, first_iteration != 0))) return rc;
-  if (p->shard_maps) return B200MPPI_OK;                     // costs_nm is the all-to-all send buffer
-  if ((rc = stage_update_partial(p, nullptr))) return rc;
+  if (p->shard_maps) return B200MPPI_OK;                     // the costs go through the all-to-all first
+  if ((rc = stage_update_partial(p, p->p2p_ready ? UPD_TAIL_BCAST : UPD_TAIL_RANK))) return rc;
   return B200MPPI_OK;
 }
 
@@ -1174,18 +1201,18 @@ extern "C" int b200mppi_planner_solve_reduce(b200mppi_planner* p, const float* e
   CU(cudaSetDevice(p->cfg.device));
   // exchanged_dev: (world_size, M_local, N/ws) -- block g holds rank g's maps for THIS rank's control sequences,
   // i.e. the map-major (M_total, N/ws) array of a one-rank solve restricted to them
-  launch_cvar(exchanged_dev, p->costs, p->n_red, p->n_red, p->M_total, p->prm.cvar_alpha, p->stream);
+  launch_cvar(exchanged_dev, p->costs, p->n_red, p->n_red, p->M_total, p->prm.cvar_alpha, FlagWait{}, p->stream);
   p->launches++;
   CHECK_LAUNCH();
   if (p->profiling) cudaEventRecord(p->ev[4], p->stream);
-  return stage_update_partial(p, nullptr);
+  return stage_update_partial(p, UPD_TAIL_RANK);
 }
 
 extern "C" int b200mppi_planner_solve_finish(b200mppi_planner* p, const float* gathered_dev, float* u_out) {
   if (!p || !gathered_dev) return fail(B200MPPI_EINVAL, "solve_finish: null argument");
   if (p->cfg.world_size > 512) return fail(B200MPPI_EINVAL, "solve_finish: world_size > 512");
   CU(cudaSetDevice(p->cfg.device));
-  int rc = stage_update_finish(p, gathered_dev, p->cfg.world_size);
+  int rc = stage_update_finish(p, gathered_dev, p->cfg.world_size, FlagWait{});
   if (rc) return rc;
   if (p->profiling) cudaEventRecord(p->ev[5], p->stream);
   if (u_out) {
@@ -1313,25 +1340,17 @@ extern "C" int b200mppi_planner_p2p_reduce(b200mppi_planner* p) {
   const int ws = p->cfg.world_size;
   int* status = (int*)(p->xbuf + p->x_status);
   if (p->shard_maps) {
-    launch_p2p_wait((const uint32_t*)(p->xbuf + p->x_flags_cost), ws, p->epoch_cost, p->p2p_timeout_ns, status, p->stream);
-    launch_cvar((const float*)p->xbuf, p->costs, p->n_red, p->n_red, p->M_total, p->prm.cvar_alpha, p->stream);
-    p->launches += 2;
+    // the CVaR kernel itself waits for every rank's cost flag, then reads the receive buffer: (M_total, N/ws), map-major
+    const FlagWait fw{(const uint32_t*)(p->xbuf + p->x_flags_cost), ws, p->epoch_cost, p->p2p_timeout_ns, status};
+    launch_cvar((const float*)p->xbuf, p->costs, p->n_red, p->n_red, p->M_total, p->prm.cvar_alpha, fw, p->stream);
+    p->launches++;
     CHECK_LAUNCH();
     if (p->profiling) cudaEventRecord(p->ev[4], p->stream);
-    if ((rc = stage_update_partial(p, nullptr))) return rc;
+    if ((rc = stage_update_partial(p, UPD_TAIL_BCAST))) return rc;     // partial -> every peer, by the kernel's last CTA
+  } else if (!p->bcast_done) {
+    // N-sharded modes: solve_local ran before the peers were connected -- redo the (cheap) partial with the broadcast tail
+    if ((rc = stage_update_partial(p, UPD_TAIL_BCAST))) return rc;
   }
-  P2PBcastArgs b{};
-  b.partial = p->rank_partial;
-  b.ws = ws; b.rank = p->cfg.rank; b.len = 2 * p->T + 2;
-  b.epoch = ++p->epoch_part;
-  const size_t parity_off = (size_t)(b.epoch & 1u) * ws * b.len * sizeof(float);
-  for (int s = 0; s < ws; ++s) {
-    b.peer_gather[s] = (float*)(p->peer_x[s] + p->x_gather + parity_off);
-    b.peer_flags[s] = (uint32_t*)(p->peer_x[s] + p->x_flags_part);
-  }
-  launch_p2p_bcast(b, p->stream);
-  p->launches++;
-  CHECK_LAUNCH();
   return B200MPPI_OK;
 }
 
@@ -1340,11 +1359,11 @@ extern "C" int b200mppi_planner_p2p_finish(b200mppi_planner* p, float* u_out) {
   if (rc) return rc;
   const int ws = p->cfg.world_size;
   int* status = (int*)(p->xbuf + p->x_status);
-  launch_p2p_wait((const uint32_t*)(p->xbuf + p->x_flags_part), ws, p->epoch_part, p->p2p_timeout_ns, status, p->stream);
-  p->launches++;
-  CHECK_LAUNCH();
+  // the apply kernel waits for every rank's partial flag itself
+  const FlagWait fw{(const uint32_t*)(p->xbuf + p->x_flags_part), ws, p->epoch_part, p->p2p_timeout_ns, status};
   const size_t parity_off = (size_t)(p->epoch_part & 1u) * ws * (2 * p->T + 2) * sizeof(float);
-  if ((rc = stage_update_finish(p, (const float*)(p->xbuf + p->x_gather + parity_off), ws))) return rc;
+  if ((rc = stage_update_finish(p, (const float*)(p->xbuf + p->x_gather + parity_off), ws, fw))) return rc;
+  p->bcast_done = false;
   if (p->profiling) cudaEventRecord(p->ev[5], p->stream);
   if (u_out) {
     int* h_status = (int*)(p->h_u + (size_t)p->T * 2);
@@ -1434,7 +1453,7 @@ extern "C" int b200mppi_planner_cvar(b200mppi_planner* p) {
   if (p->M > cvar_max_maps()) return fail(B200MPPI_EINVAL, "cvar: num_grid_samples exceeds the CVaR kernel's limit (16384)");
   CU(cudaSetDevice(p->cfg.device));
   if (p->shard_maps) return fail(B200MPPI_ESTATE, "cvar: maps are sharded, use solve_reduce");
-  launch_cvar(p->costs_nm, p->costs, p->n_local, p->n_local, p->M, p->prm.cvar_alpha, p->stream);
+  launch_cvar(p->costs_nm, p->costs, p->n_local, p->n_local, p->M, p->prm.cvar_alpha, FlagWait{}, p->stream);
   p->launches++;
   CHECK_LAUNCH();
   CU(cudaStreamSynchronize(p->stream));
@@ -1447,9 +1466,8 @@ extern "C" int b200mppi_planner_update(b200mppi_planner* p, const float* costs_h
   CU(cudaSetDevice(p->cfg.device));
   if (costs_host)
     CU(cudaMemcpyAsync(p->costs, costs_host, (size_t)p->n_red * sizeof(float), cudaMemcpyHostToDevice, p->stream));
-  int rc = stage_update_partial(p, nullptr);
+  int rc = stage_update_partial(p, p->cfg.world_size == 1 ? UPD_TAIL_APPLY : UPD_TAIL_RANK);
   if (rc) return rc;
-  if (p->cfg.world_size == 1 && (rc = stage_update_finish(p, p->rank_partial, 1))) return rc;
   CU(cudaStreamSynchronize(p->stream));
   return B200MPPI_OK;
 }

@@ -143,7 +143,9 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
 // of a map-sharded solve (rows g*M/ws .. = rank g's maps): the same kernel, the same values per lane, hence
 // bit-identical CVaR costs whatever the number of ranks.
 int cvar_max_maps();   // largest M the CVaR kernels accept
-void launch_cvar(const float* costs_mn, float* costs, int n_cnt, int ld, int M, float cvar_alpha, cudaStream_t st);
+// fw: flags to wait for before the costs are read (sharded solve, peer-memory exchange); FlagWait{} = none
+void launch_cvar(const float* costs_mn, float* costs, int n_cnt, int ld, int M, float cvar_alpha, const FlagWait& fw,
+                 cudaStream_t st);
 
 // update_useq_numba (mppi.py:1113-1191) as an online-softmax two-level reduction
 // [emu:begin update_args]
@@ -159,10 +161,22 @@ struct UpdateArgs {
   float lambda, vrange[2], wrange[2];
 };
 // [emu:end update_args]
+// what the LAST CTA of update_partial_kernel does once all CTA partials are written (reduce.cu)
+// [emu:begin update_tail]
+enum { UPD_TAIL_RANK = 0, UPD_TAIL_APPLY = 1, UPD_TAIL_BCAST = 2 };
+struct UpdateTail {
+  unsigned* counter;                    // ticket counter, zero between launches
+  int mode;
+  float* peer_gather[P2P_MAX_PEERS];    // UPD_TAIL_BCAST: peer d's gather buffer of this epoch's parity, (ws, 2T+2)
+  uint32_t* peer_flags[P2P_MAX_PEERS];  // peer d's partial flags [ws]
+  int ws, rank;
+  uint32_t epoch;
+};
+// [emu:end update_tail]
 int update_num_ctas(int N);
-void launch_update_partial(const UpdateArgs& a, cudaStream_t st);
+void launch_update_partial(const UpdateArgs& a, const UpdateTail& tl, cudaStream_t st);
 // combine `count` partials (each 2T+2 floats; this rank's own partial is entry `self`) into u and weights
-void launch_update_finish(const UpdateArgs& a, const float* gathered, int count, cudaStream_t st);
+void launch_update_finish(const UpdateArgs& a, const float* gathered, int count, const FlagWait& fw, cudaStream_t st);
 
 void launch_shift_u(float* u, int T, int shifts, cudaStream_t st);
 
@@ -187,17 +201,7 @@ struct P2PPushArgs {
   int ws, rank, n_red, Mc;
   uint32_t epoch;
 };
-struct P2PBcastArgs {
-  const float* partial;               // local (len)
-  float* peer_gather[P2P_MAX_PEERS];  // peer d's gather buffer of this epoch's parity, (ws, len)
-  uint32_t* peer_flags[P2P_MAX_PEERS];// peer d's partial flags [ws]
-  int ws, rank, len;
-  uint32_t epoch;
-};
 void launch_p2p_push(const P2PPushArgs& a, cudaStream_t st);
-void launch_p2p_bcast(const P2PBcastArgs& a, cudaStream_t st);
-void launch_p2p_wait(const uint32_t* flags, int ws, uint32_t epoch, unsigned long long timeout_ns, int* status,
-                     cudaStream_t st);
 
 // host: numba-compatible generator states (random.py:226-241)
 void create_xoroshiro_states(uint64_t* host_out, int64_t first, int64_t count, uint64_t seed);

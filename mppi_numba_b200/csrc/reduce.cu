@@ -69,12 +69,81 @@ int update_num_ctas(int N) {
   return ctas;
 }
 
+// merge `count` partials (beta, S, V[2T]) -> out (same layout).  One CTA.
+__device__ void merge_partials(const float* __restrict__ parts, int count, int T, float lambda,
+                               float* out_beta, float* out_S, float* s_scale /* smem[count] */) {
+  __shared__ float s_b;
+  float mn = INFINITY;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) mn = fminf(mn, __ldcg(parts + (size_t)i * (2 * T + 2)));
+  mn = warp_min(mn);
+  __shared__ float s_red[UPD_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = s_red[0];
+    for (int i = 1; i < UPD_THREADS / 32; ++i) v = fminf(v, s_red[i]);
+    s_b = v;
+  }
+  __syncthreads();
+  const float beta = s_b;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const float b = __ldcg(parts + (size_t)i * (2 * T + 2));
+    s_scale[i] = (b == INFINITY) ? 0.0f : softmax_weight(b, beta, lambda);
+  }
+  __syncthreads();
+  float S = 0.0f;                                   // block reduction in a fixed order (deterministic)
+  for (int i = threadIdx.x; i < count; i += blockDim.x) S = fmaf(__ldcg(parts + (size_t)i * (2 * T + 2) + 1), s_scale[i], S);
+  S = warp_sum(S);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = S;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int i = 0; i < UPD_THREADS / 32; ++i) t += s_red[i];
+    *out_beta = beta;
+    *out_S = t;
+  }
+  __syncthreads();
+}
+
+constexpr int MAX_PARTS = 512;
+
+// u_cur (clipped) from merged partials: u[j] <- clip(u[j] + (sum_i V_i[j] * scale_i) / W), and the normalised
+// weights of this rank's rollouts, weights[n] = w_raw[n] * exp(-(beta_cta - beta)/lambda) / W   (mppi.py:1173-1174).
+// `first` / `step`: the CTA's share of the weight slabs (the u update is done by the caller's CTA 0).
+__device__ void apply_update(const UpdateArgs& a, const float* __restrict__ parts, int count, const float* s_scale,
+                             float beta, float W, bool do_u, int first, int step) {
+  const int stride = 2 * a.T + 2;
+  if (do_u) {
+    for (int j = threadIdx.x; j < 2 * a.T; j += blockDim.x) {
+      float v = 0.0f;
+      for (int i = 0; i < count; ++i) v = fmaf(__ldcg(parts + (size_t)i * stride + 2 + j), s_scale[i], v);
+      float u = a.u_cur[j] + v / W;
+      const float lo = (j & 1) ? a.wrange[0] : a.vrange[0];
+      const float hi = (j & 1) ? a.wrange[1] : a.vrange[1];
+      a.u_cur[j] = fmaxf(lo, fminf(hi, u));
+    }
+  }
+  for (int c = first; c < a.num_ctas; c += step) {
+    const float bc = __ldcg(a.cta_partials + (size_t)c * stride);
+    const float sc = (bc == INFINITY) ? 0.0f : softmax_weight(bc, beta, a.lambda) / W;
+    const int r0 = c * a.rows_per_cta, r1 = min(r0 + a.rows_per_cta, a.N);
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) a.weights[r] = __ldcg(a.w_raw + r) * sc;
+  }
+}
+
 // grid = num_ctas; CTA c owns rows [c*rows_per_cta, ...).  Thread j owns float2 column j (one time
-// step) for j < T, looping if T > blockDim.
-__global__ void __launch_bounds__(UPD_THREADS) update_partial_kernel(const UpdateArgs a) {
+// step) for j < T, looping if T > blockDim.  The LAST CTA to finish (atomic ticket) merges the CTA partials into
+// this rank's partial (beta, S, V[2T]) -- in CTA order, so the result does not depend on which CTA is last -- and,
+// depending on `tail`:
+//   UPD_TAIL_RANK   stops there (the staged exchange gathers rank_partial with a collective),
+//   UPD_TAIL_APPLY  one rank: applies the update (u_cur, normalised weights) -- the whole update is ONE launch,
+//   UPD_TAIL_BCAST  stores the partial into slot `rank` of every peer's gather buffer and raises its epoch flag
+//                   (the all-gather of the peer-memory exchange, p2p.cu has the protocol).
+__global__ void __launch_bounds__(UPD_THREADS) update_partial_kernel(const UpdateArgs a, const UpdateTail tl) {
   __shared__ float s_red[UPD_THREADS / 32];
   __shared__ float s_w[64];
   __shared__ float s_beta;
+  __shared__ bool s_last;
   const int r0 = blockIdx.x * a.rows_per_cta;
   const int r1 = min(r0 + a.rows_per_cta, a.N);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -128,111 +197,70 @@ __global__ void __launch_bounds__(UPD_THREADS) update_partial_kernel(const Updat
     const int j = tid + k * UPD_THREADS;
     if (j < a.T) { part[2 + 2 * j] = acc[k].x; part[3 + 2 * j] = acc[k].y; }
   }
-}
 
-// merge `count` partials (beta, S, V[2T]) -> out (same layout).  One CTA.
-__device__ void merge_partials(const float* __restrict__ parts, int count, int T, float lambda,
-                               float* out_beta, float* out_S, float* s_scale /* smem[count] */) {
-  __shared__ float s_b;
-  float mn = INFINITY;
-  for (int i = threadIdx.x; i < count; i += blockDim.x) mn = fminf(mn, parts[(size_t)i * (2 * T + 2)]);
-  mn = warp_min(mn);
-  __shared__ float s_red[UPD_THREADS / 32];
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mn;
+  // ---- ticket: the last CTA of the grid carries on, the others are done
+  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float v = s_red[0];
-    for (int i = 1; i < UPD_THREADS / 32; ++i) v = fminf(v, s_red[i]);
-    s_b = v;
+  if (tid == 0) {
+    const unsigned prev = atomicAdd(tl.counter, 1u);
+    s_last = (prev == gridDim.x - 1);
+    if (s_last) *tl.counter = 0;
   }
   __syncthreads();
-  const float beta = s_b;
-  for (int i = threadIdx.x; i < count; i += blockDim.x) {
-    const float b = parts[(size_t)i * (2 * T + 2)];
-    s_scale[i] = (b == INFINITY) ? 0.0f : softmax_weight(b, beta, lambda);
-  }
-  __syncthreads();
-  float S = 0.0f;                                   // block reduction in a fixed order (deterministic)
-  for (int i = threadIdx.x; i < count; i += blockDim.x) S = fmaf(parts[(size_t)i * (2 * T + 2) + 1], s_scale[i], S);
-  S = warp_sum(S);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = S;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.0f;
-    for (int i = 0; i < UPD_THREADS / 32; ++i) t += s_red[i];
-    *out_beta = beta;
-    *out_S = t;
-  }
-  __syncthreads();
-}
+  if (!s_last) return;
+  __threadfence();
 
-constexpr int MAX_PARTS = 512;
-
-// CTA partials -> this rank's partial (rank_partial).  Grid = ceil(2T/32) CTAs: every CTA derives the merge
-// scales itself (<= 296 exps) and reduces 32 columns; 256 threads = 32 columns x 8 slices of the partials
-// (coalesced 128-byte rows), slices combined through shared memory.
-__global__ void __launch_bounds__(UPD_THREADS) update_rank_kernel(const UpdateArgs a) {
   __shared__ float s_scale[MAX_PARTS];
   __shared__ float s_bS[2];
-  __shared__ float s_acc[8][33];
   merge_partials(a.cta_partials, a.num_ctas, a.T, a.lambda, &s_bS[0], &s_bS[1], s_scale);
   const int stride = 2 * a.T + 2;
-  const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + col;
-  float v = 0.0f;
-  if (j < 2 * a.T)
-    for (int i = slice; i < a.num_ctas; i += 8) v = fmaf(a.cta_partials[(size_t)i * stride + 2 + j], s_scale[i], v);
-  s_acc[slice][col] = v;
-  __syncthreads();
-  if (slice == 0 && j < 2 * a.T) {
-    float t = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += s_acc[k][col];
-    a.rank_partial[2 + j] = t;
+  if (tl.mode == UPD_TAIL_APPLY) {                 // the rank partial would be the only one: apply straight away
+    apply_update(a, a.cta_partials, a.num_ctas, s_scale, s_bS[0], s_bS[1], true, 0, 1);
+    // rank_partial is still published (public buffer, tests); V is recomputed in the same order
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { a.rank_partial[0] = s_bS[0]; a.rank_partial[1] = s_bS[1]; }
-}
-
-// gathered rank partials -> u_cur (clipped), plus this rank's normalised weights
-// weights[n] = w_raw[n] * exp(-(beta_cta - beta)/lambda) / W         (mppi.py:1173-1174)
-__global__ void __launch_bounds__(UPD_THREADS) update_apply_kernel(const UpdateArgs a,
-                                                                   const float* __restrict__ gathered,
-                                                                   int count) {
-  __shared__ float s_scale[MAX_PARTS];
-  __shared__ float s_bS[2];
-  merge_partials(gathered, count, a.T, a.lambda, &s_bS[0], &s_bS[1], s_scale);
-  const float beta = s_bS[0], W = s_bS[1];
-  const int stride = 2 * a.T + 2;
-  if (blockIdx.x == 0) {
-    for (int j = threadIdx.x; j < 2 * a.T; j += blockDim.x) {
-      float v = 0.0f;
-      for (int i = 0; i < count; ++i) v = fmaf(gathered[(size_t)i * stride + 2 + j], s_scale[i], v);
-      float u = a.u_cur[j] + v / W;
-      const float lo = (j & 1) ? a.wrange[0] : a.vrange[0];
-      const float hi = (j & 1) ? a.wrange[1] : a.vrange[1];
-      a.u_cur[j] = fmaxf(lo, fminf(hi, u));
+  for (int j = tid; j < 2 * a.T; j += blockDim.x) {
+    float v = 0.0f;
+    for (int i = 0; i < a.num_ctas; ++i) v = fmaf(__ldcg(a.cta_partials + (size_t)i * stride + 2 + j), s_scale[i], v);
+    a.rank_partial[2 + j] = v;
+  }
+  if (tid == 0) { a.rank_partial[0] = s_bS[0]; a.rank_partial[1] = s_bS[1]; }
+  if (tl.mode == UPD_TAIL_BCAST) {
+    __syncthreads();                                // rank_partial complete (this CTA wrote all of it)
+    for (int q = 0; q < tl.ws; ++q) {
+      float* dst = tl.peer_gather[q] + (size_t)tl.rank * stride;
+      for (int j = tid; j < stride; j += blockDim.x) dst[j] = a.rank_partial[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < tl.ws) {
+      __threadfence_system();
+      st_flag_sys(tl.peer_flags[tid] + tl.rank, tl.epoch);
     }
   }
-  // normalised weights of this rank's rollouts, grid-stride over CTAs
-  for (int c = blockIdx.x; c < a.num_ctas; c += gridDim.x) {
-    const float bc = a.cta_partials[(size_t)c * stride];
-    const float sc = (bc == INFINITY) ? 0.0f : softmax_weight(bc, beta, a.lambda) / W;
-    const int r0 = c * a.rows_per_cta, r1 = min(r0 + a.rows_per_cta, a.N);
-    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) a.weights[r] = a.w_raw[r] * sc;
-  }
+}
+
+// gathered rank partials -> u_cur (clipped), plus this rank's normalised weights.  wait_flags != null: the partials
+// arrive through the peer-memory exchange -- every CTA first waits (bounded) until all ranks' epoch flags are up.
+__global__ void __launch_bounds__(UPD_THREADS) update_apply_kernel(const UpdateArgs a,
+                                                                   const float* __restrict__ gathered,
+                                                                   int count, const FlagWait fw) {
+  __shared__ float s_scale[MAX_PARTS];
+  __shared__ float s_bS[2];
+  flag_wait(fw);
+  merge_partials(gathered, count, a.T, a.lambda, &s_bS[0], &s_bS[1], s_scale);
+  apply_update(a, gathered, count, s_scale, s_bS[0], s_bS[1], blockIdx.x == 0, blockIdx.x, gridDim.x);
 }
 
 // [emu:end update]
 
-void launch_update_partial(const UpdateArgs& a, cudaStream_t st) {
-  update_partial_kernel<<<a.num_ctas, UPD_THREADS, 0, st>>>(a);
-  update_rank_kernel<<<(2 * a.T + 31) / 32, UPD_THREADS, 0, st>>>(a);
+void launch_update_partial(const UpdateArgs& a, const UpdateTail& tl, cudaStream_t st) {
+  update_partial_kernel<<<a.num_ctas, UPD_THREADS, 0, st>>>(a, tl);
 }
 
-void launch_update_finish(const UpdateArgs& a, const float* gathered, int count, cudaStream_t st) {
+void launch_update_finish(const UpdateArgs& a, const float* gathered, int count, const FlagWait& fw, cudaStream_t st) {
   int ctas = a.num_ctas < 32 ? a.num_ctas : 32;
   if (ctas < 1) ctas = 1;
-  update_apply_kernel<<<ctas, UPD_THREADS, 0, st>>>(a, gathered, count);
+  update_apply_kernel<<<ctas, UPD_THREADS, 0, st>>>(a, gathered, count, fw);
 }
 
 __global__ void shift_u_kernel(float* u, int T, int shifts) {

@@ -236,14 +236,16 @@ __host__ __device__ inline int cvar_block_n(int M) {
 // slot j / 32 of lane j % 32 whatever the number of ranks the maps came from.
 template <int PER>
 __global__ void __launch_bounds__(CVAR_THREADS) cvar_kernel(const float* __restrict__ costs_mn,
-                                                            float* __restrict__ costs, int n_cnt, int ld, int M, int numel) {
+                                                            float* __restrict__ costs, int n_cnt, int ld, int M, int numel,
+                                                            const FlagWait fw) {
   __shared__ float s_tile[CVAR_TILE_FLOATS];
+  flag_wait(fw);                                              // sharded solve: the peers' costs have arrived
   const int NB = cvar_block_n(M);
   const int n0 = blockIdx.x * NB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int idx = tid; idx < M * NB; idx += CVAR_THREADS) {
     const int m = idx / NB, j = idx - m * NB;
-    s_tile[j * (M + 1) + m] = (n0 + j < n_cnt) ? costs_mn[(size_t)m * ld + n0 + j] : 0.0f;
+    s_tile[j * (M + 1) + m] = (n0 + j < n_cnt) ? __ldcg(costs_mn + (size_t)m * ld + n0 + j) : 0.0f;
   }
   __syncthreads();
   for (int j = warp; j < NB; j += CVAR_THREADS / 32) {
@@ -294,12 +296,13 @@ constexpr int CVAR_LARGE_THREADS = 256;
 
 __global__ void __launch_bounds__(CVAR_LARGE_THREADS) cvar_large_kernel(const float* __restrict__ costs_mn,
                                                                         float* __restrict__ costs, int n_cnt, int ld,
-                                                                        int M, int numel) {
+                                                                        int M, int numel, const FlagWait fw) {
   extern __shared__ uint32_t s_keys[];
+  flag_wait(fw);
   __shared__ int s_cnt[2][CVAR_LARGE_THREADS / 32];
   __shared__ float s_sum[CVAR_LARGE_THREADS / 32];
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int j = tid; j < M; j += CVAR_LARGE_THREADS) s_keys[j] = float_key(costs_mn[(size_t)j * ld + n]);
+  for (int j = tid; j < M; j += CVAR_LARGE_THREADS) s_keys[j] = float_key(__ldcg(costs_mn + (size_t)j * ld + n));
   __syncthreads();
   uint32_t prefix = 0;
   int greater_total = 0;
@@ -339,7 +342,8 @@ __global__ void __launch_bounds__(CVAR_LARGE_THREADS) cvar_large_kernel(const fl
 // [emu:end cvar]
 int cvar_max_maps() { return CVAR_LARGE_MAX_MAPS; }
 
-void launch_cvar(const float* costs_mn, float* costs, int n_cnt, int ld, int M, float cvar_alpha, cudaStream_t st) {
+void launch_cvar(const float* costs_mn, float* costs, int n_cnt, int ld, int M, float cvar_alpha, const FlagWait& fw,
+                 cudaStream_t st) {
   int numel = (int)ceil((double)M * (double)cvar_alpha);    // mppi.py:744 (float32 alpha, f64 product)
   if (numel < 1) numel = 1;
   if (numel > M) numel = M;
@@ -347,18 +351,18 @@ void launch_cvar(const float* costs_mn, float* costs, int n_cnt, int ld, int M, 
     const size_t smem = (size_t)M * sizeof(uint32_t);
     cudaFuncSetAttribute(cvar_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,   // per device
                          CVAR_LARGE_MAX_MAPS * (int)sizeof(uint32_t));
-    cvar_large_kernel<<<(unsigned)n_cnt, CVAR_LARGE_THREADS, smem, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
+    cvar_large_kernel<<<(unsigned)n_cnt, CVAR_LARGE_THREADS, smem, st>>>(costs_mn, costs, n_cnt, ld, M, numel, fw);
     return;
   }
   const int nb = cvar_block_n(M);
   const unsigned blocks = (unsigned)((n_cnt + nb - 1) / nb);
   const int per = (M + 31) / 32;
-  if (per <= 1) cvar_kernel<1><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
-  else if (per <= 2) cvar_kernel<2><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
-  else if (per <= 4) cvar_kernel<4><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
-  else if (per <= 8) cvar_kernel<8><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
-  else if (per <= 16) cvar_kernel<16><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
-  else cvar_kernel<32><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel);
+  if (per <= 1) cvar_kernel<1><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel, fw);
+  else if (per <= 2) cvar_kernel<2><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel, fw);
+  else if (per <= 4) cvar_kernel<4><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel, fw);
+  else if (per <= 8) cvar_kernel<8><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel, fw);
+  else if (per <= 16) cvar_kernel<16><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel, fw);
+  else cvar_kernel<32><<<blocks, CVAR_THREADS, 0, st>>>(costs_mn, costs, n_cnt, ld, M, numel, fw);
 }
 
 // ---------------------------------------------------------------------------------------------

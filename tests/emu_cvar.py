@@ -53,6 +53,9 @@ static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 namespace b200 {
 uint32_t s_keys[1 << 15];
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+struct FlagWait { const uint32_t* flags; int ws; uint32_t epoch; unsigned long long timeout_ns; int* status; };
+static inline void flag_wait(const FlagWait&) {}
 '''
 
 HARNESS = r'''
@@ -88,18 +91,18 @@ extern "C" int emu_cvar(const float* costs_nm, float* costs, int N, int M, int l
   if (numel > M) numel = M;
   if (M > 32 * CVAR_MAX_PER_LANE) {
     if (M > (1 << 15)) return 1;
-    run([&] { cvar_large_kernel(mn.data(), costs, N, ld, M, numel); }, CVAR_LARGE_THREADS, (unsigned)N);
+    run([&] { cvar_large_kernel(mn.data(), costs, N, ld, M, numel, FlagWait{}); }, CVAR_LARGE_THREADS, (unsigned)N);
     return 0;
   }
   const int nb = cvar_block_n(M);
   const unsigned blocks = (unsigned)((N + nb - 1) / nb);
   const int per = (M + 31) / 32;
-  if (per <= 1) run([&] { cvar_kernel<1>(mn.data(), costs, N, ld, M, numel); }, CVAR_THREADS, blocks);
-  else if (per <= 2) run([&] { cvar_kernel<2>(mn.data(), costs, N, ld, M, numel); }, CVAR_THREADS, blocks);
-  else if (per <= 4) run([&] { cvar_kernel<4>(mn.data(), costs, N, ld, M, numel); }, CVAR_THREADS, blocks);
-  else if (per <= 8) run([&] { cvar_kernel<8>(mn.data(), costs, N, ld, M, numel); }, CVAR_THREADS, blocks);
-  else if (per <= 16) run([&] { cvar_kernel<16>(mn.data(), costs, N, ld, M, numel); }, CVAR_THREADS, blocks);
-  else run([&] { cvar_kernel<32>(mn.data(), costs, N, ld, M, numel); }, CVAR_THREADS, blocks);
+  if (per <= 1) run([&] { cvar_kernel<1>(mn.data(), costs, N, ld, M, numel, FlagWait{}); }, CVAR_THREADS, blocks);
+  else if (per <= 2) run([&] { cvar_kernel<2>(mn.data(), costs, N, ld, M, numel, FlagWait{}); }, CVAR_THREADS, blocks);
+  else if (per <= 4) run([&] { cvar_kernel<4>(mn.data(), costs, N, ld, M, numel, FlagWait{}); }, CVAR_THREADS, blocks);
+  else if (per <= 8) run([&] { cvar_kernel<8>(mn.data(), costs, N, ld, M, numel, FlagWait{}); }, CVAR_THREADS, blocks);
+  else if (per <= 16) run([&] { cvar_kernel<16>(mn.data(), costs, N, ld, M, numel, FlagWait{}); }, CVAR_THREADS, blocks);
+  else run([&] { cvar_kernel<32>(mn.data(), costs, N, ld, M, numel, FlagWait{}); }, CVAR_THREADS, blocks);
   return 0;
 }
 '''

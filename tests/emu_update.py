@@ -41,6 +41,13 @@ static inline float __shfl_xor_sync(unsigned, float v, int o) {
   return r;
 }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void st_flag_sys(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+struct FlagWait { const uint32_t* flags; int ws; uint32_t epoch; unsigned long long timeout_ns; int* status; };
+static inline void flag_wait(const FlagWait&) {}          // blocks run one after the other: nothing to wait for
 static inline float __double2float_rn(double d) { return (float)d; }
 struct float2 { float x, y; };
 using std::min;
@@ -87,14 +94,47 @@ extern "C" int emu_update_num_ctas(int N) {
   return b200::make(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, N, 1, 1.0f, z, z).num_ctas;
 }
 
-// launch_update_partial: CTA partials + this rank's partial (2T+2 floats)
+// launch_update_partial with UPD_TAIL_RANK: CTA partials + (last CTA) this rank's partial (2T+2 floats)
 extern "C" void emu_update_partial(const float* costs, const float* noise, float* w_raw, float* cta_partials,
                                    float* rank_partial, int N, int T, float lambda) {
   using namespace b200;
   float z[2] = {0, 0};
   const UpdateArgs a = make(costs, noise, w_raw, cta_partials, rank_partial, nullptr, nullptr, N, T, lambda, z, z);
-  run([&] { update_partial_kernel(a); }, UPD_THREADS, (unsigned)a.num_ctas);
-  run([&] { update_rank_kernel(a); }, UPD_THREADS, (unsigned)((2 * T + 31) / 32));
+  unsigned counter = 0;
+  UpdateTail tl{};
+  tl.counter = &counter; tl.mode = UPD_TAIL_RANK;
+  run([&] { update_partial_kernel(a, tl); }, UPD_THREADS, (unsigned)a.num_ctas);
+}
+
+// UPD_TAIL_APPLY: the whole one-rank update in ONE launch (partials, merge and apply by the last CTA)
+extern "C" int emu_update_one_rank(const float* costs, const float* noise, float* w_raw, float* cta_partials,
+                                   float* rank_partial, float* u_cur, float* weights, int N, int T, float lambda,
+                                   const float* vr, const float* wr) {
+  using namespace b200;
+  const UpdateArgs a = make(costs, noise, w_raw, cta_partials, rank_partial, u_cur, weights, N, T, lambda, vr, wr);
+  unsigned counter = 0;
+  UpdateTail tl{};
+  tl.counter = &counter; tl.mode = UPD_TAIL_APPLY;
+  run([&] { update_partial_kernel(a, tl); }, UPD_THREADS, (unsigned)a.num_ctas);
+  return counter == 0 ? 0 : 1;                    // the ticket counter is left at zero for the next launch
+}
+
+// UPD_TAIL_BCAST: the rank partial goes into slot `rank` of every peer's gather buffer (ws, 2T+2), flags raised
+extern "C" int emu_update_bcast(const float* costs, const float* noise, float* w_raw, float* cta_partials,
+                                float* rank_partial, int N, int T, float lambda, int ws, int rank, float* gather_all,
+                                uint32_t* flags_all, uint32_t epoch) {
+  using namespace b200;
+  float z[2] = {0, 0};
+  const UpdateArgs a = make(costs, noise, w_raw, cta_partials, rank_partial, nullptr, nullptr, N, T, lambda, z, z);
+  unsigned counter = 0;
+  UpdateTail tl{};
+  tl.counter = &counter; tl.mode = UPD_TAIL_BCAST; tl.ws = ws; tl.rank = rank; tl.epoch = epoch;
+  for (int q = 0; q < ws; ++q) {
+    tl.peer_gather[q] = gather_all + (size_t)q * ws * (2 * T + 2);
+    tl.peer_flags[q] = flags_all + (size_t)q * ws;
+  }
+  run([&] { update_partial_kernel(a, tl); }, UPD_THREADS, (unsigned)a.num_ctas);
+  return counter == 0 ? 0 : 1;
 }
 
 // launch_update_finish: combine `count` gathered rank partials into u_cur and this rank's normalised weights
@@ -106,7 +146,7 @@ extern "C" void emu_update_finish(const float* gathered, int count, const float*
                             weights, N, T, lambda, vr, wr);
   int ctas = a.num_ctas < 32 ? a.num_ctas : 32;
   if (ctas < 1) ctas = 1;
-  run([&] { update_apply_kernel(a, gathered, count); }, UPD_THREADS, (unsigned)ctas);
+  run([&] { update_apply_kernel(a, gathered, count, FlagWait{}); }, UPD_THREADS, (unsigned)ctas);
 }
 '''
 
@@ -122,7 +162,8 @@ def build(out_dir):
     kernels = _region(os.path.join(CSRC, "reduce.cu"), "update")
     kernels = re.sub(r"(?m)^(\s*)__shared__ ", r"\1static ", kernels)      # block-shared arrays: one instance
     kernels = kernels.replace("int update_num_ctas(int N) {", "static int update_num_ctas_unused(int N) {")
-    src = (PRELUDE + _region(os.path.join(CSRC, "kernels.h"), "update_args") +
+    src = (PRELUDE + "constexpr int P2P_MAX_PEERS = 16;\n" + _region(os.path.join(CSRC, "kernels.h"), "update_args") +
+           _region(os.path.join(CSRC, "kernels.h"), "update_tail") +
            _region(os.path.join(CSRC, "common.cuh"), "warp_min") + _region(os.path.join(CSRC, "common.cuh"), "warp_sum") +
            kernels + HARNESS)
     cpp = os.path.join(out_dir, "update_emu.cpp")
@@ -137,6 +178,10 @@ def build(out_dir):
     lib.emu_update_num_ctas.argtypes = [I]
     lib.emu_update_partial.restype = None
     lib.emu_update_partial.argtypes = [P, P, P, P, P, I, I, F]
+    lib.emu_update_one_rank.restype = I
+    lib.emu_update_one_rank.argtypes = [P, P, P, P, P, P, P, I, I, F, P, P]
+    lib.emu_update_bcast.restype = I
+    lib.emu_update_bcast.argtypes = [P, P, P, P, P, I, I, F, I, I, P, P, C.c_uint32]
     lib.emu_update_finish.restype = None
     lib.emu_update_finish.argtypes = [P, I, P, P, P, P, I, I, F, P, P]
     return lib

@@ -88,3 +88,52 @@ def test_sharded_update_equals_single_rank(emu):
         np.testing.assert_allclose(u, u1, rtol=1e-5, atol=2e-6)
         ws_w.append(w)
     np.testing.assert_allclose(np.concatenate(ws_w), w1, rtol=1e-4, atol=1e-12)
+
+
+@pytest.mark.parametrize("N,T", [(1000, 50), (8192, 128), (37, 3)])
+def test_one_launch_update_equals_partial_plus_finish(emu, N, T):
+    """One rank: the last CTA of update_partial_kernel applies the update itself (UPD_TAIL_APPLY) -- bit-identical to
+    the two-step path (rank partial, then update_apply_kernel on that single partial), and it follows the oracle."""
+    rng = np.random.default_rng(N * 7 + T)
+    costs = rng.uniform(900, 930, N).astype(np.float32)
+    noise = (rng.standard_normal((N, T, 2)) * [2, 3]).astype(np.float32)
+    u0 = np.stack([rng.uniform(0, 2.9, T), rng.uniform(-3, 3, T)], 1).astype(np.float32)
+    w_raw, parts, rank = _partial(emu, costs, noise, 1.0)
+    u2, w2 = _finish(emu, rank[None, :], w_raw, parts, u0, N, T, 1.0)
+    ctas = emu.emu_update_num_ctas(N)
+    w_raw1, parts1, rank1 = np.zeros(N, np.float32), np.zeros((ctas, 2 * T + 2), np.float32), np.zeros(2 * T + 2, np.float32)
+    u1, w1 = u0.copy(), np.zeros(N, np.float32)
+    assert emu.emu_update_one_rank(_p(costs), _p(noise), _p(w_raw1), _p(parts1), _p(rank1), _p(u1), _p(w1), N, T,
+                                   np.float32(1.0), _p(VR), _p(WR)) == 0
+    assert (u1 == u2).all() and (w1 == w2).all() and (rank1 == rank).all()
+    want_u, _ = MR.update_useq(1.0, costs, noise, VR, WR, u0)
+    np.testing.assert_allclose(u1, want_u, rtol=1e-5, atol=3e-6)
+
+
+def test_update_tail_broadcasts_the_rank_partial_to_every_peer(emu):
+    """UPD_TAIL_BCAST (peer-memory exchange): 3 'ranks', each stores its partial into slot `rank` of all three
+    gather buffers and raises its own epoch flag in every peer -- the gather buffers end up identical and equal to
+    the stacked rank partials; combining them gives the one-rank update."""
+    N, T, ws = 1536, 32, 3
+    rng = np.random.default_rng(11)
+    costs = rng.uniform(900, 930, N).astype(np.float32)
+    noise = (rng.standard_normal((N, T, 2)) * [2, 3]).astype(np.float32)
+    u0 = rng.uniform(0, 1, (T, 2)).astype(np.float32)
+    gather = np.zeros((ws, ws, 2 * T + 2), np.float32)
+    flags = np.zeros((ws, ws), np.uint32)
+    shards = []
+    for r in range(ws):
+        sl = slice(N * r // ws, N * (r + 1) // ws)
+        n = N // ws
+        ctas = emu.emu_update_num_ctas(n)
+        w_raw, parts, rank = np.zeros(n, np.float32), np.zeros((ctas, 2 * T + 2), np.float32), np.zeros(2 * T + 2, np.float32)
+        assert emu.emu_update_bcast(_p(np.ascontiguousarray(costs[sl])), _p(np.ascontiguousarray(noise[sl])), _p(w_raw),
+                                    _p(parts), _p(rank), n, T, np.float32(1.0), ws, r, _p(gather), _p(flags), 5) == 0
+        shards.append((w_raw, parts, rank))
+    assert (flags == 5).all()
+    for q in range(ws):
+        assert (gather[q] == np.stack([s[2] for s in shards])).all()
+    w_raw, parts, rank = _partial(emu, costs, noise, 1.0)
+    u1, _ = _finish(emu, rank[None, :], w_raw, parts, u0, N, T, 1.0)
+    u, _ = _finish(emu, gather[0], shards[0][0], shards[0][1], u0, N // ws, T, 1.0)
+    np.testing.assert_allclose(u, u1, rtol=1e-5, atol=2e-6)
