@@ -170,6 +170,34 @@ static __device__ __noinline__ float add_penalties(float cost, int ob, int un, f
   return ffma((float)un, unk_cost, cost);
 }
 
+// everything that is not "cell proven by the magic-number floors and staged in the window" (~0.1 % of the steps near
+// cell edges, plus the steps of rollouts that left the window): exact reference cell index, then the staged window
+// if the cell is in it, else global memory with the generic kernel's wrap + clamp.  Out of line: one call site, one
+// reconvergence region in the hot loop.
+static __device__ __noinline__ int lookup_slow(float ax, float ay, float res, uint32_t sb_win, unsigned uww, unsigned uwh,
+                                               int WW, int PLANE, int wx0, int wy0, int rows, int cols, int grid_rows,
+                                               int grid_cols, int grid_pitch, int mask_pitch,
+                                               const int8_t* __restrict__ g_lin, const int8_t* __restrict__ g_ang,
+                                               const int8_t* __restrict__ obstacle, const int8_t* __restrict__ unknown) {
+  const int xi = cell_index_exact(ax, res), yi = cell_index_exact(ay, res);
+  const int wx = xi - wx0, wy = yi - wy0;
+  int ql, qa, ob, un;
+  if ((unsigned)wx < uww && (unsigned)wy < uwh) {
+    const uint32_t ad = sb_win + (uint32_t)(wy * WW + wx);
+    ql = lds_s8(ad, 0); qa = lds_s8(ad + PLANE, 0); ob = lds_s8(ad + 2 * PLANE, 0); un = lds_s8(ad + 3 * PLANE, 0);
+  } else {
+    const int gy2 = min(max(yi < 0 ? yi + grid_rows : yi, 0), grid_rows - 1);
+    const int gx2 = min(max(xi < 0 ? xi + grid_cols : xi, 0), grid_cols - 1);
+    const int my = min(max(yi < 0 ? yi + rows : yi, 0), rows - 1);
+    const int mx = min(max(xi < 0 ? xi + cols : xi, 0), cols - 1);
+    ql = __ldg(g_lin + (size_t)gy2 * grid_pitch + gx2);
+    qa = __ldg(g_ang + (size_t)gy2 * grid_pitch + gx2);
+    ob = __ldg(obstacle + (size_t)my * mask_pitch + mx);
+    un = __ldg(unknown + (size_t)my * mask_pitch + mx);
+  }
+  return (ql & 0xff) | ((qa & 0xff) << 8) | ((ob & 0xff) << 16) | (un << 24);     // four int8 in one register
+}
+
 struct WinSmem {                 // dynamic shared memory carve-up (all offsets multiples of 128)
   int plane;                     // bytes per plane = WW*WH
   int off_lut, off_u, off_bar, total;
@@ -194,7 +222,7 @@ constexpr int WIN_WW = 240;       // window width in cells (inner TMA box extent
 // CTA stages that map's window once (thread 0 issues the TMA loads after the CTA has left the previous window), then
 // its warps pull chunks from a shared-memory counter until the map's part of the share is done -- warps whose
 // rollouts reached the goal early simply take the next chunk.
-template <int THREADS, int WH>
+template <int THREADS, int WH, int XR>
 __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWinArgs a,
                                                                  const __grid_constant__ CUtensorMap tm_lin,
                                                                  const __grid_constant__ CUtensorMap tm_ang,
@@ -291,25 +319,19 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const float ky = __fadd_rd(fmaf(ay, inv_lo, -1e-30f), MAGIC), ky2 = __fadd_rd(fmaf(ay, inv_hi, 1e-30f), MAGIC);
       // window-relative cell straight from the magic-number sums (bits(k) - bits(MAGIC) = floor)
       int wx = __float_as_int(kx) - magic_wx, wy = __float_as_int(ky) - magic_wy;
-      if ((__float_as_int(kx) != __float_as_int(kx2)) | (__float_as_int(ky) != __float_as_int(ky2))) {
-        wx = cell_index_exact(ax, res) - a.wx0;             // an integer may lie inside the interval: exact sequence
-        wy = cell_index_exact(ay, res) - a.wy0;
-      }
-      // ---- traction / mask lookup: staged window, global memory only for rollouts that left it
+      // ---- traction / mask lookup.  ONE rare region for everything that is not "cell proven and staged": an
+      //      integer may lie inside one of the intervals (run the exact reference sequence), or the cell lies outside
+      //      the staged window (read global memory; out-of-map indices wrap + clamp like the generic kernel)
       int ql, qa, ob, un;
-      if ((unsigned)wx < uww && (unsigned)wy < uwh) {
+      const bool fast = (__float_as_int(kx) == __float_as_int(kx2)) & (__float_as_int(ky) == __float_as_int(ky2)) &
+                        ((unsigned)wx < uww) & ((unsigned)wy < uwh);
+      if (__builtin_expect(fast, 1)) {
         const uint32_t ad = sb_win + (uint32_t)(wy * WW + wx);
         ql = lds_s8(ad, 0); qa = lds_s8(ad, PLANE); ob = lds_s8(ad, 2 * PLANE); un = lds_s8(ad, 3 * PLANE);
       } else {
-        const int xi = wx + a.wx0, yi = wy + a.wy0;
-        const int gy2 = min(max(yi < 0 ? yi + p.g.grid_rows : yi, 0), p.g.grid_rows - 1);
-        const int gx2 = min(max(xi < 0 ? xi + p.g.grid_cols : xi, 0), p.g.grid_cols - 1);
-        const int my = min(max(yi < 0 ? yi + p.g.rows : yi, 0), p.g.rows - 1);
-        const int mx = min(max(xi < 0 ? xi + p.g.cols : xi, 0), p.g.cols - 1);
-        ql = __ldg(g_lin + (size_t)gy2 * p.g.grid_pitch + gx2);
-        qa = __ldg(g_ang + (size_t)gy2 * p.g.grid_pitch + gx2);
-        ob = __ldg(a.obstacle + (size_t)my * p.g.mask_pitch + mx);
-        un = __ldg(a.unknown + (size_t)my * p.g.mask_pitch + mx);
+        const int pk = lookup_slow(ax, ay, res, sb_win, uww, uwh, WW, PLANE, a.wx0, a.wy0, p.g.rows, p.g.cols, p.g.grid_rows,
+                                   p.g.grid_cols, p.g.grid_pitch, p.g.mask_pitch, g_lin, g_ang, a.obstacle, a.unknown);
+        ql = (int)(int8_t)pk; qa = (int)(int8_t)(pk >> 8); ob = (int)(int8_t)(pk >> 16); un = pk >> 24;
       }
       // ---- noisy clipped control (mppi.py:686-689): `c2`, precomputed per (n, t) by the prepare kernel
       // ---- unicycle step (mppi.py:692-694): float64 FMA, one rounding to float32 per component.  The
@@ -324,7 +346,11 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       // cell lookup of the next one (~70 instructions per warp, 32 warps per SM) cover the L2 latency
       if (t + 1 < Tn) c2 = __ldg(ep);
       x = narrow(rx); y = narrow(ry); th = narrow(rt);
-      x64 = round_to_f32_precision(rx); y64 = round_to_f32_precision(ry); th64 = round_to_f32_precision(rt);
+      // float64 copies of the rounded state: XR of the three through the XU pipe (a second conversion, widen(narrow(.))),
+      // the others on the integer pipe -- the same values either way; the split balances issue slots against XU cycles
+      x64 = (XR >= 3) ? widen(x) : round_to_f32_precision(rx);
+      y64 = (XR >= 2) ? widen(y) : round_to_f32_precision(ry);
+      th64 = (XR >= 1) ? widen(th) : round_to_f32_precision(rt);
       // ---- stage cost (mppi.py:696-701)
       const float dx = fsub(gx, x), dy = fsub(gy, y);
       d2 = ffma(dx, dx, fmul(dy, dy));
@@ -393,6 +419,7 @@ bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int
 }
 
 constexpr int WIN_THREADS = 1024;
+constexpr int WIN_XR_DEFAULT = 0;         // measured on B200: see profiles/ (B200MPPI_WIN_XR sweeps it)
 static int win_grid_override = 0;         // B200MPPI_WIN_GRID (tuning / test hook): number of persistent CTAs
 constexpr int WIN_MAX_SMEM = 232448;      // 227 KB: per-block opt-in limit on sm_100
 
@@ -409,18 +436,30 @@ int rollout_win_threads() { return WIN_THREADS; }
 cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, const void* tm_ang, const void* tm_obs,
                                const void* tm_unk, cudaStream_t st) {
   const WinSmem L = win_smem_layout(a.WW, a.WH, a.p.T);
+  static int xr = WIN_XR_DEFAULT;
+  static bool xr_read = false;
+  if (!xr_read) {
+    if (const char* e = getenv("B200MPPI_WIN_XR")) xr = atoi(e);     // A/B hook: 0..3 state copies rounded on the XU pipe
+    if (xr < 0 || xr > 3) xr = WIN_XR_DEFAULT;
+    xr_read = true;
+  }
+  typedef void (*WinKernel)(const RolloutWinArgs, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap);
+  static const WinKernel kernels[2][4] = {
+      {rollout_win_kernel<WIN_THREADS, 232, 0>, rollout_win_kernel<WIN_THREADS, 232, 1>,
+       rollout_win_kernel<WIN_THREADS, 232, 2>, rollout_win_kernel<WIN_THREADS, 232, 3>},
+      {rollout_win_kernel<WIN_THREADS, 224, 0>, rollout_win_kernel<WIN_THREADS, 224, 1>,
+       rollout_win_kernel<WIN_THREADS, 224, 2>, rollout_win_kernel<WIN_THREADS, 224, 3>}};
   {
     // the opt-in is per device (per-context function): a process may run planners on several GPUs
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(rollout_win_kernel<WIN_THREADS, 232>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_MAX_SMEM);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(rollout_win_kernel<WIN_THREADS, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 WIN_MAX_SMEM);
-      if (e != cudaSuccess) return e;
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 4; ++j) {
+          const cudaError_t e = cudaFuncSetAttribute(kernels[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_MAX_SMEM);
+          if (e != cudaSuccess) return e;
+        }
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
@@ -446,8 +485,7 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
   const CUtensorMap& t1 = *reinterpret_cast<const CUtensorMap*>(tm_ang);
   const CUtensorMap& t2 = *reinterpret_cast<const CUtensorMap*>(tm_obs);
   const CUtensorMap& t3 = *reinterpret_cast<const CUtensorMap*>(tm_unk);
-  if (a.WH == 232) rollout_win_kernel<WIN_THREADS, 232><<<grid, WIN_THREADS, L.total, st>>>(a, t0, t1, t2, t3);
-  else rollout_win_kernel<WIN_THREADS, 224><<<grid, WIN_THREADS, L.total, st>>>(a, t0, t1, t2, t3);
+  kernels[a.WH == 232 ? 0 : 1][xr]<<<grid, WIN_THREADS, L.total, st>>>(a, t0, t1, t2, t3);
   return cudaGetLastError();
 }
 

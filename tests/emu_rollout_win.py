@@ -177,7 +177,7 @@ extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratio
     const long long total = (long long)p.M * (npad / 32);
     ctas = (int)std::min<long long>(std::max<long long>(total / 8, 1), 148);
   }
-  run([&] { rollout_win_kernel<1024, 232>(w, t_lin, t_ang, t_obs, t_unk); }, 1024, (unsigned)ctas, 1);
+  run([&] { rollout_win_kernel<1024, 232, 0>(w, t_lin, t_ang, t_obs, t_unk); }, 1024, (unsigned)ctas, 1);
   for (int n = 0; n < p.N; ++n)
     for (int m = 0; m < p.M; ++m)
       costs_nm[(size_t)n * p.M + m] = recv[n / n_per][((size_t)rank * p.M + m) * n_per + n % n_per];
