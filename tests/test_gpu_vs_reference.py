@@ -59,6 +59,7 @@ def ref():
 @pytest.mark.parametrize("mode,N,M,T,H,res,B,det_alpha", [
     ("tdm", 1024, 64, 64, 512, 0.1, 12, 1.0),        # BASELINE config 3
     ("det", 4096, 1, 128, 512, 0.2, 32, 0.3),        # BASELINE config 4
+    ("tdm", 8192, 256, 128, 1024, 0.1, 12, 1.0),     # BASELINE config 5, the headline workload, full size
     ("tdm", 128, 1100, 32, 128, 0.1, 12, 1.0),       # M > 1024: rollout_oversized_numba, cvar_alpha = 1 (its
                                                      # "sort" for alpha < 1 swaps unconditionally)
 ])
