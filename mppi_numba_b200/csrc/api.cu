@@ -638,7 +638,9 @@ struct b200mppi_planner {
   // reach-box sampling: 0 = whole maps every solve, 1 = box from the speed limit, 2 = box from this solve's
   // own clipped controls (max_n sum_t |v|, reduced by the prepare kernel into reach_d and read back mid-solve)
   int box_mode = 2;
-  float* reach_d = nullptr;
+  float* reach_d = nullptr;            // two slots, used alternately (noise_prepare_kernel)
+  int reach_slot = 0;
+  bool reach_valid = false;            // reach_d[reach_slot] holds this iteration's statistic
   unsigned* upd_counter_d = nullptr;   // ticket counter of update_partial_kernel's last-CTA tail
   bool bcast_done = false;             // this iteration's rank partial already went to the peers (update tail)
   bool prepared = false;         // noiseT / ctrl hold this iteration's controls
@@ -893,17 +895,21 @@ static bool planner_uses_window(const b200mppi_planner* p) {
 // control noise, and (windowed stochastic rollouts) the transposed clipped controls + per-n control cost + the
 // reach statistic max_n sum_t |v| of this iteration
 static int stage_noise(b200mppi_planner* p) {
-  launch_sample_noise(p->states, p->noise, p->n_local, p->T, p->prm.u_std[0], p->prm.u_std[1], p->reach_d, p->stream);
-  p->launches++;
-  CHECK_LAUNCH();
   p->prepared = false;
-  if (planner_uses_window(p)) {
-    launch_prepare_rollout(p->noise, p->u_cur, p->noiseT, p->ctrl, p->reach_d, p->n_local, p->T, p->npad,
-                           p->prm.lambda_weight, p->prm.u_std[0], p->prm.u_std[1], p->prm.vrange, p->prm.wrange, p->stream);
+  if (planner_uses_window(p)) {             // ONE launch: noise in both layouts, control costs, reach statistic
+    p->reach_slot ^= 1;
+    launch_noise_prepare(p->states, p->noise, p->u_cur, p->noiseT, p->ctrl, p->reach_d, p->reach_slot, p->n_local, p->T,
+                         p->npad, p->prm.lambda_weight, p->prm.u_std[0], p->prm.u_std[1], p->prm.vrange, p->prm.wrange,
+                         p->stream);
     p->launches++;
     CHECK_LAUNCH();
     p->prepared = true;
+    p->reach_valid = true;
+    return B200MPPI_OK;
   }
+  launch_sample_noise(p->states, p->noise, p->n_local, p->T, p->prm.u_std[0], p->prm.u_std[1], nullptr, p->stream);
+  p->launches++;
+  CHECK_LAUNCH();
   return B200MPPI_OK;
 }
 
@@ -960,7 +966,7 @@ static int stage_rollout(b200mppi_planner* p) {
     const b200mppi_tdm* l = p->lin; const b200mppi_tdm* g = p->ang;
     if (planner_tensor_maps(p, WW, WH)) {
       if (!p->prepared) {                       // noise came from outside (set_noise): derive the controls now
-        launch_prepare_rollout(p->noise, p->u_cur, p->noiseT, p->ctrl, p->reach_d, p->n_local, p->T, p->npad,
+        launch_prepare_rollout(p->noise, p->u_cur, p->noiseT, p->ctrl, nullptr, p->n_local, p->T, p->npad,
                                p->prm.lambda_weight, p->prm.u_std[0], p->prm.u_std[1], p->prm.vrange, p->prm.wrange, p->stream);
         p->launches++;
         CHECK_LAUNCH();
@@ -1091,9 +1097,9 @@ static bool planner_reach_box(b200mppi_planner* p, SampleBox* box, int* how, int
   const b200mppi_tdm* l = p->lin;
   const b200mppi_params& q = p->prm;
   double S = (double)p->T * std::fmax(std::fabs((double)q.vrange[0]), std::fabs((double)q.vrange[1]));
-  if (p->box_mode == 2 && q.num_opt == 1 && p->prepared) {
+  if (p->box_mode == 2 && q.num_opt == 1 && p->prepared && p->reach_valid) {
     float* h = p->h_u + (size_t)p->T * 2 + 2;
-    if (cudaMemcpyAsync(h, p->reach_d, sizeof(float), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
+    if (cudaMemcpyAsync(h, p->reach_d + p->reach_slot, sizeof(float), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
         cudaStreamSynchronize(p->stream) != cudaSuccess) {
       *err = fail(B200MPPI_ECUDA, std::string("reach read-back: ") + cudaGetErrorString(cudaGetLastError()));
       return false;

@@ -133,6 +133,11 @@ struct RolloutWinArgs {
 void launch_prepare_rollout(const float* noise, const float* u_cur, float* noiseT, float* ctrl, float* reach, int N,
                             int T, int npad, float lambda, float std_v, float std_w, const float vrange[2],
                             const float wrange[2], cudaStream_t st);
+// sample_noise + prepare_rollout in one launch (solve(), windowed stochastic rollouts); reach[2]: slot is max-reduced
+// into, slot ^ 1 cleared for the next launch
+void launch_noise_prepare(uint64_t* states, float* noise, const float* u_cur, float* noiseT, float* ctrl, float* reach,
+                          int slot, int N, int T, int npad, float lambda, float std_v, float std_w, const float vrange[2],
+                          const float wrange[2], cudaStream_t st);
 bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int rows, int maps, int pitch,
                         int WW, int WH);
 void rollout_win_geometry(int T, int* WW, int* WH, size_t* smem);

@@ -17,12 +17,7 @@ namespace b200 {
 // jitted without the kernel's fastmath flag) and sqrt.approx.ftz (module-wide NVVM option) --
 // SURVEY.md 2.3; logf/cosf below are the same libdevice routines.
 // [emu:begin noise]   (tests/emu_noise.py compiles the text between these markers for the host)
-__device__ __forceinline__ float xoro_normal(Xoro& s) {
-  const float u1 = xoro_unit_f32(xoro_next(s));
-  const float u2 = xoro_unit_f32(xoro_next(s));
-  const float two_pi = 6.283185307179586f;
-  return fmul(sqrt_approx(fmul(-2.0f, logf(u1))), cosf(fmul(two_pi, u2)));
-}
+// xoro_normal: common.cuh (shared with the fused noise + controls kernel of rollout_win.cu)
 
 // one thread per generator g = n*T + t (mppi.py:1367); generator and noise accesses are both
 // contiguous in g, so loads/stores are fully coalesced 16 B / 8 B per lane.

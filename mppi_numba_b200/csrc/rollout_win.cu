@@ -90,6 +90,86 @@ __global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __re
 }
 
 // [emu:end prepare]
+
+// ---------------------------------------------------------------------------------------------
+// noise + prepare in ONE launch (what solve() runs): the control noise of sample_noise_numba (mppi.py:1354-1370;
+// generator n*T + t, Box-Muller, states advanced in place) is written once in the reference's (N, T, 2) layout for the
+// update kernel and the public noise_samples_d -- and, from the same registers, through the shared-memory transpose
+// of the prepare kernel above, as the clipped float64 controls [T][npad] the rollout kernel streams, with the per-n
+// control cost and the reach statistic.  Same arithmetic, same order as the two separate kernels (bit-identical
+// outputs: tests/test_rollout_win_emulated_cpu.py).
+// `reach` has two slots used alternately by consecutive launches: this launch max-reduces into reach[slot] and clears
+// reach[slot ^ 1] for the next one (the host has read it: solve() synchronises on it).
+// [emu:begin noise_prepare]
+__global__ void __launch_bounds__(256) noise_prepare_kernel(uint64_t* __restrict__ states, float2* __restrict__ noise,
+                                                            const float* __restrict__ u_cur, double2* __restrict__ noiseT,
+                                                            float* __restrict__ ctrl, float* __restrict__ reach, int slot,
+                                                            int N, int T, int npad, float std_v, float std_w, float lambda,
+                                                            float sv2, float sw2, float v_lo, float v_hi, float w_lo,
+                                                            float w_hi) {
+  __shared__ float2 tile[32][33];
+  const int n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  if (blockIdx.x == 0 && threadIdx.x == 0 && reach) reach[slot ^ 1] = 0.0f;
+  float acc = 0.0f, vsum = 0.0f;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    for (int r = ty; r < 32; r += 8) {                         // rows = n, cols = t: generators contiguous along t
+      const int n = n0 + r, t = t0 + tx;
+      float2 e = make_float2(0.f, 0.f);
+      if (n < N && t < T) {
+        const size_t g = (size_t)n * T + t;
+        ulonglong2* sp = reinterpret_cast<ulonglong2*>(states) + g;
+        const ulonglong2 raw = *sp;
+        Xoro s{raw.x, raw.y};
+        e.x = fmul(std_v, xoro_normal(s));
+        e.y = fmul(std_w, xoro_normal(s));
+        noise[g] = e;
+        *sp = make_ulonglong2(s.s0, s.s1);
+      }
+      tile[r][tx] = e;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {                         // rows = t, cols = n  (coalesced along n)
+      const int t = t0 + r;
+      if (t < T) {
+        const float2 e = tile[tx][r];
+        double2 c;
+        c.x = f2d(fmaxf(v_lo, fminf(v_hi, fadd(u_cur[2 * t], e.x))));
+        c.y = f2d(fmaxf(w_lo, fminf(w_hi, fadd(u_cur[2 * t + 1], e.y))));
+        noiseT[(size_t)t * npad + n0 + tx] = c;
+      }
+    }
+    if (ty == 0) {                                             // lane tx owns rollout n0+tx
+      const int tend = min(32, T - t0);
+      for (int j = 0; j < tend; ++j) {
+        const float2 e = tile[tx][j];
+        const float a = div_approx(u_cur[2 * (t0 + j)], sv2);
+        const float b = div_approx(u_cur[2 * (t0 + j) + 1], sw2);
+        acc = ffma(ffma(a, e.x, fmul(b, e.y)), lambda, acc);
+        vsum = __fadd_ru(vsum, fabsf(fmaxf(v_lo, fminf(v_hi, fadd(u_cur[2 * (t0 + j)], e.x)))));
+      }
+    }
+    __syncthreads();
+  }
+  if (ty == 0) {
+    if (n0 + tx < N) ctrl[n0 + tx] = acc; else vsum = 0.0f;
+    if (reach) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) vsum = fmaxf(vsum, __shfl_xor_sync(0xffffffffu, vsum, o));
+      if (tx == 0) atomicMax(reinterpret_cast<unsigned int*>(reach + slot), __float_as_uint(vsum));
+    }
+  }
+}
+
+// [emu:end noise_prepare]
+void launch_noise_prepare(uint64_t* states, float* noise, const float* u_cur, float* noiseT, float* ctrl, float* reach,
+                          int slot, int N, int T, int npad, float lambda, float std_v, float std_w, const float vrange[2],
+                          const float wrange[2], cudaStream_t st) {
+  noise_prepare_kernel<<<npad / 32, 256, 0, st>>>(states, reinterpret_cast<float2*>(noise), u_cur,
+                                                 reinterpret_cast<double2*>(noiseT), ctrl, reach, slot, N, T, npad, std_v,
+                                                 std_w, lambda, std_v * std_v, std_w * std_w, vrange[0], vrange[1],
+                                                 wrange[0], wrange[1]);
+}
 void launch_prepare_rollout(const float* noise, const float* u_cur, float* noiseT, float* ctrl, float* reach, int N,
                             int T, int npad, float lambda, float std_v, float std_w, const float vrange[2],
                             const float wrange[2], cudaStream_t st) {

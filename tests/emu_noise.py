@@ -42,7 +42,7 @@ extern "C" void emu_sample_noise(uint64_t* states, float* noise, long long count
 
 
 def build(out_dir):
-    src = PRELUDE + _region(os.path.join(CSRC, "common.cuh"), "xoro") + _region(os.path.join(CSRC, "reduce.cu"), "noise") + HARNESS
+    src = PRELUDE + _region(os.path.join(CSRC, "common.cuh"), "xoro") + _region(os.path.join(CSRC, "common.cuh"), "normal") + _region(os.path.join(CSRC, "reduce.cu"), "noise") + HARNESS
     cpp, so = os.path.join(out_dir, "noise_emu.cpp"), os.path.join(out_dir, "libnoise_emu.so")
     open(cpp, "w").write(src)
     r = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", cpp, "-o", so],

@@ -67,6 +67,9 @@ static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __A
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void st_flag_sys(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+struct ulonglong2 { unsigned long long x, y; };
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
+static inline float xoro_unit_f32(uint64_t x) { return (float)((double)(x >> 11) * (1.0 / 9007199254740992.0)); }
 #define __grid_constant__
 #define __align__(n)
 #undef __launch_bounds__
@@ -124,6 +127,51 @@ static RolloutParams params(const float* f, const int* g, const double* ratios) 
 
 // stage_rollout of csrc/api.cu for MODE_TDM: prepare kernel, window origin, launch geometry of launch_rollout_win.
 // shift_x / shift_y move the window away from the robot (cells) to force the global-memory path.
+// The fused noise + controls kernel (launch_noise_prepare) next to the two kernels it replaces (sample_noise_kernel
+// is restated here as its one-line body: generator g -> (std_v * normal, std_w * normal), tests/emu_noise.py runs the
+// real one): states, noise, transposed controls, control costs and the reach statistic must agree bit for bit.
+extern "C" int emu_noise_prepare(const uint64_t* states_in, const float* u_cur, int N, int T, float std_v, float std_w,
+                                 float lambda, const float* vr, const float* wr, uint64_t* states_out, float* noise_out,
+                                 double* noiseT_out, float* ctrl_out, float* reach_out) {
+  using namespace b200;
+  const int npad = (N + 31) / 32 * 32;
+  std::vector<uint64_t> st((size_t)N * T * 2);
+  std::memcpy(st.data(), states_in, st.size() * 8);
+  std::vector<float> noise((size_t)N * T * 2, 0.0f), ctrl(npad, 0.0f);
+  std::vector<double2> noiseT((size_t)T * npad, double2{0, 0});
+  float reach[2] = {0.0f, 123.0f};
+  run([&] { noise_prepare_kernel(st.data(), reinterpret_cast<float2*>(noise.data()), u_cur, noiseT.data(), ctrl.data(), reach, 0,
+                                 N, T, npad, std_v, std_w, lambda, std_v * std_v, std_w * std_w, vr[0], vr[1], wr[0], wr[1]); },
+      256, (unsigned)(npad / 32), 1);
+  if (reach[1] != 0.0f) return 1;                                  // the other slot is cleared for the next launch
+  // the two separate kernels
+  std::vector<uint64_t> st2((size_t)N * T * 2);
+  std::memcpy(st2.data(), states_in, st2.size() * 8);
+  std::vector<float> noise2((size_t)N * T * 2, 0.0f), ctrl2(npad, 0.0f);
+  std::vector<double2> noiseT2((size_t)T * npad, double2{0, 0});
+  for (size_t g = 0; g < (size_t)N * T; ++g) {
+    Xoro s{st2[2 * g], st2[2 * g + 1]};
+    noise2[2 * g] = fmul(std_v, xoro_normal(s));
+    noise2[2 * g + 1] = fmul(std_w, xoro_normal(s));
+    st2[2 * g] = s.s0; st2[2 * g + 1] = s.s1;
+  }
+  float reach2 = 0.0f;
+  run([&] { prepare_rollout_kernel(reinterpret_cast<const float2*>(noise2.data()), u_cur, noiseT2.data(), ctrl2.data(), &reach2,
+                                   N, T, npad, lambda, std_v * std_v, std_w * std_w, vr[0], vr[1], wr[0], wr[1]); },
+      256, (unsigned)(npad / 32), 1);
+  if (std::memcmp(st.data(), st2.data(), st.size() * 8)) return 2;
+  if (std::memcmp(noise.data(), noise2.data(), noise.size() * 4)) return 3;
+  if (std::memcmp(noiseT.data(), noiseT2.data(), noiseT.size() * 16)) return 4;
+  if (std::memcmp(ctrl.data(), ctrl2.data(), ctrl.size() * 4)) return 5;
+  if (reach[0] != reach2) return 6;
+  std::memcpy(states_out, st.data(), st.size() * 8);
+  std::memcpy(noise_out, noise.data(), noise.size() * 4);
+  std::memcpy(noiseT_out, noiseT.data(), noiseT.size() * 16);
+  std::memcpy(ctrl_out, ctrl.data(), ctrl.size() * 4);
+  *reach_out = reach[0];
+  return 0;
+}
+
 // ctas: number of persistent CTAs (0: launch_rollout_win's own rule for a 148-SM device).
 // dst_blocks: 1 = one map-major (M, N) destination; ws > 1 = the sharded layout, ws separate (ws*M, N/ws) "receive
 // buffers" written at the rows of "rank" 1 (fill_cost_dst with direct = true) plus the epoch flags of CostSignal --
@@ -201,7 +249,8 @@ def build(out_dir):
     cell = _region(os.path.join(CSRC, "common.cuh"), "cell_index")
     cell, n = re.subn(r'int k; asm\("cvt\.rzi\.ftz\.s32\.f32[^;]*;[^;]*;', "int k = (int)res;   /* cvt.rzi */", cell)
     assert n == 1
-    prep = _region(os.path.join(CSRC, "rollout_win.cu"), "prepare")
+    prep = (_region(os.path.join(CSRC, "common.cuh"), "xoro") + _region(os.path.join(CSRC, "common.cuh"), "normal") +
+            _region(os.path.join(CSRC, "rollout_win.cu"), "prepare") + _region(os.path.join(CSRC, "rollout_win.cu"), "noise_prepare"))
     prep = re.sub(r"(?m)^(\s*)__shared__ ", r"\1static ", prep)
     kern = _region(os.path.join(CSRC, "rollout_win.cu"), "win_kernel")
     kern, n = re.subn(r'(?m)^\s*asm volatile\("fence\.[^;]*;[^;]*;\n', "", kern)        # mbarrier / proxy fences
@@ -219,6 +268,8 @@ def build(out_dir):
     assert r.returncode == 0, r.stderr[-6000:]
     lib = C.CDLL(so)
     P, I = C.c_void_p, C.c_int
+    lib.emu_noise_prepare.restype = I
+    lib.emu_noise_prepare.argtypes = [P, P, I, I, C.c_float, C.c_float, C.c_float, P, P, P, P, P, P, P]
     lib.emu_rollout_win.restype = I
     lib.emu_rollout_win.argtypes = [P, P, P, P, P, P, P, P, P, P, I, I, P, P, I, I]
     return lib

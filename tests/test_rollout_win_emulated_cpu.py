@@ -182,3 +182,30 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
                                    _p(out2), 110, 100, _p(origin), None, ctas, 1) == 0
         assert origin[0] % 16 == 0 and origin[0] > 80 + 16 and origin[1] > 80
         assert (out2 == out).all()
+
+
+@pytest.mark.parametrize("N,T", [(100, 50), (64, 128), (37, 3), (257, 33)])
+def test_fused_noise_and_controls_kernel_equals_the_two_kernels(emu, N, T):
+    """noise_prepare_kernel (what solve() launches) against sample_noise + prepare_rollout one after the other:
+    generator states, noise, float64 controls, control costs, reach statistic bit for bit (compared inside the
+    harness); the noise is the reference stream (oracle/xoroshiro.py)."""
+    from oracle import xoroshiro as X
+    win, _ = emu
+    rng = np.random.default_rng(N + T)
+    states = np.ascontiguousarray(X.create_states(N * T, 5))
+    u_cur = np.stack([rng.uniform(0, 2, T), rng.uniform(-1, 1, T)], 1).astype(F32)
+    vr, wr = _c([0, 3], F32), _c([-np.pi, np.pi], F32)
+    npad = (N + 31) // 32 * 32
+    st_out = np.zeros_like(states)
+    noise, noiseT = np.zeros((N, T, 2), F32), np.zeros((T, npad, 2), np.float64)
+    ctrl, reach = np.zeros(npad, F32), np.zeros(1, F32)
+    rc = win.emu_noise_prepare(_p(states), _p(u_cur), N, T, F32(2.0), F32(3.0), F32(1.0), _p(vr), _p(wr), _p(st_out), _p(noise),
+                               _p(noiseT), _p(ctrl), _p(reach))
+    assert rc == 0, rc
+    from oracle import mppi_ref as MR
+    want_states = states.copy()
+    want = MR.sample_noise(want_states, np.array([2.0, 3.0], F32), N, T)
+    np.testing.assert_allclose(noise, want, rtol=3e-6, atol=2e-6)
+    assert (st_out == want_states).all()
+    assert (noiseT[:, :N, 0] == np.clip(u_cur[:, None, 0] + noise[:, :, 0].T, 0, 3).astype(np.float64)).all()
+    assert (noiseT[:, :N, 1] == np.clip(u_cur[:, None, 1] + noise[:, :, 1].T, F32(-np.pi), F32(np.pi)).astype(np.float64)).all()
