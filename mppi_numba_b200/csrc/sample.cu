@@ -181,6 +181,8 @@ __device__ __forceinline__ void xoro_jump(Xoro& s, const ulonglong2* __restrict_
 // sampled value looked up from shared memory (false) or from a 16-byte register table with PRMT (true): the
 // register variant costs four more ALU-pipe instructions per cell and map, the shared-memory one a byte load
 constexpr bool SG_VALUES_IN_REGISTERS = false;
+// count the bytes >= q with one POPC per word (true) or one POPC after shifting the words' flags apart (false)
+constexpr bool SG_POPC_PER_WORD = true;
 
 template <int NT, int NW>
 __global__ void __launch_bounds__(256) sample_grids_v2_kernel(const SampleGridsV2Args a) {
@@ -276,17 +278,29 @@ __global__ void __launch_bounds__(256) sample_grids_v2_kernel(const SampleGridsV
 #pragma unroll
         for (int k = 0; k < NT; ++k) {
           const uint32_t* cw = reinterpret_cast<const uint32_t*>(s_cum + k * row_bytes_al + (ci - cs0) * bpad);
-          uint32_t bits = 0;
           // staged bytes carry bit 7 (guard): (0x80 | cum) - q never borrows across bytes (cum, q <= 127) and
-          // leaves bit 7 SET exactly for the bytes with cum >= q.  Word w contributes its four flags at bit
-          // 7-w of each byte: shift, then one LOP3 does bits | (z & mask)
-          if (NW > 0) {
+          // leaves bit 7 SET exactly for the bytes with cum >= q.
+          int ge = 0;                                         // cum is monotone: first bin >= q  =  4*nw - ge
+          if (SG_POPC_PER_WORD) {
+            // one mask + one POPC per word (POPC issues on its own quarter-rate pipe, the shifts of the variant below
+            // on the ALU pipe, which is the one this kernel saturates)
+            if (NW > 0) {
 #pragma unroll
-            for (int w = 0; w < (NW > 0 ? NW : 1); ++w) bits |= ((cw[w] - qq) >> (7 - w)) & (0x80808080u >> (7 - w));
+              for (int w = 0; w < (NW > 0 ? NW : 1); ++w) ge += __popc((cw[w] - qq) & 0x80808080u);
+            } else {
+              for (int w = 0; w < nw; ++w) ge += __popc((cw[w] - qq) & 0x80808080u);
+            }
           } else {
-            for (int w = 0; w < nw; ++w) bits |= ((cw[w] - qq) >> (7 - w)) & (0x80808080u >> (7 - w));
+            // word w contributes its four flags at bit 7-w of each byte: shift, then one LOP3 does bits | (z & mask)
+            uint32_t bits = 0;
+            if (NW > 0) {
+#pragma unroll
+              for (int w = 0; w < (NW > 0 ? NW : 1); ++w) bits |= ((cw[w] - qq) >> (7 - w)) & (0x80808080u >> (7 - w));
+            } else {
+              for (int w = 0; w < nw; ++w) bits |= ((cw[w] - qq) >> (7 - w)) & (0x80808080u >> (7 - w));
+            }
+            ge = __popc(bits);
           }
-          const int ge = __popc(bits);                        // cum is monotone: first bin >= q  =  4*nw - ge
           if (SG_VALUES_IN_REGISTERS && NW > 0 && NW <= 4) {
             const int bin = 4 * NW - ge;
             const uint32_t lo8 = __byte_perm(qreg[k][0], qreg[k][1], bin & 7);

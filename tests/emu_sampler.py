@@ -169,17 +169,18 @@ def _region(path, name):
     return m.group(1)
 
 
-def build(out_dir, values_in_registers=None):
-    """Generate + compile the emulator; returns the loaded ctypes library.  ``values_in_registers`` overrides the
-    kernel's compile-time switch SG_VALUES_IN_REGISTERS (the A/B variant of the value lookup)."""
+def build(out_dir, values_in_registers=None, popc_per_word=None):
+    """Generate + compile the emulator; returns the loaded ctypes library.  ``values_in_registers`` / ``popc_per_word``
+    override the kernel's compile-time switches SG_VALUES_IN_REGISTERS / SG_POPC_PER_WORD (the A/B variants of the
+    value lookup and of the byte count)."""
     kernel = _region(os.path.join(CSRC, "sample.cu"), "sampler_v2")
     tag = ""
-    if values_in_registers is not None:
-        kernel, n = re.subn(r"constexpr bool SG_VALUES_IN_REGISTERS = (true|false);",
-                            "constexpr bool SG_VALUES_IN_REGISTERS = %s;" % ("true" if values_in_registers else "false"),
-                            kernel)
-        assert n == 1
-        tag = "_regs" if values_in_registers else "_smem"
+    for name, val in (("SG_VALUES_IN_REGISTERS", values_in_registers), ("SG_POPC_PER_WORD", popc_per_word)):
+        if val is not None:
+            kernel, n = re.subn(r"constexpr bool %s = (true|false);" % name,
+                                "constexpr bool %s = %s;" % (name, "true" if val else "false"), kernel)
+            assert n == 1
+            tag += "_%s%d" % (name[3:8].lower(), int(bool(val)))
     src = (PRELUDE + _region(os.path.join(CSRC, "kernels.h"), "sampler_args") +
            _region(os.path.join(CSRC, "common.cuh"), "xoro") + _region(os.path.join(CSRC, "common.cuh"), "threshold") +
            kernel + HARNESS)

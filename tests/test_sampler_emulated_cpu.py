@@ -11,12 +11,18 @@ from tests.emu_sampler import build, cumulative_table
 from tests.scenarios import random_pmf
 
 
-@pytest.fixture(scope="module", params=["as-built", "values-in-registers"])
+@pytest.fixture(scope="module", params=["as-built", "values-in-registers", "one-popc"])
 def emu(request, tmp_path_factory):
-    """The kernel as built, and with its compile-time A/B switch flipped (value lookup through a register table)."""
+    """The kernel as built, and with its compile-time A/B switches flipped (value lookup through a register table;
+    the bytes >= q counted with shifts + one POPC instead of one POPC per word)."""
     import __graft_entry__
     __graft_entry__.build()
-    return build(str(tmp_path_factory.mktemp("emu")), None if request.param == "as-built" else True)
+    d = str(tmp_path_factory.mktemp("emu"))
+    if request.param == "values-in-registers":
+        return build(d, values_in_registers=True)
+    if request.param == "one-popc":
+        return build(d, popc_per_word=False)
+    return build(d)
 
 
 def _ptr(a):
