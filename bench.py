@@ -371,8 +371,11 @@ def time_small_workload(E, torch, name, local, steps, warmup):
     stream = torch.cuda.Stream(device=dev)
     check(lib.b200mppi_planner_set_stream(pl._handle, C.c_void_p(stream.cuda_stream)))   # solve() samples on this stream too
     N, M, T = sc["N"], (sc["M"] if sc["mode"] == "tdm" else 1), sc["T"]
-    for _ in range(max(warmup, 3) + 50):                         # small solves: ~0.1 ms each, warm the clocks too
+    t_w = time.perf_counter()                                    # small solves (~0.1 ms): keep the GPU loaded for 0.4 s so
+    n_w = 0                                                      # that the clocks have ramped up before anything is timed
+    while n_w < max(warmup, 3) or time.perf_counter() - t_w < 0.4:
         u = pl.solve()
+        n_w += 1
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = pl.launch_count()

@@ -209,16 +209,33 @@ __global__ void __launch_bounds__(UPD_THREADS) update_partial_kernel(const Updat
   __shared__ float s_bS[2];
   merge_partials(a.cta_partials, a.num_ctas, a.T, a.lambda, &s_bS[0], &s_bS[1], s_scale);
   const int stride = 2 * a.T + 2;
-  if (tl.mode == UPD_TAIL_APPLY) {                 // the rank partial would be the only one: apply straight away
-    apply_update(a, a.cta_partials, a.num_ctas, s_scale, s_bS[0], s_bS[1], true, 0, 1);
-    // rank_partial is still published (public buffer, tests); V is recomputed in the same order
-  }
+  const float W = s_bS[1];
+  // V[j] = sum_i V_i[j] * scale_i in CTA order (one column per thread, loads batched eight at a time -- the chain of
+  // FMAs is sequential, the L2 loads behind it must not be)
   for (int j = tid; j < 2 * a.T; j += blockDim.x) {
     float v = 0.0f;
-    for (int i = 0; i < a.num_ctas; ++i) v = fmaf(__ldcg(a.cta_partials + (size_t)i * stride + 2 + j), s_scale[i], v);
+    int i = 0;
+    for (; i + 8 <= a.num_ctas; i += 8) {
+      float x[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = __ldcg(a.cta_partials + (size_t)(i + k) * stride + 2 + j);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v = fmaf(x[k], s_scale[i + k], v);
+    }
+    for (; i < a.num_ctas; ++i) v = fmaf(__ldcg(a.cta_partials + (size_t)i * stride + 2 + j), s_scale[i], v);
     a.rank_partial[2 + j] = v;
+    if (tl.mode == UPD_TAIL_APPLY) {               // one rank: this partial is the only one -- apply straight away
+      const float u = a.u_cur[j] + v / W;
+      const float lo = (j & 1) ? a.wrange[0] : a.vrange[0];
+      const float hi = (j & 1) ? a.wrange[1] : a.vrange[1];
+      a.u_cur[j] = fmaxf(lo, fminf(hi, u));
+    }
   }
-  if (tid == 0) { a.rank_partial[0] = s_bS[0]; a.rank_partial[1] = s_bS[1]; }
+  if (tid == 0) { a.rank_partial[0] = s_bS[0]; a.rank_partial[1] = W; }
+  if (tl.mode == UPD_TAIL_APPLY) {
+    // normalised weights (mppi.py:1173-1174): the merge scale of a rollout's CTA is exp(-(beta_cta - beta)/lambda)
+    for (int r = tid; r < a.N; r += blockDim.x) a.weights[r] = __ldcg(a.w_raw + r) * (s_scale[r / a.rows_per_cta] / W);
+  }
   if (tl.mode == UPD_TAIL_BCAST) {
     __syncthreads();                                // rank_partial complete (this CTA wrote all of it)
     for (int q = 0; q < tl.ws; ++q) {
