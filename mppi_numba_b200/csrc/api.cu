@@ -48,6 +48,8 @@ struct b200mppi_tdm {
   uint64_t* states_alt = nullptr;   // double buffer for the segmented sampler
   uint64_t* jump_d = nullptr;       // jump-ahead matrices of the current tile geometry
   uint64_t* jump_tile_d = nullptr;  // [4][128][2]: whole-tile advance per tile class (sample_tile_draws)
+  uint64_t* jump_box_d = nullptr;   // segment jumps of a boxed launch (finer row segments: fewer tile rows to spread)
+  int box_segs = 1, box_seg_rows = 1;
   int jump_segs = 0, jump_seg_rows = 0, jump_rows = 0, jump_cols = 0;
   // reach-box sampling (solve() only): the sampled maps hold fresh values inside the box of the last solve and
   // stale ones outside; states_alt still holds the pre-solve generator states, so the whole maps of that very
@@ -128,22 +130,39 @@ static int tdm_prepare_jump(b200mppi_tdm* t, cudaStream_t st) {
     CU(cudaMemcpyAsync(t->jump_tile_d, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));            // h is a temporary
   }
-  if (segs > 1) {
-    // width classes: 0 = full tile column (ncol cells), 1 = the last, narrower column
-    int last_w = t->cols - (ty - 1) * ncol;
-    for (int iy = ty - 1; iy >= 0 && last_w <= 0; --iy) last_w = t->cols - iy * ncol;   // first non-empty from the right
-    if (last_w > ncol) last_w = ncol;
-    if (last_w < 0) last_w = 0;
+  // width classes: 0 = full tile column (ncol cells), 1 = the last, narrower column
+  int last_w = t->cols - (ty - 1) * ncol;
+  for (int iy = ty - 1; iy >= 0 && last_w <= 0; --iy) last_w = t->cols - iy * ncol;   // first non-empty from the right
+  if (last_w > ncol) last_w = ncol;
+  if (last_w < 0) last_w = 0;
+  auto upload_set = [&](uint64_t* dst, int nsegs, int rows_per_seg) -> int {
+    if (nsegs <= 1) return B200MPPI_OK;
     std::vector<int64_t> ks;
-    for (int sgm = 1; sgm < segs; ++sgm) {
-      ks.push_back((int64_t)sgm * seg_rows * ncol);
-      ks.push_back((int64_t)sgm * seg_rows * last_w);
+    for (int sgm = 1; sgm < nsegs; ++sgm) {
+      ks.push_back((int64_t)sgm * rows_per_seg * ncol);
+      ks.push_back((int64_t)sgm * rows_per_seg * last_w);
     }
     std::vector<uint64_t> h(ks.size() * 256);
     build_jump_matrices(ks.data(), (int)ks.size(), h.data());
-    CU(cudaMemcpyAsync(t->jump_d, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dst, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));            // h is a temporary
-  }
+    return B200MPPI_OK;
+  };
+  int rc = upload_set(t->jump_d, segs, seg_rows);
+  if (rc) return rc;
+  // a boxed launch covers a few tile rows only: finer row segments keep every SM busy through several waves
+  // (measured on config 5 with whole-map segment sizes: 24 % of the SM-cycles idle in the tail, profiles/)
+  // ~3 waves of the ~6 resident CTAs per SM, for a box of ~8 tile rows sampled ~14 maps per CTA
+  int bsegs = (3 * 6 * 148 + 8 * ((t->num_maps + 13) / 14) - 1) / (8 * ((t->num_maps + 13) / 14));
+  if (const char* e = getenv("B200MPPI_SAMPLE_BOX_SEGS")) bsegs = atoi(e);
+  if (bsegs > SAMPLE_MAX_SEGS) bsegs = SAMPLE_MAX_SEGS;
+  if (bsegs > nrow) bsegs = nrow;
+  if (bsegs < segs) bsegs = segs;
+  if (bsegs < 1) bsegs = 1;
+  const int bseg_rows = (nrow + bsegs - 1) / bsegs;
+  if (!t->jump_box_d) CU(cudaMalloc(&t->jump_box_d, (size_t)(SAMPLE_MAX_SEGS - 1) * 2 * 256 * sizeof(uint64_t)));
+  if ((rc = upload_set(t->jump_box_d, bsegs, bseg_rows))) return rc;
+  t->box_segs = bsegs; t->box_seg_rows = bseg_rows;
   t->jump_segs = segs; t->jump_seg_rows = seg_rows; t->jump_rows = t->rows; t->jump_cols = t->cols;
   return B200MPPI_OK;
 }
@@ -166,8 +185,9 @@ static void fill_v2(const b200mppi_tdm* t, SampleGridsV2Args& a, int slot) {
 struct SampleBox { int row_lo, row_hi, col_lo, col_hi; };
 
 // Restrict a whole-map launch description to the tile rows / row range / tile columns covering `b`.
-static void apply_box(SampleGridsV2Args& a, const SampleBox& b) {
+static void apply_box(const b200mppi_tdm* t, SampleGridsV2Args& a, const SampleBox& b) {
   const int nrow = (a.rows + a.tx - 1) / a.tx, ncol = (a.cols + a.ty - 1) / a.ty;
+  a.segs = t->box_segs; a.seg_rows = t->box_seg_rows; a.jump = t->jump_box_d;
   a.row_lo = b.row_lo; a.row_hi = b.row_hi;
   a.tix_lo = b.row_lo / nrow;
   a.tiy_lo = b.col_lo / ncol;
@@ -193,7 +213,7 @@ static int tdm_sample_on(b200mppi_tdm* t, double alpha_dyn, cudaStream_t st, con
   if (t->thr_ok && sample_grids_v2_fits(v2, 1)) {
     if (box) {
       SampleGridsV2Args bx = v2;
-      apply_box(bx, *box);
+      apply_box(t, bx, *box);
       if (sample_grids_v2_fits(bx, 1)) { v2 = bx; boxed = true; }
     }
     launch_sample_grids_v2(v2, 1, st);
@@ -236,7 +256,7 @@ static int tdm_sample_pair_on(b200mppi_tdm* l, b200mppi_tdm* g, double alpha_dyn
     bool boxed = false;
     if (box) {
       SampleGridsV2Args bx = v2;
-      apply_box(bx, *box);
+      apply_box(l, bx, *box);
       if (sample_grids_v2_fits(bx, 2)) { v2 = bx; boxed = true; }
     }
     launch_sample_grids_v2(v2, 2, st);
@@ -344,7 +364,7 @@ extern "C" int b200mppi_tdm_destroy(b200mppi_tdm* t) {
   if (!t) return B200MPPI_OK;
   cudaSetDevice(t->cfg.device);
   cudaFree(t->grid); cudaFree(t->states); cudaFree(t->pmf); cudaFree(t->cum); cudaFree(t->qvals);
-  cudaFree(t->obstacle); cudaFree(t->unknown); cudaFree(t->risk); cudaFree(t->thr_d); cudaFree(t->states_alt); cudaFree(t->jump_d); cudaFree(t->jump_tile_d);
+  cudaFree(t->obstacle); cudaFree(t->unknown); cudaFree(t->risk); cudaFree(t->thr_d); cudaFree(t->states_alt); cudaFree(t->jump_d); cudaFree(t->jump_tile_d); cudaFree(t->jump_box_d);
   if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
   delete t;
   return B200MPPI_OK;
@@ -748,7 +768,8 @@ static int planner_init(b200mppi_planner* p, const b200mppi_config* cfg) {
   CU(cudaMalloc(&p->costs_nm, (size_t)p->n_local * p->M * sizeof(float)));
   if (p->shard_maps) CU(cudaMalloc(&p->costs_x, (size_t)p->n_local * p->M * sizeof(float)));
   p->npad = round_up(p->n_local, 32);
-  CU(cudaMalloc(&p->noiseT, (size_t)p->T * p->npad * 2 * sizeof(double)));
+  CU(cudaMalloc(&p->noiseT, (size_t)(p->T + 1) * p->npad * 2 * sizeof(double)));      // + 1 row: unguarded prefetch
+  CU(cudaMemsetAsync(p->noiseT, 0, (size_t)(p->T + 1) * p->npad * 2 * sizeof(double), p->stream));
   CU(cudaMalloc(&p->ctrl, (size_t)p->npad * sizeof(float)));
   p->use_win = getenv("B200MPPI_NO_WINDOW") == nullptr;
   CU(cudaMalloc(&p->reach_d, 256));

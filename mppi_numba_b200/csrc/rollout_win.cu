@@ -34,6 +34,8 @@ namespace b200 {
 // -- identical for all M maps of a control sequence, so computed once here (coalesced per-step loads
 // for lanes = consecutive n) -- and the per-n control cost sum_t lambda*(u_v/s_v^2*e_v + u_w/s_w^2*e_w)
 // (mppi.py:708-710), accumulated in the reference's order t = 0..T-1.
+// noiseT has T + 1 rows of npad double2 (the rollout kernel prefetches one row ahead without a guard; row T is never
+// used and never written).
 // [emu:begin prepare]
 __global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __restrict__ noise,
                                                               const float* __restrict__ u_cur,
@@ -384,7 +386,10 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const int Tn = live ? p.T : 0;                        // run zero steps and store nothing, but stay with their warp
     const double2* __restrict__ ep = reinterpret_cast<const double2*>(a.noiseT) + n;
     float x = p.x0[0], y = p.x0[1], th = p.x0[2];
-    double x64 = widen(x), y64 = widen(y), th64 = widen(th);   // same values, float64 registers
+    // the float64 state is carried UNROUNDED across the back edge (rx, ry, rt: the float64 FMA results, initially the
+    // float32 state itself) and rounded to float32 precision at the top of the next step: the FMA of a step then
+    // writes straight into the carried registers (no register moves at the end of the loop body)
+    double rx = widen(x), ry = widen(y), rt = widen(th);
     float cost = 0.0f, d2 = 1e9f;
     double2 c2 = __ldg(ep);                                 // controls of step t (loaded during step t-1, see below)
     for (int t = 0; t < Tn; ++t) {
@@ -419,18 +424,18 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const double dv = lds_f64(sb_lutL + (uint32_t)(ql * 8)) * c2.x;
       const float cs = cos_approx(th);
       const float sn = sin_approx(th);
-      const double rx = fma(dv, widen(cs), x64);
-      const double ry = fma(dv, widen(sn), y64);
-      const double rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), c2.y, th64);
+      // float64 copies of the float32-rounded state: XR of the three through the XU pipe (a second conversion,
+      // widen(narrow(.))), the others on the integer pipe -- the same values either way
+      const double x64 = (XR >= 3) ? widen(x) : round_to_f32_precision(rx);
+      const double y64 = (XR >= 2) ? widen(y) : round_to_f32_precision(ry);
+      const double th64 = (XR >= 1) ? widen(th) : round_to_f32_precision(rt);
+      rx = fma(dv, widen(cs), x64);
+      ry = fma(dv, widen(sn), y64);
+      rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), c2.y, th64);
       // `c2` is dead from here on: fetch the next step's controls straight into it -- the rest of this step and the
       // cell lookup of the next one (~70 instructions per warp, 32 warps per SM) cover the L2 latency
-      if (t + 1 < Tn) c2 = __ldg(ep);
+      c2 = __ldg(ep);                                       // (row T exists: the buffer has T + 1 rows, no guard needed)
       x = narrow(rx); y = narrow(ry); th = narrow(rt);
-      // float64 copies of the rounded state: XR of the three through the XU pipe (a second conversion, widen(narrow(.))),
-      // the others on the integer pipe -- the same values either way; the split balances issue slots against XU cycles
-      x64 = (XR >= 3) ? widen(x) : round_to_f32_precision(rx);
-      y64 = (XR >= 2) ? widen(y) : round_to_f32_precision(ry);
-      th64 = (XR >= 1) ? widen(th) : round_to_f32_precision(rt);
       // ---- stage cost (mppi.py:696-701)
       const float dx = fsub(gx, x), dy = fsub(gy, y);
       d2 = ffma(dx, dx, fmul(dy, dy));

@@ -185,7 +185,7 @@ extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratio
   w.p = params(f, g, ratios);
   const RolloutParams& p = w.p;
   const int npad = (p.N + 31) / 32 * 32;
-  std::vector<double2> noiseT((size_t)p.T * npad, double2{0, 0});
+  std::vector<double2> noiseT((size_t)(p.T + 1) * npad, double2{0, 0});      // + 1 row: the kernel prefetches unguarded
   std::vector<float> ctrl(npad, 0.0f);
   float reach = 0.0f;
   run([&] { prepare_rollout_kernel(reinterpret_cast<const float2*>(noise), u_cur, noiseT.data(), ctrl.data(), &reach, p.N, p.T, npad,
