@@ -324,7 +324,12 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   const int tid = threadIdx.x, lane = tid & 31;
   const int cpm = a.npad >> 5;                               // chunks per map
   const long long total = (long long)p.M * cpm;
-  const long long w_lo = total * blockIdx.x / gridDim.x, w_hi = total * (blockIdx.x + 1) / gridDim.x;
+  // share boundaries are multiples of a.unit chunks (32 = one chunk per warp of the CTA when the shares are long
+  // enough: every map segment is then a whole number of passes and all warps reach the end-of-segment barrier
+  // together -- ncu showed 0.8 of 7.8 warps parked there with chunk-granular shares; 1 for short shares)
+  const long long units = (total + a.unit - 1) / a.unit;
+  const long long w_lo = min(total, units * blockIdx.x / gridDim.x * a.unit);
+  const long long w_hi = min(total, units * (blockIdx.x + 1) / gridDim.x * a.unit);
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -566,11 +571,13 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
   const long long total = (long long)a.p.M * (a.npad / 32);
   const int ctas = (int)std::min<long long>(std::max<long long>(total / 8, 1), sms);
   const dim3 grid(win_grid_override > 0 ? win_grid_override : ctas);
+  RolloutWinArgs b = a;
+  b.unit = (total / (32LL * grid.x) >= 4) ? 32 : 1;        // whole passes per share once a share is >= 4 passes long
   const CUtensorMap& t0 = *reinterpret_cast<const CUtensorMap*>(tm_lin);
   const CUtensorMap& t1 = *reinterpret_cast<const CUtensorMap*>(tm_ang);
   const CUtensorMap& t2 = *reinterpret_cast<const CUtensorMap*>(tm_obs);
   const CUtensorMap& t3 = *reinterpret_cast<const CUtensorMap*>(tm_unk);
-  kernels[a.WH == 232 ? 0 : 1][xr]<<<grid, WIN_THREADS, L.total, st>>>(a, t0, t1, t2, t3);
+  kernels[a.WH == 232 ? 0 : 1][xr]<<<grid, WIN_THREADS, L.total, st>>>(b, t0, t1, t2, t3);
   return cudaGetLastError();
 }
 
