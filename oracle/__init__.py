@@ -18,7 +18,7 @@ unpinned by the reference -- README.md:66 ``pip3 install numba`` -- the image ha
 The oracle is therefore pinned against OUTPUTS OF THE REFERENCE ITSELF, run in the build
 container under Numba's CUDA simulator (``oracle/make_golden.py`` -> ``tests/golden/*.npz``,
 script committed) and against known-answer vectors of numba 0.65.0's generator
-(``tests/test_oracle_rng.py``).  The simulator is the exact-math (no fast-math) variant of the
+(``tests/test_oracle_golden.py::test_xoroshiro_known_answers``).  The simulator is the exact-math (no fast-math) variant of the
 reference; where compiled typing differs from the simulator the golden
 inputs are chosen so both agree (bin values that are multiples of 1/4).
 """
