@@ -210,11 +210,18 @@ __global__ void __launch_bounds__(UPD_THREADS) update_partial_kernel(const Updat
   merge_partials(a.cta_partials, a.num_ctas, a.T, a.lambda, &s_bS[0], &s_bS[1], s_scale);
   const int stride = 2 * a.T + 2;
   const float W = s_bS[1];
-  // V[j] = sum_i V_i[j] * scale_i in CTA order (one column per thread, loads batched eight at a time -- the chain of
+  // V[j] = sum_i V_i[j] * scale_i in CTA order (one column per thread, loads batched 32 at a time -- the chain of
   // FMAs is sequential, the L2 loads behind it must not be)
   for (int j = tid; j < 2 * a.T; j += blockDim.x) {
     float v = 0.0f;
     int i = 0;
+    for (; i + 32 <= a.num_ctas; i += 32) {
+      float x[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) x[k] = __ldcg(a.cta_partials + (size_t)(i + k) * stride + 2 + j);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v = fmaf(x[k], s_scale[i + k], v);
+    }
     for (; i + 8 <= a.num_ctas; i += 8) {
       float x[8];
 #pragma unroll

@@ -103,19 +103,22 @@ __global__ void __launch_bounds__(256) prepare_rollout_kernel(const float2* __re
 // `reach` has two slots used alternately by consecutive launches: this launch max-reduces into reach[slot] and clears
 // reach[slot ^ 1] for the next one (the host has read it: solve() synchronises on it).
 // [emu:begin noise_prepare]
+constexpr int NP_NB = 8;            // control sequences per CTA: 1024 CTAs of 8 x 32 threads at config 5 (occupancy; the
+                                    // Box-Muller chains are long and latency-bound)
 __global__ void __launch_bounds__(256) noise_prepare_kernel(uint64_t* __restrict__ states, float2* __restrict__ noise,
                                                             const float* __restrict__ u_cur, double2* __restrict__ noiseT,
                                                             float* __restrict__ ctrl, float* __restrict__ reach, int slot,
                                                             int N, int T, int npad, float std_v, float std_w, float lambda,
                                                             float sv2, float sw2, float v_lo, float v_hi, float w_lo,
                                                             float w_hi) {
-  __shared__ float2 tile[32][33];
-  const int n0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  __shared__ float2 tile[NP_NB][33];
+  const int n0 = blockIdx.x * NP_NB;
+  const int tx = threadIdx.x & 31, r = threadIdx.x >> 5;       // generation: row r = control sequence, lane = time step
+  const int tn = threadIdx.x & (NP_NB - 1), tt = threadIdx.x >> 3;   // transposed write: 8 consecutive n per time step
   if (blockIdx.x == 0 && threadIdx.x == 0 && reach) reach[slot ^ 1] = 0.0f;
   float acc = 0.0f, vsum = 0.0f;
   for (int t0 = 0; t0 < T; t0 += 32) {
-    for (int r = ty; r < 32; r += 8) {                         // rows = n, cols = t: generators contiguous along t
+    {                                                          // generators (n0 + r) * T + t0 + tx: contiguous along the lanes
       const int n = n0 + r, t = t0 + tx;
       float2 e = make_float2(0.f, 0.f);
       if (n < N && t < T) {
@@ -131,20 +134,20 @@ __global__ void __launch_bounds__(256) noise_prepare_kernel(uint64_t* __restrict
       tile[r][tx] = e;
     }
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) {                         // rows = t, cols = n  (coalesced along n)
-      const int t = t0 + r;
+    {                                                          // rows = t, 8 consecutive n per row: 128-byte segments
+      const int t = t0 + tt;
       if (t < T) {
-        const float2 e = tile[tx][r];
+        const float2 e = tile[tn][tt];
         double2 c;
         c.x = f2d(fmaxf(v_lo, fminf(v_hi, fadd(u_cur[2 * t], e.x))));
         c.y = f2d(fmaxf(w_lo, fminf(w_hi, fadd(u_cur[2 * t + 1], e.y))));
-        noiseT[(size_t)t * npad + n0 + tx] = c;
+        noiseT[(size_t)t * npad + n0 + tn] = c;
       }
     }
-    if (ty == 0) {                                             // lane tx owns rollout n0+tx
+    if (threadIdx.x < NP_NB) {                                 // lane tn owns rollout n0 + tn: sums in the reference's order t = 0..T-1
       const int tend = min(32, T - t0);
       for (int j = 0; j < tend; ++j) {
-        const float2 e = tile[tx][j];
+        const float2 e = tile[tn][j];
         const float a = div_approx(u_cur[2 * (t0 + j)], sv2);
         const float b = div_approx(u_cur[2 * (t0 + j) + 1], sw2);
         acc = ffma(ffma(a, e.x, fmul(b, e.y)), lambda, acc);
@@ -153,12 +156,13 @@ __global__ void __launch_bounds__(256) noise_prepare_kernel(uint64_t* __restrict
     }
     __syncthreads();
   }
-  if (ty == 0) {
-    if (n0 + tx < N) ctrl[n0 + tx] = acc; else vsum = 0.0f;
+  if (threadIdx.x < 32) {                                      // whole first warp takes part in the shuffles
+    const bool own = threadIdx.x < NP_NB && n0 + tn < N;
+    if (own) ctrl[n0 + tn] = acc; else vsum = 0.0f;
     if (reach) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) vsum = fmaxf(vsum, __shfl_xor_sync(0xffffffffu, vsum, o));
-      if (tx == 0) atomicMax(reinterpret_cast<unsigned int*>(reach + slot), __float_as_uint(vsum));
+      if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(reach + slot), __float_as_uint(vsum));
     }
   }
 }
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(256) noise_prepare_kernel(uint64_t* __restrict
 void launch_noise_prepare(uint64_t* states, float* noise, const float* u_cur, float* noiseT, float* ctrl, float* reach,
                           int slot, int N, int T, int npad, float lambda, float std_v, float std_w, const float vrange[2],
                           const float wrange[2], cudaStream_t st) {
-  noise_prepare_kernel<<<npad / 32, 256, 0, st>>>(states, reinterpret_cast<float2*>(noise), u_cur,
+  noise_prepare_kernel<<<npad / NP_NB, 256, 0, st>>>(states, reinterpret_cast<float2*>(noise), u_cur,
                                                  reinterpret_cast<double2*>(noiseT), ctrl, reach, slot, N, T, npad, std_v,
                                                  std_w, lambda, std_v * std_v, std_w * std_w, vrange[0], vrange[1],
                                                  wrange[0], wrange[1]);
@@ -355,7 +359,10 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   const float MAGIC = 12582912.0f;                          // 1.5 * 2^23
   int magic_wx = 0x4B400000 + a.wx0, magic_wy = 0x4B400000 + a.wy0;
   asm volatile("" : "+r"(magic_wx), "+r"(magic_wy));       // keep the folded constants (else re-derived per step)
-  const float inv_lo = inv_res * (1.0f - 4.8e-7f), inv_hi = inv_res * (1.0f + 4.8e-7f);
+  // interval half-width 2.4e-7 (relative): the exact quotient q = a/res satisfies |fl(a*fl(inv*(1-+d))) - q(1-+d)| <=
+  // 3 * 2^-24 |q| = 1.79e-7 |q| (roundings of 1/res, of the scaled reciprocal, of the FMA), so d = 2.4e-7 keeps q inside
+  // [lower end, upper end] with a third to spare; a wider interval only sends more steps to the exact sequence
+  const float inv_lo = inv_res * (1.0f - 2.4e-7f), inv_hi = inv_res * (1.0f + 2.4e-7f);
   const unsigned uww = (unsigned)a.ww, uwh = (unsigned)a.wh;     // staged AND inside the map (<= WW, WH)
 
   uint32_t phase = 0;
@@ -400,8 +407,8 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     for (int t = 0; t < Tn; ++t) {
       ep += a.npad;
       // ---- cell index of both axes: floor(a/res) by round-down magic-number addition on the FP32 pipe, taken
-      //      at BOTH ends of an interval that contains the exact quotient a/res (relative half-width 4.8e-7,
-      //      about 2.6x the worst rounding error of a * (1/res); the +-1e-30 covers a == 0 and flushed
+      //      at BOTH ends of an interval that contains the exact quotient a/res (relative half-width 2.4e-7,
+      //      1.34x the worst accumulated rounding error, see inv_lo / inv_hi; the +-1e-30 covers a == 0 and flushed
       //      denormals).  Equal floors at both ends prove the cell -- it is then what the reference's exact
       //      sequence (the true floor of a/res) yields; otherwise run that sequence.
       const float ax = fsub(x, xlo), ay = fsub(y, ylo);

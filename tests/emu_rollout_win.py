@@ -142,7 +142,7 @@ extern "C" int emu_noise_prepare(const uint64_t* states_in, const float* u_cur, 
   float reach[2] = {0.0f, 123.0f};
   run([&] { noise_prepare_kernel(st.data(), reinterpret_cast<float2*>(noise.data()), u_cur, noiseT.data(), ctrl.data(), reach, 0,
                                  N, T, npad, std_v, std_w, lambda, std_v * std_v, std_w * std_w, vr[0], vr[1], wr[0], wr[1]); },
-      256, (unsigned)(npad / 32), 1);
+      256, (unsigned)(npad / NP_NB), 1);
   if (reach[1] != 0.0f) return 1;                                  // the other slot is cleared for the next launch
   // the two separate kernels
   std::vector<uint64_t> st2((size_t)N * T * 2);

@@ -61,7 +61,7 @@ def test_windowed_kernel_matches_reference_and_generic_kernel(emu, gname):
 
 def test_two_sided_floor_criterion_never_disagrees_with_the_reference_floor_division():
     """The windowed kernel takes floor(a/res) from round-down magic-number sums at both ends of the interval
-    [a*inv*(1-4.8e-7) - 1e-30, a*inv*(1+4.8e-7) + 1e-30] and trusts it only when both ends give the same integer.
+    [a*inv*(1-2.4e-7) - 1e-30, a*inv*(1+2.4e-7) + 1e-30] and trusts it only when both ends give the same integer.
     Whenever they do, the integer must be what the reference's float floor-division yields (oracle floor_div_f32,
     numba real_divmod as compiled): random positions, positions within 1e-5 cells of an edge, exact multiples of the
     resolution, tiny and denormal offsets, ten resolutions."""
@@ -84,10 +84,14 @@ def test_two_sided_floor_criterion_never_disagrees_with_the_reference_floor_divi
     for res in (0.05, 0.1, 0.2, 0.25, 0.5, 1.0, 2.0, 0.3, 0.07, 3.3):
         r = F32(res)
         inv = F32(1.0) / r
-        inv_lo, inv_hi = F32(inv * F32(1.0 - 4.8e-7)), F32(inv * F32(1.0 + 4.8e-7))
+        inv_lo, inv_hi = F32(inv * F32(1.0 - 2.4e-7)), F32(inv * F32(1.0 + 2.4e-7))
         n = 200000
         k = rng.integers(-300, 2500, n)
-        sets = (rng.uniform(-50, 250, n).astype(F32), (k * np.float64(res) + rng.normal(0, 1e-5, n) * res).astype(F32),
+        # edge-hugging positions: within 1e-5, 1e-6 cells and a few float32 ulps (relative 1e-7 .. 4e-7) of an edge
+        near = [(k * np.float64(res) * (1.0 + rng.choice([-1, 1], n) * rng.uniform(0.5e-7, 4e-7, n))).astype(F32),
+                (k * np.float64(res) + rng.normal(0, 1e-6, n) * res).astype(F32)]
+        near += [np.nextafter(near[0], F32(np.inf)), np.nextafter(near[0], F32(-np.inf))]
+        sets = tuple(near) + (rng.uniform(-50, 250, n).astype(F32), (k * np.float64(res) + rng.normal(0, 1e-5, n) * res).astype(F32),
                 (k * np.float64(res)).astype(F32), rng.uniform(-1e-6, 1e-6, n).astype(F32),
                 (rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-37, -5, n)).astype(F32),
                 np.array([0.0, -0.0, 1.2e-38, -1.2e-38], F32))
