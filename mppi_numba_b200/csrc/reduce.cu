@@ -171,19 +171,29 @@ __global__ void __launch_bounds__(UPD_THREADS) update_partial_kernel(const Updat
       a.w_raw[rb + tid] = w;
     }
     __syncthreads();
-    for (int i = 0; i < nr; ++i) {
-      const float w = s_w[i];
-      if (tid == 0) S += w;
-      const float2* row = eps + (size_t)(rb + i) * a.T;
+    // rows in batches of eight: the loads of a batch are issued before its FMAs (issue is in order -- an FMA waiting
+    // for its row would hold back the next row's load); accumulation order is the row order, as before
+    for (int i0 = 0; i0 < nr; i0 += 8) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int j = tid + k * UPD_THREADS;
         if (j < a.T) {
-          const float2 e = __ldg(row + j);
-          acc[k].x = fmaf(w, e.x, acc[k].x);
-          acc[k].y = fmaf(w, e.y, acc[k].y);
+          float2 e[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            e[q] = (i0 + q < nr) ? __ldg(eps + (size_t)(rb + i0 + q) * a.T + j) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (i0 + q < nr) {
+              const float w = s_w[i0 + q];
+              acc[k].x = fmaf(w, e[q].x, acc[k].x);
+              acc[k].y = fmaf(w, e[q].y, acc[k].y);
+            }
+          }
         }
       }
+      if (tid == 0)
+        for (int q = 0; q < 8 && i0 + q < nr; ++q) S += s_w[i0 + q];
     }
   }
   if (tid == 0) { part[0] = (r1 > r0) ? beta : INFINITY; part[1] = S; }

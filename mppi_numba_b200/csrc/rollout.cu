@@ -243,9 +243,22 @@ __global__ void __launch_bounds__(CVAR_THREADS) cvar_kernel(const float* __restr
   const int NB = cvar_block_n(M);
   const int n0 = blockIdx.x * NB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int idx = tid; idx < M * NB; idx += CVAR_THREADS) {
-    const int m = idx / NB, j = idx - m * NB;
-    s_tile[j * (M + 1) + m] = (n0 + j < n_cnt) ? __ldcg(costs_mn + (size_t)m * ld + n0 + j) : 0.0f;
+  // slab load: NB is a power of two; eight independent L2 loads in flight per thread before the shared-memory stores
+  // (issue is in order: a store waiting for its load would hold back the next load)
+  const int nb_shift = 31 - __clz(NB);
+  for (int base = tid; base < M * NB; base += 8 * CVAR_THREADS) {
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int idx = base + k * CVAR_THREADS;
+      const int m = idx >> nb_shift, j = idx & (NB - 1);
+      x[k] = (idx < M * NB && n0 + j < n_cnt) ? __ldcg(costs_mn + (size_t)m * ld + n0 + j) : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int idx = base + k * CVAR_THREADS;
+      if (idx < M * NB) s_tile[(idx & (NB - 1)) * (M + 1) + (idx >> nb_shift)] = x[k];
+    }
   }
   __syncthreads();
   for (int j = warp; j < NB; j += CVAR_THREADS / 32) {

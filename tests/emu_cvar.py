@@ -54,6 +54,7 @@ static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4
 namespace b200 {
 uint32_t s_keys[1 << 15];
 template <class T> static inline T __ldcg(const T* p) { return *p; }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 struct FlagWait { const uint32_t* flags; int ws; uint32_t epoch; unsigned long long timeout_ns; int* status; };
 static inline void flag_wait(const FlagWait&) {}
 '''

@@ -50,6 +50,7 @@ struct FlagWait { const uint32_t* flags; int ws; uint32_t epoch; unsigned long l
 static inline void flag_wait(const FlagWait&) {}          // blocks run one after the other: nothing to wait for
 static inline float __double2float_rn(double d) { return (float)d; }
 struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 using std::min;
 using std::max;
 namespace b200 {
