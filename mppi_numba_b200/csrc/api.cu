@@ -182,7 +182,7 @@ static void fill_v2(const b200mppi_tdm* t, SampleGridsV2Args& a, int slot) {
 }
 
 // Cells [row_lo, row_hi) x [col_lo, col_hi) that the rollouts of the coming solve can read (planner: reach_box).
-struct SampleBox { int row_lo, row_hi, col_lo, col_hi; };
+struct SampleBox { int row_lo, row_hi, col_lo, col_hi; float cx, cy, r; };   // + the reach disc in cells (r = 0: none)
 
 // Restrict a whole-map launch description to the tile rows / row range / tile columns covering `b`.
 static void apply_box(const b200mppi_tdm* t, SampleGridsV2Args& a, const SampleBox& b) {
@@ -198,6 +198,7 @@ static void apply_box(const b200mppi_tdm* t, SampleGridsV2Args& a, const SampleB
   if (gm < 1) gm = 1;
   a.gm = gm;
   a.write_states = 0;
+  a.disc_cx = b.cx; a.disc_cy = b.cy; a.disc_r = b.r;
 }
 
 // One TDM.  Fast staged sampler when the PMF is well-formed, else the generic per-generator kernel.
@@ -658,6 +659,7 @@ struct b200mppi_planner {
   // reach-box sampling: 0 = whole maps every solve, 1 = box from the speed limit, 2 = box from this solve's
   // own clipped controls (max_n sum_t |v|, reduced by the prepare kernel into reach_d and read back mid-solve)
   int box_mode = 2;
+  bool disc = true;              // sample the reach disc inside the box (B200MPPI_SAMPLE_DISC=0: the whole box)
   float* reach_d = nullptr;            // two slots, used alternately (noise_prepare_kernel)
   int reach_slot = 0;
   bool reach_valid = false;            // reach_d[reach_slot] holds this iteration's statistic
@@ -781,6 +783,7 @@ static int planner_init(b200mppi_planner* p, const b200mppi_config* cfg) {
     else if (!strcmp(e, "static")) p->box_mode = 1;
     else p->box_mode = 2;
   }
+  if (const char* e = getenv("B200MPPI_SAMPLE_DISC")) p->disc = atoi(e) != 0;
   p->num_ctas = update_num_ctas(p->n_red);
   p->rows_per_cta = (p->n_red + p->num_ctas - 1) / p->num_ctas;
   p->num_ctas = (p->n_red + p->rows_per_cta - 1) / p->rows_per_cta;
@@ -1138,6 +1141,11 @@ static bool planner_reach_box(b200mppi_planner* p, SampleBox* box, int* how, int
   if (!(fx0 > 2.0 && fy0 > 2.0 && fx1 < (double)l->cols - 3.0 && fy1 < (double)l->rows - 3.0)) return false;
   box->col_lo = (int)std::floor(fx0) - 1; box->col_hi = (int)std::floor(fx1) + 3;      // [lo, hi)
   box->row_lo = (int)std::floor(fy0) - 1; box->row_hi = (int)std::floor(fy1) + 3;
+  // the same bound as a disc: a rollout stays within Euclidean distance R of x0, so the cell it reads lies within
+  // R/res + sqrt(2) cells of the robot's (fractional) cell position; + 1.5 for float32 effects, rounded up
+  box->cx = (float)(((double)q.x0[0] - (double)l->pxl[0]) / res);
+  box->cy = (float)(((double)q.x0[1] - (double)l->pyl[0]) / res);
+  box->r = p->disc ? (float)(R / res + 3.0) * 1.0001f : 0.0f;
   return true;
 }
 

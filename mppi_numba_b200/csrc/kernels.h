@@ -36,11 +36,15 @@ struct SampleGridsV2Args {
   // generator stores its advanced state (whole-map walks only -- a boxed launch leaves the states to
   // advance_states_kernel, which jumps every generator over its whole tile)
   int gm, tix_lo, tiy_lo, nact, row_lo, row_hi, write_states;
+  // reach DISC inside the box (disc_r = 0: none): centre cell (disc_cx, disc_cy) and radius in cells, margins included;
+  // a CTA samples only the tile columns its rows can reach (sample.cu)
+  float disc_cx, disc_cy, disc_r;
 };
 constexpr int SG_GM = 8;          // maps per CTA of a whole-map launch
 constexpr int SG_GM_MAX = 32;
 inline void sample_box_full(SampleGridsV2Args& a) {
   a.gm = SG_GM; a.tix_lo = 0; a.tiy_lo = 0; a.nact = a.ty; a.row_lo = 0; a.row_hi = a.rows; a.write_states = 1;
+  a.disc_cx = a.disc_cy = a.disc_r = 0.0f;
 }
 void build_jump_matrices(const int64_t* ks, int count, uint64_t* out);
 // q(r) of a RAW 64-bit draw r as a two-table lookup over its top 8 bits (see sample_threshold_q in common.cuh):

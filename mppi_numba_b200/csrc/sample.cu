@@ -191,10 +191,37 @@ __global__ void __launch_bounds__(256) sample_grids_v2_kernel(const SampleGridsV
   const int bpad = nw * 4;
   const int ncol = (a.cols + a.ty - 1) / a.ty;
   const int nrow = (a.rows + a.tx - 1) / a.tx;
+  const int tix = a.tix_lo + blockIdx.x / a.segs, seg = blockIdx.x % a.segs;
+  const int t0 = min(tix * nrow, a.rows), t1 = min(t0 + nrow, a.rows);          // the generator's tile rows
+  // this CTA's row segment of the tile.  A generator's stream is split into `segs` consecutive row
+  // segments handled by different CTAs: segment `seg` starts from the state jumped ahead by
+  // seg*seg_rows*(c1-c0) draws (GF(2) matrix), so the union of the segments is the reference's stream.
+  const int r0 = min(t0 + seg * a.seg_rows, t1), r1 = min(r0 + a.seg_rows, t1);
+  // rows of this segment inside the reach box (CTA-uniform)
+  const int rs0 = max(r0, a.row_lo), rs1 = min(r1, a.row_hi);
+  // active tile columns of THIS CTA: those of the launch, narrowed to the reach DISC when one is given -- the rows
+  // [rs0, rs1) are at least dy cells away from the centre row, so only columns within sqrt(R^2 - dy^2) of the centre
+  // column can be read.  Threads are re-mapped onto the narrower range, which parks whole warps instead of lanes.
+  int tiy_lo = a.tiy_lo, nact = a.nact;
+  if (a.disc_r > 0.0f && rs0 < rs1) {
+    // row r holds the positions [r, r + 1) in cell coordinates: distance of [rs0, rs1) from the centre
+    const float dy = (a.disc_cy < (float)rs0) ? (float)rs0 - a.disc_cy
+                   : (a.disc_cy > (float)rs1) ? a.disc_cy - (float)rs1 : 0.0f;
+    const float w2 = a.disc_r * a.disc_r - dy * dy;
+    if (w2 <= 0.0f) {
+      nact = 0;                                               // the whole segment lies outside the disc
+    } else {
+      const float w = sqrtf(w2) + 1.0f;
+      const int lo = max(a.tiy_lo, (int)floorf((a.disc_cx - w) / (float)ncol));
+      const int hi = min(a.tiy_lo + a.nact - 1, (int)floorf((a.disc_cx + w) / (float)ncol));
+      tiy_lo = lo; nact = max(hi - lo + 1, 0);
+    }
+  }
+  if (nact == 0) return;                                      // CTA-uniform: nothing to sample here
   // staged column window [cs0, cs1): the active tile columns, start rounded down to 16 cells (16-byte stores)
-  const int cfirst = min(a.tiy_lo * ncol, a.cols);
+  const int cfirst = min(tiy_lo * ncol, a.cols);
   const int cs0 = cfirst & ~15;
-  const int cs1 = min((a.tiy_lo + a.nact) * ncol, a.cols);
+  const int cs1 = min((tiy_lo + nact) * ncol, a.cols);
   const int wcols = cs1 - cs0;
   const int row_bytes = wcols * bpad;                        // the window's slice of one cumulative-table row
   const int row_bytes_al = (row_bytes + 15) & ~15;
@@ -207,8 +234,7 @@ __global__ void __launch_bounds__(256) sample_grids_v2_kernel(const SampleGridsV
   unsigned char* s_q = reinterpret_cast<unsigned char*>(s_T + SAMPLE_TABLE_WORDS);   // [NT][128]
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int tiy = a.tiy_lo + tid % a.nact, mloc = tid / a.nact;
-  const int tix = a.tix_lo + blockIdx.x / a.segs, seg = blockIdx.x % a.segs;
+  const int tiy = tiy_lo + tid % nact, mloc = tid / nact;
   const int m = blockIdx.y * gm + mloc;
   const bool active = (mloc < gm) && (m < a.num_maps);
 
@@ -232,12 +258,7 @@ __global__ void __launch_bounds__(256) sample_grids_v2_kernel(const SampleGridsV
     }
   }
 
-  const int t0 = min(tix * nrow, a.rows), t1 = min(t0 + nrow, a.rows);          // the generator's tile rows
   const int c0 = min(tiy * ncol, a.cols), c1 = min(c0 + ncol, a.cols);
-  // this CTA's row segment of the tile.  A generator's stream is split into `segs` consecutive row
-  // segments handled by different CTAs: segment `seg` starts from the state jumped ahead by
-  // seg*seg_rows*(c1-c0) draws (GF(2) matrix), so the union of the segments is the reference's stream.
-  const int r0 = min(t0 + seg * a.seg_rows, t1), r1 = min(r0 + a.seg_rows, t1);
   const int wc = c1 - c0;
   const int last_seg = (t1 > t0 && wc > 0) ? (t1 - t0 - 1) / a.seg_rows : 0;     // owner of the final state
 
@@ -251,9 +272,8 @@ __global__ void __launch_bounds__(256) sample_grids_v2_kernel(const SampleGridsV
       xoro_jump(s, reinterpret_cast<const ulonglong2*>(a.jump) + ((size_t)(seg - 1) * 2 + cls) * 128);
     }
   }
-  // rows of this segment inside the reach box (CTA-uniform); the draws of the segment's rows above the box are
-  // consumed without sampling (one xoroshiro step per cell), rows below it are simply not walked
-  const int rs0 = max(r0, a.row_lo), rs1 = min(r1, a.row_hi);
+  // the draws of the segment's rows above the box are consumed without sampling (one xoroshiro step per cell), rows
+  // below it are simply not walked
   if (active && rs0 < rs1)
     for (int64_t i = (int64_t)(rs0 - r0) * wc; i > 0; --i) xoro_next(s);
 

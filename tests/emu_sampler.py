@@ -77,12 +77,13 @@ static void run(const SampleGridsV2Args& a, int threads, unsigned gx, unsigned g
 
 // nt TDMs (1 or 2) sampled from the generator states `states` (numba layout, gen = tix*(ty*M)+m*ty+tiy).
 // cum: (nt)(rows, cols, bpad) int8 running sums; grids: (nt)(M, grid_rows, pitch); qvals: (nt)(128).
+// disc = {cx, cy, r} (cells) or null: the reach disc inside the box (per-CTA narrowing of the tile columns).
 // box = {row_lo, row_hi, col_lo, col_hi} (cells) or null: with a box the launch is restricted as apply_box (api.cu)
 // does it and the states come from advance_states_kernel -- what tdm_sample_pair_on does for a boxed solve.
 extern "C" int emu_sample_v2(int nt, int8_t* grid0, int8_t* grid1, const int8_t* cum0, const int8_t* cum1,
                              const uint64_t* states, uint64_t* states_out, const int8_t* qv0, const int8_t* qv1, int bpad,
                              int rows, int cols, int grid_rows, int pitch, int tx, int ty, int num_maps, int segs,
-                             double alpha, int q_cap, const int* box) {
+                             double alpha, int q_cap, const int* box, const float* disc) {
   using namespace b200;
   SampleGridsV2Args a{};
   std::vector<uint64_t> out2(states_out ? 0 : 1);
@@ -127,6 +128,7 @@ extern "C" int emu_sample_v2(int nt, int8_t* grid0, int8_t* grid1, const int8_t*
     if (gm < 1) gm = 1;
     a.gm = gm;
     a.write_states = 0;
+    if (disc) { a.disc_cx = disc[0]; a.disc_cy = disc[1]; a.disc_r = disc[2]; }
     tix_hi = std::min(tx - 1, (std::max(a.row_hi, a.row_lo + 1) - 1) / nrow);       // launch_v2_nt (sample.cu)
   }
   const int threads = ((a.nact * a.gm + 31) / 32) * 32;
@@ -195,7 +197,7 @@ def build(out_dir, values_in_registers=None, popc_per_word=None):
     lib = C.CDLL(so)
     P = C.c_void_p
     lib.emu_sample_v2.restype = C.c_int
-    lib.emu_sample_v2.argtypes = [C.c_int, P, P, P, P, P, P, P, P] + [C.c_int] * 9 + [C.c_double, C.c_int, P]
+    lib.emu_sample_v2.argtypes = [C.c_int, P, P, P, P, P, P, P, P] + [C.c_int] * 9 + [C.c_double, C.c_int, P, P]
     return lib
 
 

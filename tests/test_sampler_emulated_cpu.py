@@ -58,7 +58,7 @@ def test_sampler_kernel_source_matches_oracle(emu, B, nt, segs, alpha, M, shape,
     q_cap = int(min(int(np.cumsum(p.astype(np.int64), axis=0)[-1].min()) for p in pmfs))
     rc = emu.emu_sample_v2(nt, _ptr(grids[0]), _ptr(grids[nt - 1]), _ptr(cums[0]), _ptr(cums[nt - 1]), _ptr(st_in),
                            _ptr(st_out), _ptr(q), _ptr(q), bpad, rows, cols, grid_rows, pitch, tx, ty, M, segs,
-                           float(alpha), min(q_cap, 127), None)
+                           float(alpha), min(q_cap, 127), None, None)
     assert rc == 0
     for k in range(nt):
         want = np.full((M, grid_rows, pitch), -7, dtype=np.int8)
@@ -94,7 +94,7 @@ def test_sampler_kernel_source_random_configurations(emu):
         st_in = np.ascontiguousarray(states0.copy())
         st_out = np.zeros_like(st_in)
         rc = emu.emu_sample_v2(nt, _ptr(grids[0]), _ptr(grids[nt - 1]), _ptr(cums[0]), _ptr(cums[nt - 1]), _ptr(st_in),
-                               _ptr(st_out), _ptr(q), _ptr(q), bpad, rows, cols, grid_rows, pitch, tx, ty, M, segs, alpha, 100, None)
+                               _ptr(st_out), _ptr(q), _ptr(q), bpad, rows, cols, grid_rows, pitch, tx, ty, M, segs, alpha, 100, None, None)
         assert rc == 0, case
         for k in range(nt):
             want = np.full((M, grid_rows, pitch), -7, dtype=np.int8)
@@ -110,6 +110,7 @@ def test_sampler_kernel_source_boxed_launch(emu):
     nothing is written, and advance_states_kernel leaves every generator exactly where the whole-map walk does --
     random boxes, tiles, segment counts, map counts (maps per CTA follow the number of active tile columns)."""
     rng = np.random.default_rng(77)
+    skipped = 0
     for case in range(14):
         B = int(rng.choice([3, 5, 12, 12, 32]))
         nt = int(rng.integers(1, 3))
@@ -121,6 +122,11 @@ def test_sampler_kernel_source_boxed_launch(emu):
         r_lo = int(rng.integers(0, rows - 1)); r_hi = int(rng.integers(r_lo + 1, rows + 1))
         c_lo = int(rng.integers(0, cols - 1)); c_hi = int(rng.integers(c_lo + 1, cols + 1))
         box = np.array([r_lo, r_hi, c_lo, c_hi], dtype=np.int32)
+        # every second case: the reach disc inscribed in the box (what solve() passes), centre at a fractional cell
+        disc = None
+        if case % 2:
+            cy, cx = 0.5 * (r_lo + r_hi) + rng.uniform(-0.4, 0.4), 0.5 * (c_lo + c_hi) + rng.uniform(-0.4, 0.4)
+            disc = np.array([cx, cy, 0.5 * max(r_hi - r_lo, c_hi - c_lo) + 0.5], dtype=np.float32)
         bpad = (B + 3) // 4 * 4
         bin_values = np.linspace(0, 1, B)
         bounds = np.array([0.0, 1.0], dtype=np.float32)
@@ -135,7 +141,7 @@ def test_sampler_kernel_source_boxed_launch(emu):
         st_out = np.zeros_like(st_in)
         rc = emu.emu_sample_v2(nt, _ptr(grids[0]), _ptr(grids[nt - 1]), _ptr(cums[0]), _ptr(cums[nt - 1]), _ptr(st_in),
                                _ptr(st_out), _ptr(q), _ptr(q), bpad, rows, cols, grid_rows, pitch, tx, ty, M, segs, alpha, 100,
-                               _ptr(box))
+                               _ptr(box), _ptr(disc) if disc is not None else None)
         tag = "case %d: B=%d nt=%d t=(%d,%d) map=(%d,%d) M=%d segs=%d alpha=%g box=%s" % (
             case, B, nt, tx, ty, rows, cols, M, segs, alpha, box.tolist())
         assert rc == 0, tag
@@ -146,10 +152,58 @@ def test_sampler_kernel_source_boxed_launch(emu):
             want = np.full((M, grid_rows, pitch), -7, dtype=np.int8)
             st = states0.copy()
             TR.sample_grids(want, pmfs[k], st, bin_values, bounds, alpha, (tx, ty), M)
-            assert (grids[k][:, r_lo:r_hi, c_lo:c_hi] == want[:, r_lo:r_hi, c_lo:c_hi]).all(), tag
             inside = np.zeros((grid_rows, pitch), bool)
             inside[r_lo:r_hi, tc_lo:tc_hi] = True
-            assert (grids[k][:, inside] == want[:, inside]).all(), tag
-            assert (grids[k][:, ~inside] == -7).all(), tag
+            assert (grids[k][:, ~inside] == -7).all(), tag                    # nothing outside the box's tile columns
+            if disc is None:
+                assert (grids[k][:, inside] == want[:, inside]).all(), tag
+            else:
+                # every cell that holds a position within r of the centre is sampled (= the whole-map value); a cell
+                # the launch did not sample is untouched
+                yy, xx = np.mgrid[0:grid_rows, 0:pitch]
+                dyc = np.maximum(np.maximum(yy - disc[1], disc[1] - (yy + 1)), 0)
+                dxc = np.maximum(np.maximum(xx - disc[0], disc[0] - (xx + 1)), 0)
+                need = inside & (dxc ** 2 + dyc ** 2 <= float(disc[2]) ** 2)
+                got = grids[k]
+                assert (got[:, need] == want[:, need]).all(), tag
+                assert ((got == want) | (got == -7))[:, inside].all(), tag
+                skipped += int(((got == -7) & inside[None]).sum())
             assert (st_out == st).all(), tag
         assert (st_in == states0).all()
+
+
+def test_sampler_kernel_source_disc_parks_corner_tiles(emu):
+    """A 64 x 64 map in 8 x 8 tiles, box = the interior, disc of radius 26 around the centre, 2-row segments: the
+    segments near the top and the bottom of the box sample only the tile columns under the disc (the corner tiles
+    stay untouched), every cell the disc needs equals the whole-map value, the generators advance as for whole maps."""
+    rng = np.random.default_rng(5)
+    B, nt, tx, ty, rows, cols, M, segs, alpha = 12, 2, 8, 8, 64, 64, 5, 4, 1.0
+    box = np.array([4, 60, 4, 60], dtype=np.int32)
+    disc = np.array([32.3, 31.6, 26.0], dtype=np.float32)
+    bpad = 12
+    bin_values = np.linspace(0, 1, B)
+    bounds = np.array([0.0, 1.0], dtype=np.float32)
+    pmfs = [random_pmf(rng, B, rows, cols) for _ in range(nt)]
+    grid_rows, pitch = rows, 64
+    states0 = X.create_states(tx * ty * M, 3)
+    q = np.zeros(128, dtype=np.int8)
+    q[:B] = TR.quantise_bin_values(bin_values, bounds)
+    grids = [np.full((M, grid_rows, pitch), -7, dtype=np.int8) for _ in range(nt)]
+    cums = [cumulative_table(p, bpad) for p in pmfs]
+    st_in = np.ascontiguousarray(states0.copy())
+    st_out = np.zeros_like(st_in)
+    assert emu.emu_sample_v2(nt, _ptr(grids[0]), _ptr(grids[1]), _ptr(cums[0]), _ptr(cums[1]), _ptr(st_in), _ptr(st_out),
+                             _ptr(q), _ptr(q), bpad, rows, cols, grid_rows, pitch, tx, ty, M, segs, alpha, 100, _ptr(box),
+                             _ptr(disc)) == 0
+    yy, xx = np.mgrid[0:rows, 0:cols]
+    dyc = np.maximum(np.maximum(yy - disc[1], disc[1] - (yy + 1)), 0)
+    dxc = np.maximum(np.maximum(xx - disc[0], disc[0] - (xx + 1)), 0)
+    need = (dxc ** 2 + dyc ** 2 <= 26.0 ** 2) & (yy >= 4) & (yy < 60) & (xx >= 4) & (xx < 60)
+    for k in range(nt):
+        want = np.full((M, grid_rows, pitch), -7, dtype=np.int8)
+        st = states0.copy()
+        TR.sample_grids(want, pmfs[k], st, bin_values, bounds, alpha, (tx, ty), M)
+        assert (grids[k][:, need] == want[:, need]).all()
+        assert ((grids[k] == want) | (grids[k] == -7)).all()
+        assert (grids[k][:, 4:8, 4:8] == -7).all() and (grids[k][:, 56:60, 56:60] == -7).all()     # corner tiles parked
+        assert (st_out == st).all()
