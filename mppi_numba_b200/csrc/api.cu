@@ -1616,6 +1616,8 @@ extern "C" int b200mppi_planner_synchronize(b200mppi_planner* p) {
   if (!p) return fail(B200MPPI_EINVAL, "null planner");
   CU(cudaSetDevice(p->cfg.device));
   CU(cudaStreamSynchronize(p->stream));
+  collect_timings(p);                          // stage-level callers (solve_local + synchronize) get their stage times too
+  (void)cudaGetLastError();                    // events of stages that did not run are unrecorded
   return B200MPPI_OK;
 }
 
