@@ -104,6 +104,7 @@ static void tdm_advance_sig(b200mppi_tdm* t) {
 // Row segments per generator tile: enough CTAs to fill the GPU (the stream of a generator is sequential,
 // so parallelism beyond M*tx*ty generators comes from GF(2) jump-ahead), at most SAMPLE_MAX_SEGS.
 constexpr int SAMPLE_MAX_SEGS = 33;
+constexpr int SAMPLE_BOX_MAX_SEGS = 128;   // boxed launches of a rank holding few maps go down to one-row segments
 static int tdm_prepare_jump(b200mppi_tdm* t, cudaStream_t st) {
   const int tx = t->cfg.tdm_thread_x, ty = t->cfg.tdm_thread_y;
   const int nrow = (t->rows + tx - 1) / tx, ncol = (t->cols + ty - 1) / ty;
@@ -155,12 +156,12 @@ static int tdm_prepare_jump(b200mppi_tdm* t, cudaStream_t st) {
   // ~3 waves of the ~6 resident CTAs per SM, for a box of ~8 tile rows sampled ~14 maps per CTA
   int bsegs = (3 * 6 * 148 + 8 * ((t->num_maps + 13) / 14) - 1) / (8 * ((t->num_maps + 13) / 14));
   if (const char* e = getenv("B200MPPI_SAMPLE_BOX_SEGS")) bsegs = atoi(e);
-  if (bsegs > SAMPLE_MAX_SEGS) bsegs = SAMPLE_MAX_SEGS;
+  if (bsegs > SAMPLE_BOX_MAX_SEGS) bsegs = SAMPLE_BOX_MAX_SEGS;
   if (bsegs > nrow) bsegs = nrow;
   if (bsegs < segs) bsegs = segs;
   if (bsegs < 1) bsegs = 1;
   const int bseg_rows = (nrow + bsegs - 1) / bsegs;
-  if (!t->jump_box_d) CU(cudaMalloc(&t->jump_box_d, (size_t)(SAMPLE_MAX_SEGS - 1) * 2 * 256 * sizeof(uint64_t)));
+  if (!t->jump_box_d) CU(cudaMalloc(&t->jump_box_d, (size_t)(SAMPLE_BOX_MAX_SEGS - 1) * 2 * 256 * sizeof(uint64_t)));
   if ((rc = upload_set(t->jump_box_d, bsegs, bseg_rows))) return rc;
   t->box_segs = bsegs; t->box_seg_rows = bseg_rows;
   t->jump_segs = segs; t->jump_seg_rows = seg_rows; t->jump_rows = t->rows; t->jump_cols = t->cols;
