@@ -138,13 +138,8 @@ static int tdm_prepare_jump(b200mppi_tdm* t, cudaStream_t st) {
   if (last_w < 0) last_w = 0;
   auto upload_set = [&](uint64_t* dst, int nsegs, int rows_per_seg) -> int {
     if (nsegs <= 1) return B200MPPI_OK;
-    std::vector<int64_t> ks;
-    for (int sgm = 1; sgm < nsegs; ++sgm) {
-      ks.push_back((int64_t)sgm * rows_per_seg * ncol);
-      ks.push_back((int64_t)sgm * rows_per_seg * last_w);
-    }
-    std::vector<uint64_t> h(ks.size() * 256);
-    build_jump_matrices(ks.data(), (int)ks.size(), h.data());
+    std::vector<uint64_t> h((size_t)(nsegs - 1) * 2 * 256);
+    build_jump_series((int64_t)rows_per_seg * ncol, (int64_t)rows_per_seg * last_w, nsegs, h.data());
     CU(cudaMemcpyAsync(dst, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));            // h is a temporary
     return B200MPPI_OK;

@@ -47,6 +47,7 @@ inline void sample_box_full(SampleGridsV2Args& a) {
   a.disc_cx = a.disc_cy = a.disc_r = 0.0f;
 }
 void build_jump_matrices(const int64_t* ks, int count, uint64_t* out);
+void build_jump_series(int64_t k0, int64_t k1, int segs, uint64_t* out);     // (s-1)*2 + c -> A^(s * k_c), s = 1 .. segs-1
 // q(r) of a RAW 64-bit draw r as a two-table lookup over its top 8 bits (see sample_threshold_q in common.cuh):
 // table = thr[256] (u64) followed by qbase[256] (u8).  false if alpha is not representable that way.
 constexpr int SAMPLE_TABLE_WORDS = 256 + 256 / 8;

@@ -503,6 +503,23 @@ void build_jump_matrices(const int64_t* ks, int count, uint64_t* out) {
   }
 }
 
+// out: [(segs-1)*2][128][2] u64, matrix (s-1)*2 + c advances a state by s*k[c] draws (c = 0, 1), s = 1 .. segs-1:
+// the segment-start jumps of the sampler, built with one product per matrix (A^(s k) = A^k * A^((s-1) k)).
+void build_jump_series(int64_t k0, int64_t k1, int segs, uint64_t* out) {
+  if (segs < 2) return;
+  const int64_t ks[2] = {k0, k1};
+  std::vector<uint64_t> b(2 * 256);
+  build_jump_matrices(ks, 2, b.data());
+  Gf2Mat base[2], acc[2], tmp;
+  for (int c = 0; c < 2; ++c) { std::memcpy(base[c].c, b.data() + (size_t)c * 256, sizeof(base[c].c)); acc[c] = base[c]; }
+  for (int sgm = 1; sgm < segs; ++sgm)
+    for (int c = 0; c < 2; ++c) {
+      std::memcpy(out + ((size_t)(sgm - 1) * 2 + c) * 256, acc[c].c, sizeof(acc[c].c));
+      gf2_mul(base[c], acc[c], tmp);
+      acc[c] = tmp;
+    }
+}
+
 // Host: breakpoints of q(v) = int8(ceil(f64(f32(v * 2^-53)) * 100.0 * alpha)) (terrain.py:682-683 as
 // compiled: cvt.rn.f64.u64, mul.f64 2^-53, cvt.rn.f32.f64, cvt.f64.f32, mul.f64 100, mul.f64 alpha,
 // cvt.rpi.f64, cvt.rzi.s16 -> low byte).  Returns false if q is not a monotone map into [0, q_cap]
