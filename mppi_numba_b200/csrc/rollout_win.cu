@@ -294,7 +294,7 @@ __host__ __device__ inline WinSmem win_smem_layout(int WW, int WH, int T) {
   const int planes = (4 * s.plane + 127) & ~127;
   s.off_lut = planes;                              // 2 x 256 doubles
   s.off_u = s.off_lut + 2 * 256 * 8;               // 2T floats
-  s.off_bar = (s.off_u + 2 * T * 4 + 15) & ~15;       // mbarrier (8 bytes)
+  s.off_bar = (s.off_u + 2 * T * 4 + 15) & ~15;       // mbarrier (8 bytes) + the chunk counter
   s.total = s.off_bar + 16;
   return s;
 }
@@ -306,7 +306,8 @@ constexpr int WIN_WW = 240;       // window width in cells (inner TMA box extent
 // every SM gets the same number of chunks whatever M and N are (a (tiles, M) grid of one-tile CTAs quantises: 256
 // tile units on 148 SMs at 8 GPUs = two rounds where 1.73 would do).  A share spans one to a few maps: per map the
 // CTA stages that map's window once (thread 0 issues the TMA loads after the CTA has left the previous window), then
-// its warps take the chunks of the map's part of the share round-robin.
+// its warps pull chunks from a shared-memory counter until the map's part of the share is done -- warps whose
+// rollouts reached the goal early simply take the next chunk.
 template <int THREADS, int WH, int XR>
 __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWinArgs a,
                                                                  const __grid_constant__ CUtensorMap tm_lin,
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   double* s_lutA = s_lutL + 256;
   float* s_u = reinterpret_cast<float*>(smem + L.off_u);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  int* s_next = reinterpret_cast<int*>(bar + 1);             // chunk counter of the current map
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int cpm = a.npad >> 5;                               // chunks per map
@@ -371,6 +373,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     w += c_hi - c_lo;
     __syncthreads();                                        // every warp has left the previous window (and the tables are written)
     if (tid == 0) {
+      *s_next = c_lo;
       // order the CTA's generic-proxy reads of the previous window before the async-proxy writes of the next one
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(bar, 4u * (uint32_t)PLANE);
@@ -379,16 +382,17 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       tma_load_2d(smem + 2 * PLANE, &tm_obs, bar, a.wx0, a.wy0);
       tma_load_2d(smem + 3 * PLANE, &tm_unk, bar, a.wx0, a.wy0);
     }
+    __syncthreads();                                        // s_next visible
     mbar_wait(bar, phase);
     phase ^= 1u;
     const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
     const int8_t* __restrict__ g_ang = a.ang_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
 
-    // chunks of this map's part of the share, dealt to the warps round-robin.  (Static on purpose: with a shared
-    // counter the hardware's warp priorities let some warps run three chunks while others are still on their first,
-    // and the stragglers then finish alone -- measured on a rank of an 8-GPU solve, 55 chunks per CTA: 0.185 ms with
-    // the counter against 0.11 ms of work.)
-    for (int c = c_lo + (tid >> 5); c < c_hi; c += THREADS / 32) {
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(s_next, 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= c_hi) break;
       const int n = (c << 5) + lane;
       const bool live = n < p.N;                            // ragged last chunk (n is padded to whole warps): such lanes
       const int Tn = live ? p.T : 0;                        // run zero steps and store nothing, but stay with their warp

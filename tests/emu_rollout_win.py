@@ -2,8 +2,8 @@
 INFRASTRUCTURE; technique of tests/emu_sampler.py).  The kernels' text is lifted from csrc/rollout_win.cu between
 the ``[emu:... prepare]`` / ``[emu:... win_kernel]`` markers.  What stands in for the hardware: a CUtensorMap is a
 plain descriptor (base, dims, pitch, box) and ``tma_load_2d/3d`` copy the box with zero fill outside the tensor
-(what CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE does for integer types); the mbarrier wait is a CTA barrier (thread 0 has
-finished its copies when it gets there); shared-space addresses are offsets into one static buffer; ``__fadd_rd`` is a round-down add
+(what CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE does for integer types); mbarrier calls are no-ops (the copy is done when
+the call returns); shared-space addresses are offsets into one static buffer; ``__fadd_rd`` is a round-down add
 derived from the rounded sum and its exact error (TwoSum); 1024 std::threads stand for the CTA.  Arithmetic helpers as in
 tests/emu_rollout.py (IEEE meaning; libm for the MUFU approximations)."""
 import ctypes as C
@@ -78,8 +78,7 @@ alignas(128) unsigned char smem[1 << 18];
 static inline uint32_t smem_u32(const void* p) { return (uint32_t)((const unsigned char*)p - smem); }
 static inline void mbar_init(uint64_t*, int) {}
 static inline void mbar_expect_tx(uint64_t*, uint32_t) {}
-static inline void mbar_wait(uint64_t*, uint32_t) { g_bar->arrive_and_wait(); }   // every thread of the CTA waits once per
-                                                                                     // window; thread 0 has copied by then
+static inline void mbar_wait(uint64_t*, uint32_t) {}
 static inline void tma_box(unsigned char* dst, const CUtensorMap* tm, int c0, int c1, int c2) {
   for (int y = 0; y < tm->WH; ++y)
     for (int x = 0; x < tm->WW; ++x) {
