@@ -579,7 +579,10 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
   const int ctas = (int)std::min<long long>(std::max<long long>(total / 8, 1), sms);
   const dim3 grid(win_grid_override > 0 ? win_grid_override : ctas);
   RolloutWinArgs b = a;
-  b.unit = (total / (32LL * grid.x) >= 4) ? 32 : 1;        // whole passes per share once a share is >= 4 passes long
+  // whole passes (32 chunks) per share as soon as every CTA gets at least one: a share cut at arbitrary chunks splits
+  // into map segments like 33 + 22 chunks = three partial passes where 32 + 23 or 64 would be two (measured on a rank
+  // of an 8-GPU solve, 55 chunks per CTA: slowest SM 1.7x the average)
+  b.unit = (total / (32LL * grid.x) >= 1) ? 32 : 1;
   const CUtensorMap& t0 = *reinterpret_cast<const CUtensorMap*>(tm_lin);
   const CUtensorMap& t1 = *reinterpret_cast<const CUtensorMap*>(tm_ang);
   const CUtensorMap& t2 = *reinterpret_cast<const CUtensorMap*>(tm_obs);

@@ -225,7 +225,7 @@ extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratio
     const long long total = (long long)p.M * (npad / 32);
     ctas = (int)std::min<long long>(std::max<long long>(total / 8, 1), 148);
   }
-  w.unit = ((long long)p.M * (npad / 32) / (32LL * ctas) >= 4) ? 32 : 1;     // launch_rollout_win
+  w.unit = ((long long)p.M * (npad / 32) / (32LL * ctas) >= 1) ? 32 : 1;     // launch_rollout_win
   if (unit_override > 0) w.unit = unit_override;
   run([&] { rollout_win_kernel<1024, 232, 0>(w, t_lin, t_ang, t_obs, t_unk); }, 1024, (unsigned)ctas, 1);
   for (int n = 0; n < p.N; ++n)
