@@ -385,6 +385,13 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     __syncthreads();                                        // s_next visible
     mbar_wait(bar, phase);
     phase ^= 1u;
+    // the barrier above releases all 32 warps in lockstep: they would hit the XU / LSU / FP64 sections of the step
+    // together, pass after pass.  Spread the warps of a scheduler over one step period (a.stagger cycles per slot)
+    if (a.stagger > 0) {
+      const long long t0 = clock64();
+      const long long wait = (long long)(tid >> 7) * a.stagger;
+      while (clock64() - t0 < wait) { }
+    }
     const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
     const int8_t* __restrict__ g_ang = a.ang_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
 
@@ -516,6 +523,7 @@ bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int
 }
 
 constexpr int WIN_THREADS = 1024;
+constexpr int WIN_STAGGER_DEFAULT = 0;    // cycles between the warps of a scheduler after a window barrier (B200MPPI_WIN_STAGGER)
 constexpr int WIN_XR_DEFAULT = 0;         // measured on B200: see profiles/ (B200MPPI_WIN_XR sweeps it)
 static int win_grid_override = 0;         // B200MPPI_WIN_GRID (tuning / test hook): number of persistent CTAs
 constexpr int WIN_MAX_SMEM = 232448;      // 227 KB: per-block opt-in limit on sm_100
@@ -579,6 +587,13 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
   const int ctas = (int)std::min<long long>(std::max<long long>(total / 8, 1), sms);
   const dim3 grid(win_grid_override > 0 ? win_grid_override : ctas);
   RolloutWinArgs b = a;
+  static int stagger = WIN_STAGGER_DEFAULT;
+  static bool stagger_read = false;
+  if (!stagger_read) {
+    if (const char* e = getenv("B200MPPI_WIN_STAGGER")) stagger = atoi(e);
+    stagger_read = true;
+  }
+  b.stagger = stagger;
   // whole passes (32 chunks) per share as soon as every CTA gets at least one: a share cut at arbitrary chunks splits
   // into map segments like 33 + 22 chunks = three partial passes where 32 + 23 or 64 would be two (measured on a rank
   // of an 8-GPU solve, 55 chunks per CTA: slowest SM 1.7x the average)
