@@ -561,6 +561,8 @@ def run_b200(args, sc):
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     km = kernel_metrics(args.workload) if world == 1 else None
     kd = (km or {}).get("kernels", {}).get(dom)
+    if dom == "sample_grids" and not box[0]:
+        kd = None                         # the committed capture is of the boxed launch
     traffic = kd.get("dram_bytes") if kd else None
     sm_hz = (clk.get("sm_mhz") or 1965.0) * 1e6
     issue_peak = 148 * 4 * sm_hz

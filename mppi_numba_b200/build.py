@@ -40,6 +40,7 @@ def build_library(force=False, verbose=False):
 
 
 def _build_locked(force, verbose):
+    extra = os.environ.get("B200MPPI_NVCC_FLAGS", "").split()      # A/B builds of compile-time switches (e.g. -DSG_POPC_VARIANT=0)
     hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
     objs = []
     log = []
@@ -48,7 +49,7 @@ def _build_locked(force, verbose):
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _newer(o, [s] + hdrs):
-            cmd = [NVCC] + FLAGS + ["-c", s, "-o", o]
+            cmd = [NVCC] + FLAGS + extra + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             log.append(r.stderr)
             if r.returncode != 0:

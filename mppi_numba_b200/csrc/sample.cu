@@ -182,7 +182,10 @@ __device__ __forceinline__ void xoro_jump(Xoro& s, const ulonglong2* __restrict_
 // register variant costs four more ALU-pipe instructions per cell and map, the shared-memory one a byte load
 constexpr bool SG_VALUES_IN_REGISTERS = false;
 // count the bytes >= q with one POPC per word (true) or one POPC after shifting the words' flags apart (false)
-constexpr bool SG_POPC_PER_WORD = true;
+#ifndef SG_POPC_VARIANT
+#define SG_POPC_VARIANT 1
+#endif
+constexpr bool SG_POPC_PER_WORD = SG_POPC_VARIANT;
 
 template <int NT, int NW>
 __global__ void __launch_bounds__(256) sample_grids_v2_kernel(const SampleGridsV2Args a) {

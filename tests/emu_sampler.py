@@ -179,7 +179,7 @@ def build(out_dir, values_in_registers=None, popc_per_word=None):
     tag = ""
     for name, val in (("SG_VALUES_IN_REGISTERS", values_in_registers), ("SG_POPC_PER_WORD", popc_per_word)):
         if val is not None:
-            kernel, n = re.subn(r"constexpr bool %s = (true|false);" % name,
+            kernel, n = re.subn(r"constexpr bool %s = [A-Za-z_0-9]+;" % name,
                                 "constexpr bool %s = %s;" % (name, "true" if val else "false"), kernel)
             assert n == 1
             tag += "_%s%d" % (name[3:8].lower(), int(bool(val)))
