@@ -178,6 +178,25 @@ __device__ __forceinline__ void xoro_jump(Xoro& s, const ulonglong2* __restrict_
   s.s0 = a0; s.s1 = a1;
 }
 
+// the same product with the matrix staged in shared memory (every thread of a CTA applies the same one or two
+// matrices: 2 KB each, one cooperative copy instead of 128 dependent cache loads per thread)
+__device__ __forceinline__ void xoro_jump_smem(Xoro& s, const ulonglong2* mat) {
+  uint64_t a0 = 0, a1 = 0;
+#pragma unroll 8
+  for (int j = 0; j < 64; ++j) {
+    const ulonglong2 c = mat[j];
+    const uint64_t mk = 0ULL - ((s.s0 >> j) & 1ULL);
+    a0 ^= c.x & mk; a1 ^= c.y & mk;
+  }
+#pragma unroll 8
+  for (int j = 0; j < 64; ++j) {
+    const ulonglong2 c = mat[64 + j];
+    const uint64_t mk = 0ULL - ((s.s1 >> j) & 1ULL);
+    a0 ^= c.x & mk; a1 ^= c.y & mk;
+  }
+  s.s0 = a0; s.s1 = a1;
+}
+
 // sampled value looked up from shared memory (false) or from a 16-byte register table with PRMT (true): the
 // register variant costs four more ALU-pipe instructions per cell and map, the shared-memory one a byte load
 constexpr bool SG_VALUES_IN_REGISTERS = false;
@@ -235,6 +254,7 @@ __global__ void __launch_bounds__(256) sample_grids_v2_kernel(const SampleGridsV
   uint64_t* s_T = reinterpret_cast<uint64_t*>(s_stage + NT * gm * stage_pitch);   // [256] bucket thresholds
   const unsigned char* s_Q = reinterpret_cast<const unsigned char*>(s_T + 256);      // [256] q at bucket start
   unsigned char* s_q = reinterpret_cast<unsigned char*>(s_T + SAMPLE_TABLE_WORDS);   // [NT][128]
+  ulonglong2* s_J = reinterpret_cast<ulonglong2*>(s_q + NT * 128);                   // [2][128] segment-start jumps
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int tiy = tiy_lo + tid % nact, mloc = tid / nact;
@@ -266,13 +286,18 @@ __global__ void __launch_bounds__(256) sample_grids_v2_kernel(const SampleGridsV
   const int last_seg = (t1 > t0 && wc > 0) ? (t1 - t0 - 1) / a.seg_rows : 0;     // owner of the final state
 
   const int64_t gen = (int64_t)tix * ((int64_t)a.ty * a.num_maps) + (int64_t)m * a.ty + tiy;
+  if (seg > 0) {                                            // both width classes of this segment's jump (CTA-uniform)
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.jump) + (size_t)(seg - 1) * 2 * 128;
+    for (int i = tid; i < 2 * 128; i += nthreads) s_J[i] = __ldg(src + i);
+    __syncthreads();
+  }
   Xoro s{0, 0};
   if (active) {
     const ulonglong2 raw = reinterpret_cast<const ulonglong2*>(a.t[0].states)[gen];
     s.s0 = raw.x; s.s1 = raw.y;
     if (seg > 0 && r1 > r0 && wc > 0) {
       const int cls = (wc == ncol) ? 0 : 1;                 // full-width tile column or the narrower last one
-      xoro_jump(s, reinterpret_cast<const ulonglong2*>(a.jump) + ((size_t)(seg - 1) * 2 + cls) * 128);
+      xoro_jump_smem(s, s_J + cls * 128);
     }
   }
   // the draws of the segment's rows above the box are consumed without sampling (one xoroshiro step per cell), rows
@@ -389,6 +414,10 @@ __global__ void __launch_bounds__(256) sample_grids_v2_kernel(const SampleGridsV
 __global__ void __launch_bounds__(128) advance_states_kernel(const ulonglong2* __restrict__ in, ulonglong2* __restrict__ out0,
                                                              ulonglong2* __restrict__ out1, const ulonglong2* __restrict__ mats,
                                                              int rows, int cols, int tx, int ty, int num_maps) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ulonglong2* s_M = reinterpret_cast<ulonglong2*>(smem);      // the four tile-class matrices, 8 KB
+  for (int i = threadIdx.x; i < 4 * 128; i += blockDim.x) s_M[i] = __ldg(mats + i);
+  __syncthreads();
   const int64_t gen = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gen >= (int64_t)tx * ty * num_maps) return;
   const int tix = (int)(gen / ((int64_t)ty * num_maps)), tiy = (int)(gen % ty);
@@ -397,7 +426,7 @@ __global__ void __launch_bounds__(128) advance_states_kernel(const ulonglong2* _
   const int c0 = min(tiy * ncol, cols), c1 = min(c0 + ncol, cols);
   const ulonglong2 raw = in[gen];
   Xoro s{raw.x, raw.y};
-  if (t1 > t0 && c1 > c0) xoro_jump(s, mats + (((t1 - t0 == nrow) ? 0 : 2) + ((c1 - c0 == ncol) ? 0 : 1)) * 128);
+  if (t1 > t0 && c1 > c0) xoro_jump_smem(s, s_M + (((t1 - t0 == nrow) ? 0 : 2) + ((c1 - c0 == ncol) ? 0 : 1)) * 128);
   out0[gen] = make_ulonglong2(s.s0, s.s1);
   if (out1) out1[gen] = make_ulonglong2(s.s0, s.s1);
 }
@@ -407,7 +436,7 @@ __global__ void __launch_bounds__(128) advance_states_kernel(const ulonglong2* _
 void launch_advance_states(const uint64_t* states, uint64_t* out0, uint64_t* out1, const uint64_t* mats, int rows,
                            int cols, int tx, int ty, int num_maps, cudaStream_t st) {
   const int64_t total = (int64_t)tx * ty * num_maps;
-  advance_states_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+  advance_states_kernel<<<(unsigned)((total + 127) / 128), 128, 4 * 128 * 16, st>>>(
       reinterpret_cast<const ulonglong2*>(states), reinterpret_cast<ulonglong2*>(out0),
       reinterpret_cast<ulonglong2*>(out1), reinterpret_cast<const ulonglong2*>(mats), rows, cols, tx, ty, num_maps);
 }
@@ -433,7 +462,8 @@ size_t sample_grids_v2_smem(const SampleGridsV2Args& a, int nt) {
   const int wcols = v2_window_cols(a);
   const int row_bytes_al = (wcols * a.t[0].bpad + 15) & ~15;
   const int stage_pitch = (wcols + 15) & ~15;
-  return (size_t)nt * row_bytes_al + (size_t)nt * a.gm * stage_pitch + SAMPLE_TABLE_WORDS * 8 + (size_t)nt * 128;
+  return (size_t)nt * row_bytes_al + (size_t)nt * a.gm * stage_pitch + SAMPLE_TABLE_WORDS * 8 + (size_t)nt * 128 +
+         2 * 128 * 16;
 }
 
 static int v2_threads(const SampleGridsV2Args& a) { return ((a.nact * a.gm + 31) / 32) * 32; }

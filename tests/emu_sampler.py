@@ -150,12 +150,19 @@ extern "C" int emu_sample_v2(int nt, int8_t* grid0, int8_t* grid1, const int8_t*
     std::vector<uint64_t> mats(4 * 256);
     build_jump_matrices(ks, 4, mats.data());
     const int64_t total = (int64_t)tx * ty * num_maps;
-    blockDim = {128, 1, 1}; gridDim = {(unsigned)((total + 127) / 128), 1, 1};
-    for (int64_t g = 0; g < (int64_t)gridDim.x * 128; ++g) {
-      blockIdx = {(unsigned)(g / 128), 0, 0}; threadIdx = {(unsigned)(g % 128), 0, 0};
-      advance_states_kernel(reinterpret_cast<const ulonglong2*>(states), reinterpret_cast<ulonglong2*>(states_out),
-                            nt == 2 ? reinterpret_cast<ulonglong2*>(alt.data()) : nullptr,
-                            reinterpret_cast<const ulonglong2*>(mats.data()), rows, cols, tx, ty, num_maps);
+    const unsigned nblk = (unsigned)((total + 127) / 128);
+    for (unsigned bx = 0; bx < nblk; ++bx) {                   // 128 host threads per block (the kernel stages in shared memory)
+      std::barrier<> bar(128);
+      g_bar = &bar;
+      std::vector<std::thread> th;
+      for (int t = 0; t < 128; ++t)
+        th.emplace_back([&, t] {
+          threadIdx = {(unsigned)t, 0, 0}; blockIdx = {bx, 0, 0}; blockDim = {128, 1, 1}; gridDim = {nblk, 1, 1};
+          advance_states_kernel(reinterpret_cast<const ulonglong2*>(states), reinterpret_cast<ulonglong2*>(states_out),
+                                nt == 2 ? reinterpret_cast<ulonglong2*>(alt.data()) : nullptr,
+                                reinterpret_cast<const ulonglong2*>(mats.data()), rows, cols, tx, ty, num_maps);
+        });
+      for (auto& x : th) x.join();
     }
   }
   if (nt == 2 && std::memcmp(alt.data(), states_out, alt.size() * 8) != 0) return 2;   // both TDMs advance alike
