@@ -127,6 +127,7 @@ struct RolloutWinArgs {
   int ww, wh;               // the part of the window that lies inside the map: staged cells [0, ww) x [0, wh)
   int npad;                 // row length of noiseT
   int unit;                 // share granularity in chunks (set by launch_rollout_win)
+  int sync_passes;          // 1: chunks dealt pass by pass with a CTA barrier in between (short shares), 0: shared counter
   int stagger;              // cycles by which the warps of a scheduler are spread after a window barrier (0: none)
   const int8_t* lin_grid; const int8_t* ang_grid; const int8_t* obstacle; const int8_t* unknown;
   const float* noiseT;      // [T][npad] double2: clipped noisy controls (v, w), already widened to f64

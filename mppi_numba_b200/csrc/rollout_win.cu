@@ -395,13 +395,27 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
     const int8_t* __restrict__ g_ang = a.ang_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
 
-    for (;;) {
-      int c = 0;
-      if (lane == 0) c = atomicAdd(s_next, 1);
-      c = __shfl_sync(0xffffffffu, c, 0);
-      if (c >= c_hi) break;
-      const int n = (c << 5) + lane;
-      const bool live = n < p.N;                            // ragged last chunk (n is padded to whole warps): such lanes
+    // How the warps get their chunks.  Long shares: from the shared counter (a warp that is done takes the next chunk;
+    // the hardware favours some warps of a scheduler, they simply run more chunks).  Short shares (a.sync_passes: a few
+    // passes per CTA, e.g. a rank of an 8-GPU solve): pass by pass -- warp w takes chunk c_lo + 32*pass + w and the CTA
+    // meets at a barrier after every pass.  With the counter the favoured warps would run three or four of the CTA's
+    // ~64 chunks back to back while the others are still on their first, and those then finish alone at a fraction
+    // of the issue rate (measured: slowest SM 1.7x the average); per-pass barriers bound that lag to one chunk.
+    for (int pass = 0;; ++pass) {
+      int c;
+      if (a.sync_passes) {
+        if (c_lo + pass * (THREADS / 32) >= c_hi) break;    // CTA-uniform
+        if (pass > 0) __syncthreads();
+        c = c_lo + pass * (THREADS / 32) + (tid >> 5);
+      } else {
+        c = 0;
+        if (lane == 0) c = atomicAdd(s_next, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= c_hi) break;
+      }
+      const bool has = c < c_hi;                            // pass mode: no chunk left for this warp in the last pass
+      const int n = has ? (c << 5) + lane : lane;
+      const bool live = has && n < p.N;                     // ragged last chunk (n is padded to whole warps): such lanes
       const int Tn = live ? p.T : 0;                        // run zero steps and store nothing, but stay with their warp
     const double2* __restrict__ ep = reinterpret_cast<const double2*>(a.noiseT) + n;
     float x = p.x0[0], y = p.x0[1], th = p.x0[2];
@@ -523,6 +537,7 @@ bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int
 }
 
 constexpr int WIN_THREADS = 1024;
+constexpr int WIN_SYNC_MAX_PASSES = 4;    // shares of at most this many passes are run pass by pass (see the kernel)
 constexpr int WIN_STAGGER_DEFAULT = 0;    // cycles between the warps of a scheduler after a window barrier (B200MPPI_WIN_STAGGER)
 constexpr int WIN_XR_DEFAULT = 0;         // measured on B200: see profiles/ (B200MPPI_WIN_XR sweeps it)
 static int win_grid_override = 0;         // B200MPPI_WIN_GRID (tuning / test hook): number of persistent CTAs
@@ -594,10 +609,18 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
     stagger_read = true;
   }
   b.stagger = stagger;
+  static int sync_mode = -1;                                // B200MPPI_WIN_SYNC = 0 | 1 (A/B hook), default: by share length
+  static bool sync_read = false;
+  if (!sync_read) {
+    if (const char* e = getenv("B200MPPI_WIN_SYNC")) sync_mode = atoi(e);
+    sync_read = true;
+  }
   // whole passes (32 chunks) per share as soon as every CTA gets at least one: a share cut at arbitrary chunks splits
   // into map segments like 33 + 22 chunks = three partial passes where 32 + 23 or 64 would be two (measured on a rank
   // of an 8-GPU solve, 55 chunks per CTA: slowest SM 1.7x the average)
   b.unit = (total / (32LL * grid.x) >= 1) ? 32 : 1;
+  const long long passes = (total + 32LL * grid.x - 1) / (32LL * grid.x);
+  b.sync_passes = sync_mode >= 0 ? (sync_mode != 0) : (passes <= WIN_SYNC_MAX_PASSES);
   const CUtensorMap& t0 = *reinterpret_cast<const CUtensorMap*>(tm_lin);
   const CUtensorMap& t1 = *reinterpret_cast<const CUtensorMap*>(tm_ang);
   const CUtensorMap& t2 = *reinterpret_cast<const CUtensorMap*>(tm_obs);
