@@ -395,12 +395,11 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
     const int8_t* __restrict__ g_ang = a.ang_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
 
-    // How the warps get their chunks.  Long shares: from the shared counter (a warp that is done takes the next chunk;
-    // the hardware favours some warps of a scheduler, they simply run more chunks).  Short shares (a.sync_passes: a few
-    // passes per CTA, e.g. a rank of an 8-GPU solve): pass by pass -- warp w takes chunk c_lo + 32*pass + w and the CTA
-    // meets at a barrier after every pass.  With the counter the favoured warps would run three or four of the CTA's
-    // ~64 chunks back to back while the others are still on their first, and those then finish alone at a fraction
-    // of the issue rate (measured: slowest SM 1.7x the average); per-pass barriers bound that lag to one chunk.
+    // How the warps get their chunks: from the shared counter (a warp that is done takes the next chunk; the hardware
+    // favours some warps of a scheduler, they simply run more chunks and the issue slots stay full).  The alternative
+    // kept for A/B timing (a.sync_passes, B200MPPI_WIN_SYNC=1): pass by pass -- warp w takes chunk c_lo + 32*pass + w and
+    // the CTA meets at a barrier after every pass.  It is slower even for two-pass shares: a pass started in lockstep
+    // ends with its low-priority warps running alone at a fraction of the issue rate.
     for (int pass = 0;; ++pass) {
       int c;
       if (a.sync_passes) {
@@ -537,7 +536,10 @@ bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int
 }
 
 constexpr int WIN_THREADS = 1024;
-constexpr int WIN_SYNC_MAX_PASSES = 4;    // shares of at most this many passes are run pass by pass (see the kernel)
+constexpr int WIN_SYNC_MAX_PASSES = 0;    // shares of at most this many passes are run pass by pass (see the kernel);
+                                          // 0 = never: measured on a rank of an 8-GPU solve (2 passes per CTA) 0.207 ms
+                                          // against 0.186 ms with the shared counter -- a pass started in lockstep ends
+                                          // with its low-priority warps alone, the counter keeps the favoured warps busy
 constexpr int WIN_STAGGER_DEFAULT = 0;    // cycles between the warps of a scheduler after a window barrier (B200MPPI_WIN_STAGGER)
 constexpr int WIN_XR_DEFAULT = 0;         // measured on B200: see profiles/ (B200MPPI_WIN_XR sweeps it)
 static int win_grid_override = 0;         // B200MPPI_WIN_GRID (tuning / test hook): number of persistent CTAs
