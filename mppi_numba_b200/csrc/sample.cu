@@ -251,10 +251,12 @@ __global__ void __launch_bounds__(256) sample_grids_v2_kernel(const SampleGridsV
   const int gm = a.gm;
   unsigned char* s_cum = smem;                               // [NT][row_bytes_al]
   unsigned char* s_stage = s_cum + NT * row_bytes_al;        // [NT][gm][stage_pitch]
-  uint64_t* s_T = reinterpret_cast<uint64_t*>(s_stage + NT * gm * stage_pitch);   // [256] bucket thresholds
+  uint64_t* s_T = reinterpret_cast<uint64_t*>(s_stage + max(NT * gm * stage_pitch, 2 * 128 * 16));   // [256] bucket thresholds
   const unsigned char* s_Q = reinterpret_cast<const unsigned char*>(s_T + 256);      // [256] q at bucket start
   unsigned char* s_q = reinterpret_cast<unsigned char*>(s_T + SAMPLE_TABLE_WORDS);   // [NT][128]
-  ulonglong2* s_J = reinterpret_cast<ulonglong2*>(s_q + NT * 128);                   // [2][128] segment-start jumps
+  // [2][128] segment-start jump matrices: they live in the (not yet used) output stage -- every thread has applied
+  // them before the row loop's first barrier, after which the stage is written
+  ulonglong2* s_J = reinterpret_cast<ulonglong2*>(s_stage);
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int tiy = tiy_lo + tid % nact, mloc = tid / nact;
@@ -462,8 +464,8 @@ size_t sample_grids_v2_smem(const SampleGridsV2Args& a, int nt) {
   const int wcols = v2_window_cols(a);
   const int row_bytes_al = (wcols * a.t[0].bpad + 15) & ~15;
   const int stage_pitch = (wcols + 15) & ~15;
-  return (size_t)nt * row_bytes_al + (size_t)nt * a.gm * stage_pitch + SAMPLE_TABLE_WORDS * 8 + (size_t)nt * 128 +
-         2 * 128 * 16;
+  const size_t stage = std::max((size_t)nt * a.gm * stage_pitch, (size_t)2 * 128 * 16);     // the jump matrices overlay it
+  return (size_t)nt * row_bytes_al + stage + SAMPLE_TABLE_WORDS * 8 + (size_t)nt * 128;
 }
 
 static int v2_threads(const SampleGridsV2Args& a) { return ((a.nact * a.gm + 31) / 32) * 32; }
