@@ -272,6 +272,10 @@ int b200mppi_planner_synchronize(b200mppi_planner* pl);
 int b200mppi_debug_sample_threshold(double alpha_dyn, int32_t q_cap, const uint64_t* draws, int64_t n,
                                     uint8_t* q_out);
 
+/* Debug hook: per-CTA start / end times (ns) and chunk shares of the windowed rollout kernel's launches that follow
+ * (enable != 0), read back into out[4 * ctas] (tools/rollout_cta_times.py). */
+int b200mppi_debug_rollout_cta_times(int32_t enable, int64_t* out, int32_t ctas);
+
 /* Tracing: CUDA-event time of each stage of the last solve/solve_local+finish, milliseconds.
  * Enabled with b200mppi_planner_set_profiling(pl, 1) (adds event records, no syncs). */
 enum {

@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   const float inv_lo = inv_res * (1.0f - 2.4e-7f), inv_hi = inv_res * (1.0f + 2.4e-7f);
   const unsigned uww = (unsigned)a.ww, uwh = (unsigned)a.wh;     // staged AND inside the map (<= WW, WH)
 
+  const long long dbg_t0 = a.dbg ? (long long)globaltimer_ns() : 0;
   uint32_t phase = 0;
   for (long long w = w_lo; w < w_hi;) {
     const int m = (int)(w / cpm);
@@ -484,6 +485,12 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     if (live) *cost_ptr(a.dst, m, n) = cost;                // map-major: the warp's 32 lanes store one 128-byte line
     }
   }
+  if (a.dbg && tid == 0) {                                  // per-CTA wall time (tools/rollout_cta_times.py)
+    a.dbg[4 * blockIdx.x + 0] = dbg_t0;
+    a.dbg[4 * blockIdx.x + 1] = (long long)globaltimer_ns();
+    a.dbg[4 * blockIdx.x + 2] = w_lo;
+    a.dbg[4 * blockIdx.x + 3] = w_hi;
+  }
   // sharded solve, peer-memory exchange: the costs above went straight into the receive buffers of the ranks that
   // reduce them; the LAST CTA to get here raises this rank's epoch flag in every peer (p2p.cu has the protocol)
   if (a.sig.ws > 0) {
@@ -536,6 +543,8 @@ bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int
 }
 
 constexpr int WIN_THREADS = 1024;
+static long long* win_debug_buffer = nullptr;   // b200mppi_debug_rollout_cta_times: 4 x int64 per CTA (start ns, end ns, share)
+void rollout_win_set_debug(long long* dev) { win_debug_buffer = dev; }
 constexpr int WIN_SYNC_MAX_PASSES = 0;    // shares of at most this many passes are run pass by pass (see the kernel);
                                           // 0 = never: measured on a rank of an 8-GPU solve (2 passes per CTA) 0.207 ms
                                           // against 0.186 ms with the shared counter -- a pass started in lockstep ends
@@ -611,16 +620,17 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
     stagger_read = true;
   }
   b.stagger = stagger;
+  b.dbg = win_debug_buffer;
   static int sync_mode = -1;                                // B200MPPI_WIN_SYNC = 0 | 1 (A/B hook), default: by share length
   static bool sync_read = false;
   if (!sync_read) {
     if (const char* e = getenv("B200MPPI_WIN_SYNC")) sync_mode = atoi(e);
     sync_read = true;
   }
-  // whole passes (32 chunks) per share as soon as every CTA gets at least one: a share cut at arbitrary chunks splits
-  // into map segments like 33 + 22 chunks = three partial passes where 32 + 23 or 64 would be two (measured on a rank
-  // of an 8-GPU solve, 55 chunks per CTA: slowest SM 1.7x the average)
-  b.unit = (total / (32LL * grid.x) >= 1) ? 32 : 1;
+  // whole passes (32 chunks) per share once a share is at least 4 passes long (no end-of-segment stragglers); shorter
+  // shares stay chunk-granular: rounding 3.46 passes per CTA (a rank of a 4-GPU solve) to 3 or 4 costs more than it
+  // saves (measured 0.387 against 0.308 ms)
+  b.unit = (total / (32LL * grid.x) >= 4) ? 32 : 1;
   const long long passes = (total + 32LL * grid.x - 1) / (32LL * grid.x);
   b.sync_passes = sync_mode >= 0 ? (sync_mode != 0) : (passes <= WIN_SYNC_MAX_PASSES);
   const CUtensorMap& t0 = *reinterpret_cast<const CUtensorMap*>(tm_lin);

@@ -64,6 +64,7 @@ static inline int __shfl_sync(unsigned, int v, int src) {
   return r;
 }
 static inline long long clock64() { return 0; }
+static inline unsigned long long globaltimer_ns() { return 0; }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }

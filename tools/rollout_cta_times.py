@@ -1,0 +1,44 @@
+"""Per-CTA wall times of the persistent rollout kernel for one rank of a G-rank solve (run alone on one GPU).
+    python tools/rollout_cta_times.py c5 8"""
+import contextlib, ctypes as C, io, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import mppi_numba_b200 as E
+from mppi_numba_b200._lib import lib, check
+from bench import build_scenario
+name, G = sys.argv[1], int(sys.argv[2])
+sc = build_scenario(name)
+with contextlib.redirect_stdout(io.StringIO()):
+    cfg = E.Config(**sc["cfg"])
+    lin, ang = E.TDM_Numba(cfg, rank=0, world_size=G), E.TDM_Numba(cfg, rank=0, world_size=G)
+    lin.set_TDM_from_PMF_grid(sc["pmf_lin"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+    ang.set_TDM_from_PMF_grid(sc["pmf_ang"], sc["tdm_dict"], sc["obstacle"], sc["unknown"])
+    pl = E.MPPI_Numba(cfg, rank=0, world_size=G)
+    pl.setup(sc["params"], lin, ang)
+pl.move_mppi_task_vars_to_device()
+def solve():
+    if G == 1: pl.solve()
+    else:
+        check(lib.b200mppi_planner_solve_local(pl._handle, 1)); check(lib.b200mppi_planner_synchronize(pl._handle))
+for _ in range(6): solve()
+out = np.zeros((148, 4), np.int64)
+check(lib.b200mppi_debug_rollout_cta_times(1, None, 0))
+solve()
+check(lib.b200mppi_debug_rollout_cta_times(0, out.ctypes.data_as(C.c_void_p), 148))
+t0 = out[:, 0].min()
+dur = (out[:, 1] - out[:, 0]) / 1e3
+start = (out[:, 0] - t0) / 1e3
+end = (out[:, 1] - t0) / 1e3
+M = sc["M"] // G
+cpm = (sc["N"] + 31) // 32
+print("kernel span %.1f us; CTA duration min/median/max %.1f / %.1f / %.1f us; latest start %.1f us" % (end.max(), dur.min(), np.median(dur), dur.max(), start.max()))
+order = np.argsort(-dur)
+for b in list(order[:12]) + list(order[-4:]):
+    lo, hi = out[b, 2], out[b, 3]
+    segs = []
+    w = lo
+    while w < hi:
+        m = w // cpm
+        e = min(hi, (m + 1) * cpm)
+        segs.append(int(e - w)); w = e
+    print("cta %3d dur %6.1f us start %5.1f chunks %3d segments %s" % (b, dur[b], start[b], hi - lo, segs))
