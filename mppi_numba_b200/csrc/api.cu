@@ -1630,16 +1630,18 @@ extern "C" int b200mppi_planner_last_timings(b200mppi_planner* p, float* ms) {
 }
 
 // Debug hook (tools/rollout_cta_times.py): per-CTA start / end times (ns, %globaltimer) and chunk shares of the NEXT
-// windowed rollout launches of this process; enable = 0 switches it off.  out: 4 x int64 per CTA, `ctas` records.
+// windowed rollout launches of this process; enable = 0 switches it off.  out: 6 x int64 per CTA (start ns, end ns, share
+// lo / hi in chunks, lane-steps on the slow path, of which outside the staged window), `ctas` records.
 extern "C" int b200mppi_debug_rollout_cta_times(int32_t enable, int64_t* out, int32_t ctas) {
   static long long* dev = nullptr;
   if (enable) {
-    if (!dev) { CU(cudaMalloc(&dev, 1024 * 4 * sizeof(long long))); CU(cudaMemset(dev, 0, 1024 * 4 * sizeof(long long))); }
+    if (!dev) CU(cudaMalloc(&dev, 1024 * 6 * sizeof(long long)));
+    CU(cudaMemset(dev, 0, 1024 * 6 * sizeof(long long)));
     rollout_win_set_debug(dev);
   }
   if (out && dev && ctas > 0 && ctas <= 1024) {
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(out, dev, (size_t)ctas * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, dev, (size_t)ctas * 6 * sizeof(long long), cudaMemcpyDeviceToHost));
   }
   if (!enable) rollout_win_set_debug(nullptr);
   return B200MPPI_OK;

@@ -447,6 +447,11 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
         const uint32_t ad = sb_win + (uint32_t)(wy * WW + wx);
         ql = lds_s8(ad, 0); qa = lds_s8(ad, PLANE); ob = lds_s8(ad, 2 * PLANE); un = lds_s8(ad, 3 * PLANE);
       } else {
+        if (a.dbg) {                                        // debug hook: lane-steps on the slow path / outside the window
+          atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 6 * blockIdx.x + 4, 1ull);
+          if (!(((unsigned)wx < uww) & ((unsigned)wy < uwh)))
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 6 * blockIdx.x + 5, 1ull);
+        }
         const int pk = lookup_slow(ax, ay, res, sb_win, uww, uwh, WW, PLANE, a.wx0, a.wy0, p.g.rows, p.g.cols, p.g.grid_rows,
                                    p.g.grid_cols, p.g.grid_pitch, p.g.mask_pitch, g_lin, g_ang, a.obstacle, a.unknown);
         ql = (int)(int8_t)pk; qa = (int)(int8_t)(pk >> 8); ob = (int)(int8_t)(pk >> 16); un = pk >> 24;
@@ -486,10 +491,10 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     }
   }
   if (a.dbg && tid == 0) {                                  // per-CTA wall time (tools/rollout_cta_times.py)
-    a.dbg[4 * blockIdx.x + 0] = dbg_t0;
-    a.dbg[4 * blockIdx.x + 1] = (long long)globaltimer_ns();
-    a.dbg[4 * blockIdx.x + 2] = w_lo;
-    a.dbg[4 * blockIdx.x + 3] = w_hi;
+    a.dbg[6 * blockIdx.x + 0] = dbg_t0;
+    a.dbg[6 * blockIdx.x + 1] = (long long)globaltimer_ns();
+    a.dbg[6 * blockIdx.x + 2] = w_lo;
+    a.dbg[6 * blockIdx.x + 3] = w_hi;
   }
   // sharded solve, peer-memory exchange: the costs above went straight into the receive buffers of the ranks that
   // reduce them; the LAST CTA to get here raises this rank's epoch flag in every peer (p2p.cu has the protocol)
@@ -543,7 +548,8 @@ bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int
 }
 
 constexpr int WIN_THREADS = 1024;
-static long long* win_debug_buffer = nullptr;   // b200mppi_debug_rollout_cta_times: 4 x int64 per CTA (start ns, end ns, share)
+static long long* win_debug_buffer = nullptr;   // b200mppi_debug_rollout_cta_times: 6 x int64 per CTA (start ns, end ns, share lo / hi,
+                                                // lane-steps on the slow path, of which outside the window)
 void rollout_win_set_debug(long long* dev) { win_debug_buffer = dev; }
 constexpr int WIN_SYNC_MAX_PASSES = 0;    // shares of at most this many passes are run pass by pass (see the kernel);
                                           // 0 = never: measured on a rank of an 8-GPU solve (2 passes per CTA) 0.207 ms

@@ -21,7 +21,7 @@ def solve():
     else:
         check(lib.b200mppi_planner_solve_local(pl._handle, 1)); check(lib.b200mppi_planner_synchronize(pl._handle))
 for _ in range(6): solve()
-out = np.zeros((148, 4), np.int64)
+out = np.zeros((148, 6), np.int64)
 check(lib.b200mppi_debug_rollout_cta_times(1, None, 0))
 solve()
 check(lib.b200mppi_debug_rollout_cta_times(0, out.ctypes.data_as(C.c_void_p), 148))
@@ -41,4 +41,9 @@ for b in list(order[:12]) + list(order[-4:]):
         m = w // cpm
         e = min(hi, (m + 1) * cpm)
         segs.append(int(e - w)); w = e
-    print("cta %3d dur %6.1f us start %5.1f chunks %3d segments %s" % (b, dur[b], start[b], hi - lo, segs))
+    steps = (hi - lo) * 32 * sc["T"]
+    print("cta %3d dur %6.1f us chunks %3d segments %s slow %.3f of lane-steps, outside window %.3f" % (
+        b, dur[b], hi - lo, segs, out[b, 4] / steps, out[b, 5] / steps), flush=True)
+tot = ((out[:, 3] - out[:, 2]) * 32 * sc["T"]).sum()
+print("all CTAs: slow path %.4f of lane-steps, outside the window %.4f; corr(duration, outside) = %.2f" % (
+    out[:, 4].sum() / tot, out[:, 5].sum() / tot, np.corrcoef(dur, out[:, 5] / ((out[:, 3] - out[:, 2]) * 32 * sc["T"]))[0, 1]))
