@@ -493,7 +493,9 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   if (a.dbg && tid == 0) {                                  // per-CTA wall time (tools/rollout_cta_times.py)
     a.dbg[6 * blockIdx.x + 0] = dbg_t0;
     a.dbg[6 * blockIdx.x + 1] = (long long)globaltimer_ns();
-    a.dbg[6 * blockIdx.x + 2] = w_lo;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.dbg[6 * blockIdx.x + 2] = w_lo | ((long long)smid << 40);           // SM id in the upper bits
     a.dbg[6 * blockIdx.x + 3] = w_hi;
   }
   // sharded solve, peer-memory exchange: the costs above went straight into the receive buffers of the ranks that

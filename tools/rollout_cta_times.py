@@ -25,6 +25,8 @@ out = np.zeros((148, 6), np.int64)
 check(lib.b200mppi_debug_rollout_cta_times(1, None, 0))
 solve()
 check(lib.b200mppi_debug_rollout_cta_times(0, out.ctypes.data_as(C.c_void_p), 148))
+smid = out[:, 2] >> 40
+out[:, 2] &= (1 << 40) - 1
 t0 = out[:, 0].min()
 dur = (out[:, 1] - out[:, 0]) / 1e3
 start = (out[:, 0] - t0) / 1e3
@@ -47,3 +49,16 @@ for b in list(order[:12]) + list(order[-4:]):
 tot = ((out[:, 3] - out[:, 2]) * 32 * sc["T"]).sum()
 print("all CTAs: slow path %.4f of lane-steps, outside the window %.4f; corr(duration, outside) = %.2f" % (
     out[:, 4].sum() / tot, out[:, 5].sum() / tot, np.corrcoef(dur, out[:, 5] / ((out[:, 3] - out[:, 2]) * 32 * sc["T"]))[0, 1]))
+
+print("by SM id (duration us):")
+o = np.argsort(smid)
+line = []
+for b in o:
+    line.append("%d:%.0f" % (smid[b], dur[b]))
+print(" ".join(line))
+pair = {}
+for b in range(len(dur)):
+    pair.setdefault(int(smid[b]) // 2, []).append(dur[b])
+both = [v for v in pair.values() if len(v) == 2]
+print("SM pairs (smid // 2) with both SMs busy: %d; mean |difference| within a pair %.1f us; mean of pair minima %.1f, maxima %.1f" % (
+    len(both), np.mean([abs(v[0] - v[1]) for v in both]), np.mean([min(v) for v in both]), np.mean([max(v) for v in both])))
