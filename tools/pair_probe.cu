@@ -1,0 +1,63 @@
+// Which SM resource is shared between SMs?  One CTA (one SM busy) against 148 CTAs (all SMs busy) of the same
+// per-thread loop of ONE instruction type: if the per-SM rate drops when the neighbours work, the unit is shared.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/pair_probe tools/pair_probe.cu && /tmp/pair_probe
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <int OP>
+__global__ void __launch_bounds__(1024) probe(float* out, int iters, float seed) {
+  float a0 = seed + threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  double d0 = a0, d1 = a1, d2 = a2, d3 = a3;
+  for (int i = 0; i < iters; ++i) {
+    if (OP == 0) {        // MUFU.SIN
+      asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(a0)); asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(a1));
+      asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(a2)); asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(a3));
+    } else if (OP == 1) { // F2F.F64.F32 + F2F.F32.F64 round trip
+      asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d0) : "f"(a0)); asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(a0) : "d"(d0));
+      asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d1) : "f"(a1)); asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(a1) : "d"(d1));
+    } else if (OP == 2) { // DFMA
+      asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d0) : "d"(d1), "d"(d2)); asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d3) : "d"(d1), "d"(d2));
+      asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d1) : "d"(d2), "d"(d3)); asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d2) : "d"(d3), "d"(d0));
+    } else if (OP == 3) { // FFMA
+      asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a0) : "f"(a1), "f"(a2)); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a3) : "f"(a1), "f"(a2));
+      asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a1) : "f"(a2), "f"(a3)); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a2) : "f"(a3), "f"(a0));
+    } else if (OP == 4) { // integer LOP3 / IADD mix
+      unsigned u0 = __float_as_uint(a0), u1 = __float_as_uint(a1);
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(u0) : "r"(u1)); asm volatile("xor.b32 %0, %0, %1;" : "+r"(u1) : "r"(u0));
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(u0) : "r"(u1)); asm volatile("xor.b32 %0, %0, %1;" : "+r"(u1) : "r"(u0));
+      a0 = __uint_as_float(u0); a1 = __uint_as_float(u1);
+    } else if (OP == 5) { // MUFU.SQRT
+      asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(a0)); asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(a1));
+      asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(a2)); asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(a3));
+    }
+  }
+  if (a0 + a1 + a2 + a3 + (float)(d0 + d1 + d2 + d3) == 12345.678f) out[0] = a0;
+}
+
+template <int OP>
+void run(const char* name, int iters) {
+  float* out; cudaMalloc(&out, 4);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float ms[3];
+  const int grids[3] = {1, 74, 148};
+  for (int k = 0; k < 3; ++k) {
+    probe<OP><<<grids[k], 1024>>>(out, iters, 1.0f);            // warm-up
+    cudaEventRecord(e0);
+    probe<OP><<<grids[k], 1024>>>(out, iters, 1.0f);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms[k], e0, e1);
+  }
+  printf("%-28s 1 CTA %.3f ms | 74 CTAs %.3f ms (x%.2f) | 148 CTAs %.3f ms (x%.2f)\n", name, ms[0], ms[1], ms[1] / ms[0], ms[2], ms[2] / ms[0]);
+  cudaFree(out);
+}
+
+int main() {
+  const int it = 20000;
+  run<3>("FFMA", it);
+  run<4>("IADD/LOP3", it);
+  run<0>("MUFU.SIN", it);
+  run<5>("MUFU.SQRT", it);
+  run<1>("F2F f32<->f64 round trip", it);
+  run<2>("DFMA", it);
+  return 0;
+}
