@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const int n = has ? (c << 5) + lane : lane;
       const bool live = has && n < p.N;                     // ragged last chunk (n is padded to whole warps): such lanes
       const int Tn = live ? p.T : 0;                        // run zero steps and store nothing, but stay with their warp
-    const double2* __restrict__ ep = reinterpret_cast<const double2*>(a.noiseT) + n;
+    const double2* __restrict__ ep = reinterpret_cast<const double2*>(a.noiseT) + (a.stagger < 0 ? (n & ~31) : n);   // DIAG: stagger < 0 = one address per warp
     float x = p.x0[0], y = p.x0[1], th = p.x0[2];
     // the float64 state is carried UNROUNDED across the back edge (rx, ry, rt: the float64 FMA results, initially the
     // float32 state itself) and rounded to float32 precision at the top of the next step: the FMA of a step then

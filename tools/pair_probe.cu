@@ -34,6 +34,44 @@ __global__ void __launch_bounds__(1024) probe(float* out, int iters, float seed)
   if (a0 + a1 + a2 + a3 + (float)(d0 + d1 + d2 + d3) == 12345.678f) out[0] = a0;
 }
 
+// L2-resident stream: every thread loads 16 B per iteration, coalesced (512 B per warp), from an 8 MB buffer, with
+// `pad` FFMA per load in between (the rollout kernel: ~74 instructions per 512 B)
+template <int PAD>
+__global__ void __launch_bounds__(1024) stream(const double2* __restrict__ src, float* out, int iters, int words) {
+  const int gt = blockIdx.x * 1024 + threadIdx.x;
+  double acc = 0.0; float f = threadIdx.x;
+  int idx = gt % words;
+  for (int i = 0; i < iters; ++i) {
+    const double2 v = __ldg(src + idx);
+    idx += 8192; if (idx >= words) idx -= words;
+    acc += v.x + v.y;
+#pragma unroll
+    for (int k = 0; k < PAD; ++k) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(f));
+  }
+  if (acc + f == 12345.678) out[0] = (float)acc;
+}
+
+template <int PAD>
+void run_stream(const char* name, int iters) {
+  const int words = 8 << 16;                                        // 8 MB of double2
+  double2* src; cudaMalloc(&src, (size_t)words * 16); cudaMemset(src, 0, (size_t)words * 16);
+  float* out; cudaMalloc(&out, 4);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float ms[3];
+  const int grids[3] = {1, 74, 148};
+  for (int k = 0; k < 3; ++k) {
+    stream<PAD><<<grids[k], 1024>>>(src, out, iters, words);
+    cudaEventRecord(e0);
+    stream<PAD><<<grids[k], 1024>>>(src, out, iters, words);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms[k], e0, e1);
+  }
+  const double gb = 1024.0 * 16 * iters / 1e6;                      // MB per CTA
+  printf("%-28s 1 CTA %.3f ms (%.0f GB/s/SM) | 74 CTAs %.3f ms (x%.2f) | 148 CTAs %.3f ms (x%.2f, %.0f GB/s/SM, %.2f TB/s)\n", name, ms[0],
+         gb / ms[0], ms[1], ms[1] / ms[0], ms[2], ms[2] / ms[0], gb / ms[2], gb * 148 / ms[2] / 1e3);
+  cudaFree(src); cudaFree(out);
+}
+
 template <int OP>
 void run(const char* name, int iters) {
   float* out; cudaMalloc(&out, 4);
@@ -59,5 +97,9 @@ int main() {
   run<5>("MUFU.SQRT", it);
   run<1>("F2F f32<->f64 round trip", it);
   run<2>("DFMA", it);
+  run_stream<0>("L2 stream 16 B/thread", 4000);
+  run_stream<16>("L2 stream + 16 FFMA", 4000);
+  run_stream<32>("L2 stream + 32 FFMA", 4000);
+  run_stream<64>("L2 stream + 64 FFMA", 4000);
   return 0;
 }
