@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const int n = has ? (c << 5) + lane : lane;
       const bool live = has && n < p.N;                     // ragged last chunk (n is padded to whole warps): such lanes
       const int Tn = live ? p.T : 0;                        // run zero steps and store nothing, but stay with their warp
-    const double2* __restrict__ ep = reinterpret_cast<const double2*>(a.noiseT) + (a.stagger < 0 ? (n & ~31) : n);   // DIAG: stagger < 0 = one address per warp
+    const double2* __restrict__ ep = reinterpret_cast<const double2*>(a.noiseT) + (a.stagger == -1 ? (n & ~31) : a.stagger == -2 ? (n & ~31) + (lane >> 1) : a.stagger == -3 ? (n & ~31) + (lane >> 2) : n);   // DIAG
     float x = p.x0[0], y = p.x0[1], th = p.x0[2];
     // the float64 state is carried UNROUNDED across the back edge (rx, ry, rt: the float64 FMA results, initially the
     // float32 state itself) and rounded to float32 precision at the top of the next step: the FMA of a step then
@@ -472,7 +472,12 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), c2.y, th64);
       // `c2` is dead from here on: fetch the next step's controls straight into it -- the rest of this step and the
       // cell lookup of the next one (~70 instructions per warp, 32 warps per SM) cover the L2 latency
-      c2 = __ldg(ep);                                       // (row T exists: the buffer has T + 1 rows, no guard needed)
+      if (a.stagger > -4) c2 = __ldg(ep);
+      else if (a.stagger == -4) c2 = __ldcg(ep);
+      else if (a.stagger == -5) asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(c2.x), "=d"(c2.y) : "l"(ep));
+      else if (a.stagger == -6) { c2.x = __ldg(&ep->x); c2.y = __ldg(&ep->y); }
+      else asm volatile("ld.global.nc.L1::evict_first.v2.f64 {%0, %1}, [%2];" : "=d"(c2.x), "=d"(c2.y) : "l"(ep));
+      // DIAG (row T exists: the buffer has T + 1 rows, no guard needed)
       x = narrow(rx); y = narrow(ry); th = narrow(rt);
       // ---- stage cost (mppi.py:696-701)
       const float dx = fsub(gx, x), dy = fsub(gy, y);

@@ -51,6 +51,59 @@ __global__ void __launch_bounds__(1024) stream(const double2* __restrict__ src, 
   if (acc + f == 12345.678) out[0] = (float)acc;
 }
 
+// the same stream in the rollout kernel's setting: one 1024-thread CTA per SM holding 222 KB of shared memory (what is
+// left of the 256 KB is the L1), 4 byte loads from shared memory per iteration; per-CTA durations by globaltimer
+template <int PAD>
+__global__ void __launch_bounds__(1024) stream_smem(const double2* __restrict__ src, float* out, int iters, int words, int bcast,
+                                                    long long* dur) {
+  extern __shared__ signed char win[];
+  const int gt = blockIdx.x * 1024 + threadIdx.x;
+  for (int i = threadIdx.x; i < 222 * 1024; i += 1024) win[i] = (signed char)i;
+  __syncthreads();
+  long long t0 = 0;
+  if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  double acc = 0.0; float f = threadIdx.x;
+  int idx = (bcast ? (gt & ~31) : gt) % words;
+  unsigned h = gt * 2654435761u;
+  for (int i = 0; i < iters; ++i) {
+    const double2 v = __ldg(src + idx);
+    idx += 8192; if (idx >= words) idx -= words;
+    h = h * 1664525u + 1013904223u;
+    const int a0 = (h >> 8) % (55 * 1024);
+    acc += v.x + v.y + win[a0] + win[a0 + 55 * 1024] + win[a0 + 110 * 1024] + win[a0 + 165 * 1024];
+#pragma unroll
+    for (int k = 0; k < PAD; ++k) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(f));
+  }
+  if (acc + f == 12345.678) out[0] = (float)acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); dur[blockIdx.x] = t1 - t0; }
+}
+
+#include <algorithm>
+#include <vector>
+template <int PAD>
+void run_stream_smem(const char* name, int iters, int bcast) {
+  const int words = 1 << 20;                                        // 16 MB of double2
+  double2* src; cudaMalloc(&src, (size_t)words * 16); cudaMemset(src, 0, (size_t)words * 16);
+  float* out; cudaMalloc(&out, 4);
+  long long* dur; cudaMalloc(&dur, 148 * 8);
+  cudaFuncSetAttribute(stream_smem<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+  const int grids[2] = {1, 148};
+  printf("%-34s", name);
+  for (int k = 0; k < 2; ++k) {
+    stream_smem<PAD><<<grids[k], 1024, 222 * 1024>>>(src, out, iters, words, bcast, dur);
+    stream_smem<PAD><<<grids[k], 1024, 222 * 1024>>>(src, out, iters, words, bcast, dur);
+    cudaDeviceSynchronize();
+    std::vector<long long> d(grids[k]);
+    cudaMemcpy(d.data(), dur, grids[k] * 8, cudaMemcpyDeviceToHost);
+    std::sort(d.begin(), d.end());
+    printf(" | %3d CTAs: per-CTA us min %.1f  p25 %.1f  median %.1f  p75 %.1f  max %.1f", grids[k], d[0] / 1e3, d[d.size() / 4] / 1e3,
+           d[d.size() / 2] / 1e3, d[d.size() * 3 / 4] / 1e3, d.back() / 1e3);
+  }
+  printf("\n");
+  cudaFree(src); cudaFree(out); cudaFree(dur);
+}
+
 template <int PAD>
 void run_stream(const char* name, int iters) {
   const int words = 8 << 16;                                        // 8 MB of double2
@@ -101,5 +154,8 @@ int main() {
   run_stream<16>("L2 stream + 16 FFMA", 4000);
   run_stream<32>("L2 stream + 32 FFMA", 4000);
   run_stream<64>("L2 stream + 64 FFMA", 4000);
+  run_stream_smem<32>("222KB smem, stream + 32 FFMA", 2000, 0);
+  run_stream_smem<64>("222KB smem, stream + 64 FFMA", 2000, 0);
+  run_stream_smem<64>("222KB smem, bcast  + 64 FFMA", 2000, 1);
   return 0;
 }
