@@ -273,8 +273,8 @@ int b200mppi_debug_sample_threshold(double alpha_dyn, int32_t q_cap, const uint6
                                     uint8_t* q_out);
 
 /* Debug hook: per-CTA start / end times (ns) and chunk shares of the windowed rollout kernel's launches that follow
- * (enable != 0), read back into out[6 * ctas]: start, end, share lo / hi, lane-steps on the slow path, of which outside
- * the staged window (tools/rollout_cta_times.py). */
+ * (enable != 0), read back into out[6 * ctas]: start, end, share lo / hi (SM id in bits 40+ of lo), lane-steps on the slow
+ * path, of which outside the staged window (bits 40+: warp-steps run) (tools/rollout_cta_times.py). */
 int b200mppi_debug_rollout_cta_times(int32_t enable, int64_t* out, int32_t ctas);
 
 /* Tracing: CUDA-event time of each stage of the last solve/solve_local+finish, milliseconds.

@@ -331,9 +331,24 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   // share boundaries are multiples of a.unit chunks (32 = one chunk per warp of the CTA when the shares are long
   // enough: every map segment is then a whole number of passes and all warps reach the end-of-segment barrier
   // together -- ncu showed 0.8 of 7.8 warps parked there with chunk-granular shares; 1 for short shares)
-  const long long units = (total + a.unit - 1) / a.unit;
-  const long long w_lo = min(total, units * blockIdx.x / gridDim.x * a.unit);
-  const long long w_hi = min(total, units * (blockIdx.x + 1) / gridDim.x * a.unit);
+  //
+  // a.unit == 0 (short shares and at least one CTA per map: the 8-GPU regime): shares never cross a map.  Map m gets q
+  // or q + 1 of the CTAs (q = CTAs / maps) and its chunks are split evenly among them.  A share that crosses a map
+  // boundary costs a second window and, worse, two partial passes (a handful of warps running alone twice): measured
+  // at 32 maps on 148 CTAs, such CTAs took 81-145 us against 57 us for the others.
+  long long w_lo, w_hi;
+  if (a.unit == 0) {
+    const int G = (int)gridDim.x, b = (int)blockIdx.x, q = G / p.M, r = G - q * p.M;    // the first r maps get q + 1 CTAs
+    int m, j, k;
+    if (b < r * (q + 1)) { m = b / (q + 1); j = b - m * (q + 1); k = q + 1; }
+    else { const int b2 = b - r * (q + 1); m = r + b2 / q; j = b2 - (m - r) * q; k = q; }
+    w_lo = (long long)m * cpm + (long long)cpm * j / k;
+    w_hi = (long long)m * cpm + (long long)cpm * (j + 1) / k;
+  } else {
+    const long long units = (total + a.unit - 1) / a.unit;
+    w_lo = min(total, units * blockIdx.x / gridDim.x * a.unit);
+    w_hi = min(total, units * (blockIdx.x + 1) / gridDim.x * a.unit);
+  }
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -417,7 +432,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const int n = has ? (c << 5) + lane : lane;
       const bool live = has && n < p.N;                     // ragged last chunk (n is padded to whole warps): such lanes
       const int Tn = live ? p.T : 0;                        // run zero steps and store nothing, but stay with their warp
-    const double2* __restrict__ ep = reinterpret_cast<const double2*>(a.noiseT) + (a.stagger == -1 ? (n & ~31) : a.stagger == -2 ? (n & ~31) + (lane >> 1) : a.stagger == -3 ? (n & ~31) + (lane >> 2) : n);   // DIAG
+    const double2* __restrict__ ep = reinterpret_cast<const double2*>(a.noiseT) + n;
     float x = p.x0[0], y = p.x0[1], th = p.x0[2];
     // the float64 state is carried UNROUNDED across the back edge (rx, ry, rt: the float64 FMA results, initially the
     // float32 state itself) and rounded to float32 precision at the top of the next step: the FMA of a step then
@@ -425,7 +440,8 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     double rx = widen(x), ry = widen(y), rt = widen(th);
     float cost = 0.0f, d2 = 1e9f;
     double2 c2 = __ldg(ep);                                 // controls of step t (loaded during step t-1, see below)
-    for (int t = 0; t < Tn; ++t) {
+    int t = 0;
+    for (; t < Tn; ++t) {
       ep += a.npad;
       // ---- cell index of both axes: floor(a/res) by round-down magic-number addition on the FP32 pipe, taken
       //      at BOTH ends of an interval that contains the exact quotient a/res (relative half-width 2.4e-7,
@@ -472,12 +488,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), c2.y, th64);
       // `c2` is dead from here on: fetch the next step's controls straight into it -- the rest of this step and the
       // cell lookup of the next one (~70 instructions per warp, 32 warps per SM) cover the L2 latency
-      if (a.stagger > -4) c2 = __ldg(ep);
-      else if (a.stagger == -4) c2 = __ldcg(ep);
-      else if (a.stagger == -5) asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(c2.x), "=d"(c2.y) : "l"(ep));
-      else if (a.stagger == -6) { c2.x = __ldg(&ep->x); c2.y = __ldg(&ep->y); }
-      else asm volatile("ld.global.nc.L1::evict_first.v2.f64 {%0, %1}, [%2];" : "=d"(c2.x), "=d"(c2.y) : "l"(ep));
-      // DIAG (row T exists: the buffer has T + 1 rows, no guard needed)
+      c2 = __ldg(ep);                                       // (row T exists: the buffer has T + 1 rows, no guard needed)
       x = narrow(rx); y = narrow(ry); th = narrow(rt);
       // ---- stage cost (mppi.py:696-701)
       const float dx = fsub(gx, x), dy = fsub(gy, y);
@@ -488,6 +499,10 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     }
     // the loop is left early exactly when d2 <= tol2 and otherwise ends with d2 > tol2 (d2 = 1e9 for T = 0), so the
     // reference's goal_reached flag is recovered from d2 -- no flag register (and no constant) inside the loop
+    if (a.dbg) {                                            // debug hook: steps this warp ran for the chunk (its slowest lane)
+      const int steps = __reduce_max_sync(0xffffffffu, t < Tn ? t + 1 : t);
+      if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 6 * blockIdx.x + 5, (unsigned long long)steps << 40);
+    }
     const float not_reached = (d2 <= p.tol2) ? 0.0f : 1.0f;
     cost = fadd(cost, a.ctrl[n]);                                           // control cost (mppi.py:708-710)
     const double num = f2d(not_reached) * f2d(sqrt_approx(d2));              // terminal cost (mppi.py:26-28)
@@ -498,9 +513,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   if (a.dbg && tid == 0) {                                  // per-CTA wall time (tools/rollout_cta_times.py)
     a.dbg[6 * blockIdx.x + 0] = dbg_t0;
     a.dbg[6 * blockIdx.x + 1] = (long long)globaltimer_ns();
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    a.dbg[6 * blockIdx.x + 2] = w_lo | ((long long)smid << 40);           // SM id in the upper bits
+    a.dbg[6 * blockIdx.x + 2] = w_lo | ((long long)sm_id() << 40);           // SM id in the upper bits
     a.dbg[6 * blockIdx.x + 3] = w_hi;
   }
   // sharded solve, peer-memory exchange: the costs above went straight into the receive buffers of the ranks that
@@ -643,7 +656,7 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
   // whole passes (32 chunks) per share once a share is at least 4 passes long (no end-of-segment stragglers); shorter
   // shares stay chunk-granular: rounding 3.46 passes per CTA (a rank of a 4-GPU solve) to 3 or 4 costs more than it
   // saves (measured 0.387 against 0.308 ms)
-  b.unit = (total / (32LL * grid.x) >= 4) ? 32 : 1;
+  b.unit = (total / (32LL * grid.x) >= 4) ? 32 : ((int)grid.x >= a.p.M ? 0 : 1);
   const long long passes = (total + 32LL * grid.x - 1) / (32LL * grid.x);
   b.sync_passes = sync_mode >= 0 ? (sync_mode != 0) : (passes <= WIN_SYNC_MAX_PASSES);
   const CUtensorMap& t0 = *reinterpret_cast<const CUtensorMap*>(tm_lin);

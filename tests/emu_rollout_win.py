@@ -63,10 +63,22 @@ static inline int __shfl_sync(unsigned, int v, int src) {
   w.bar.arrive_and_wait();
   return r;
 }
+static inline int __reduce_max_sync(unsigned, int v) {
+  EmuWarp& w = g_warps[threadIdx.x >> 5];
+  w.ibuf[threadIdx.x & 31] = v;
+  w.bar.arrive_and_wait();
+  int r = w.ibuf[0];
+  for (int i = 1; i < 32; ++i) r = w.ibuf[i] > r ? w.ibuf[i] : r;
+  w.bar.arrive_and_wait();
+  return r;
+}
 static inline long long clock64() { return 0; }
 static inline unsigned long long globaltimer_ns() { return 0; }
+static inline unsigned sm_id() { return 0; }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void st_flag_sys(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 struct ulonglong2 { unsigned long long x, y; };
@@ -229,6 +241,7 @@ extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratio
   }
   w.unit = ((long long)p.M * (npad / 32) / (32LL * ctas) >= 1) ? 32 : 1;     // launch_rollout_win
   if (unit_override > 0) w.unit = unit_override;
+  if (unit_override < 0) w.unit = 0;                         // shares by map (needs ctas >= M)
   w.sync_passes = sync_passes;
   run([&] { rollout_win_kernel<1024, 232, 0>(w, t_lin, t_ang, t_obs, t_unk); }, 1024, (unsigned)ctas, 1);
   for (int n = 0; n < p.N; ++n)

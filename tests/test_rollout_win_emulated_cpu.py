@@ -135,7 +135,7 @@ def test_windowed_kernel_on_a_cell_edge_takes_the_exact_sequence(emu):
 
 
 @pytest.mark.parametrize("ctas,blocks,unit,sync", [(0, 1, 0, 0), (1, 1, 0, 0), (3, 1, 0, 1), (7, 3, 0, 0), (5, 7, 0, 1), (3, 1, 32, 0),
-                                                   (2, 1, 16, 1), (1, 1, 32, 1)])
+                                                   (2, 1, 16, 1), (1, 1, 32, 1), (2, 1, -1, 0), (5, 3, -1, 0), (7, 1, -1, 1)])
 def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_oracle(emu, ctas, blocks, unit, sync):
     """N = 2100 control sequences (66 chunks of 32 per map, the last one ragged) x 2 maps on a persistent grid of
     `ctas` CTAs (0: the launcher's own rule): shares of 132 chunks that start and end inside a map, CTAs that
@@ -144,7 +144,8 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
     cost) whatever the grid, and both follow the oracle.  blocks > 1: the sharded destination layout -- every cost
     stored into the "receive buffer" of the rank that reduces its control sequence, flags raised once by the last
     CTA (checked inside the harness).  N = 2100 = 3 x 700 = 7 x 300.  unit > 0: share boundaries at multiples of
-    `unit` chunks (0 = the launcher's rule); sync = 1: the chunks are dealt pass by pass with a CTA barrier in between
+    `unit` chunks (0 = the launcher's rule; -1 = shares that never cross a map: map m gets ctas/M or one more of the
+    CTAs, what the launcher picks for short shares when there are at least as many CTAs as maps); sync = 1: the chunks are dealt pass by pass with a CTA barrier in between
     (what the launcher picks for short shares) instead of pulled from the shared counter."""
     from tests.scenarios import make_scenario, oracle_rollout_costs   # noqa: F401  (scenario generator only)
     from oracle import mppi_ref as MR

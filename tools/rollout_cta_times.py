@@ -27,6 +27,8 @@ solve()
 check(lib.b200mppi_debug_rollout_cta_times(0, out.ctypes.data_as(C.c_void_p), 148))
 smid = out[:, 2] >> 40
 out[:, 2] &= (1 << 40) - 1
+wsteps = out[:, 5] >> 40
+out[:, 5] &= (1 << 40) - 1
 t0 = out[:, 0].min()
 dur = (out[:, 1] - out[:, 0]) / 1e3
 start = (out[:, 0] - t0) / 1e3
@@ -50,6 +52,10 @@ tot = ((out[:, 3] - out[:, 2]) * 32 * sc["T"]).sum()
 print("all CTAs: slow path %.4f of lane-steps, outside the window %.4f; corr(duration, outside) = %.2f" % (
     out[:, 4].sum() / tot, out[:, 5].sum() / tot, np.corrcoef(dur, out[:, 5] / ((out[:, 3] - out[:, 2]) * 32 * sc["T"]))[0, 1]))
 
+print("warp-steps per CTA min/median/max %d / %d / %d; corr(duration, warp-steps) = %.3f; ns per warp-step min/median/max %.1f / %.1f / %.1f" % (
+    wsteps.min(), np.median(wsteps), wsteps.max(), np.corrcoef(dur, wsteps)[0, 1], (dur * 1e3 / wsteps).min(), np.median(dur * 1e3 / wsteps), (dur * 1e3 / wsteps).max()))
+print("by block (duration us / warp-steps):")
+print(" ".join("%d:%.0f/%d" % (b, dur[b], wsteps[b]) for b in range(len(dur))))
 print("by SM id (duration us):")
 o = np.argsort(smid)
 line = []
