@@ -606,6 +606,16 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
        rollout_win_kernel<WIN_THREADS, 232, 2>, rollout_win_kernel<WIN_THREADS, 232, 3>},
       {rollout_win_kernel<WIN_THREADS, 224, 0>, rollout_win_kernel<WIN_THREADS, 224, 1>,
        rollout_win_kernel<WIN_THREADS, 224, 2>, rollout_win_kernel<WIN_THREADS, 224, 3>}};
+  // A/B hook: B200MPPI_WIN_THREADS = 512 | 640 | 768 | 896 (fewer resident warps per SM; WH = 232, XR = 0 only)
+  static const WinKernel alt_kernels[4] = {rollout_win_kernel<512, 232, 0>, rollout_win_kernel<640, 232, 0>,
+                                           rollout_win_kernel<768, 232, 0>, rollout_win_kernel<896, 232, 0>};
+  static int alt_threads = 0;
+  static bool alt_read = false;
+  if (!alt_read) {
+    if (const char* e = getenv("B200MPPI_WIN_THREADS")) alt_threads = atoi(e);
+    if (alt_threads != 512 && alt_threads != 640 && alt_threads != 768 && alt_threads != 896) alt_threads = 0;
+    alt_read = true;
+  }
   {
     // the opt-in is per device (per-context function): a process may run planners on several GPUs
     static bool attr_set[64] = {};
@@ -617,6 +627,7 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
           const cudaError_t e = cudaFuncSetAttribute(kernels[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_MAX_SMEM);
           if (e != cudaSuccess) return e;
         }
+      for (int i = 0; i < 4; ++i) cudaFuncSetAttribute(alt_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_MAX_SMEM);
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
@@ -663,7 +674,10 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
   const CUtensorMap& t1 = *reinterpret_cast<const CUtensorMap*>(tm_ang);
   const CUtensorMap& t2 = *reinterpret_cast<const CUtensorMap*>(tm_obs);
   const CUtensorMap& t3 = *reinterpret_cast<const CUtensorMap*>(tm_unk);
-  kernels[a.WH == 232 ? 0 : 1][xr]<<<grid, WIN_THREADS, L.total, st>>>(b, t0, t1, t2, t3);
+  if (alt_threads && a.WH == 232)
+    alt_kernels[(alt_threads - 512) / 128]<<<grid, alt_threads, L.total, st>>>(b, t0, t1, t2, t3);
+  else
+    kernels[a.WH == 232 ? 0 : 1][xr]<<<grid, WIN_THREADS, L.total, st>>>(b, t0, t1, t2, t3);
   return cudaGetLastError();
 }
 
