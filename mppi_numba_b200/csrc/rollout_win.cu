@@ -308,6 +308,13 @@ constexpr int WIN_WW = 240;       // window width in cells (inner TMA box extent
 // CTA stages that map's window once (thread 0 issues the TMA loads after the CTA has left the previous window), then
 // its warps pull chunks from a shared-memory counter until the map's part of the share is done -- warps whose
 // rollouts reached the goal early simply take the next chunk.
+// per-CTA timing / counting hook (tools/rollout_cta_times.py): compiled in only with -DB200MPPI_WIN_DEBUG_HOOK
+// (B200MPPI_NVCC_FLAGS of build.py) -- the hot loop's register allocation is tight enough for a dead branch to show
+#ifdef B200MPPI_WIN_DEBUG_HOOK
+#define WIN_DBG(a) ((a).dbg != nullptr)
+#else
+#define WIN_DBG(a) false
+#endif
 template <int THREADS, int WH, int XR>
 __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWinArgs a,
                                                                  const __grid_constant__ CUtensorMap tm_lin,
@@ -380,7 +387,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   const float inv_lo = inv_res * (1.0f - 2.4e-7f), inv_hi = inv_res * (1.0f + 2.4e-7f);
   const unsigned uww = (unsigned)a.ww, uwh = (unsigned)a.wh;     // staged AND inside the map (<= WW, WH)
 
-  const long long dbg_t0 = a.dbg ? (long long)globaltimer_ns() : 0;
+  const long long dbg_t0 = WIN_DBG(a) ? (long long)globaltimer_ns() : 0;
   uint32_t phase = 0;
   for (long long w = w_lo; w < w_hi;) {
     const int m = (int)(w / cpm);
@@ -463,7 +470,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
         const uint32_t ad = sb_win + (uint32_t)(wy * WW + wx);
         ql = lds_s8(ad, 0); qa = lds_s8(ad, PLANE); ob = lds_s8(ad, 2 * PLANE); un = lds_s8(ad, 3 * PLANE);
       } else {
-        if (a.dbg) {                                        // debug hook: lane-steps on the slow path / outside the window
+        if (WIN_DBG(a)) {                                   // debug hook: lane-steps on the slow path / outside the window
           atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 6 * blockIdx.x + 4, 1ull);
           if (!(((unsigned)wx < uww) & ((unsigned)wy < uwh)))
             atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 6 * blockIdx.x + 5, 1ull);
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     }
     // the loop is left early exactly when d2 <= tol2 and otherwise ends with d2 > tol2 (d2 = 1e9 for T = 0), so the
     // reference's goal_reached flag is recovered from d2 -- no flag register (and no constant) inside the loop
-    if (a.dbg) {                                            // debug hook: steps this warp ran for the chunk (its slowest lane)
+    if (WIN_DBG(a)) {                                       // debug hook: steps this warp ran for the chunk (its slowest lane)
       const int steps = __reduce_max_sync(0xffffffffu, t < Tn ? t + 1 : t);
       if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 6 * blockIdx.x + 5, (unsigned long long)steps << 40);
     }
@@ -510,7 +517,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     if (live) *cost_ptr(a.dst, m, n) = cost;                // map-major: the warp's 32 lanes store one 128-byte line
     }
   }
-  if (a.dbg && tid == 0) {                                  // per-CTA wall time (tools/rollout_cta_times.py)
+  if (WIN_DBG(a) && tid == 0) {                                // per-CTA wall time (tools/rollout_cta_times.py)
     a.dbg[6 * blockIdx.x + 0] = dbg_t0;
     a.dbg[6 * blockIdx.x + 1] = (long long)globaltimer_ns();
     a.dbg[6 * blockIdx.x + 2] = w_lo | ((long long)sm_id() << 40);           // SM id in the upper bits
@@ -668,6 +675,13 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
   // shares stay chunk-granular: rounding 3.46 passes per CTA (a rank of a 4-GPU solve) to 3 or 4 costs more than it
   // saves (measured 0.387 against 0.308 ms)
   b.unit = (total / (32LL * grid.x) >= 4) ? 32 : ((int)grid.x >= a.p.M ? 0 : 1);
+  static int unit_override = -1;                            // B200MPPI_WIN_UNIT = 0 | 1 | 32 (A/B hook)
+  static bool unit_read = false;
+  if (!unit_read) {
+    if (const char* e = getenv("B200MPPI_WIN_UNIT")) unit_override = atoi(e);
+    unit_read = true;
+  }
+  if (unit_override == 1 || unit_override == 32 || (unit_override == 0 && (int)grid.x >= a.p.M)) b.unit = unit_override;
   const long long passes = (total + 32LL * grid.x - 1) / (32LL * grid.x);
   b.sync_passes = sync_mode >= 0 ? (sync_mode != 0) : (passes <= WIN_SYNC_MAX_PASSES);
   const CUtensorMap& t0 = *reinterpret_cast<const CUtensorMap*>(tm_lin);
