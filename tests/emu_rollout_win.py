@@ -107,6 +107,9 @@ static inline int lds_s8(uint32_t addr, int imm_plane) { return (int)(int8_t)sme
 static inline double lds_f64(uint32_t addr) { double v; std::memcpy(&v, smem + addr, 8); return v; }
 static inline double widen(float a) { return (double)a; }
 static inline float narrow(double a) { return (float)a; }
+static inline double widen_early(float a) { return (double)a; }
+static inline float narrow_early(double a) { return (float)a; }
+#define WIN_TRIG_AHEAD 1
 '''
 
 HARNESS = r'''
