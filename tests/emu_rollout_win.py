@@ -109,6 +109,8 @@ static inline double widen(float a) { return (double)a; }
 static inline float narrow(double a) { return (float)a; }
 static inline double widen_early(float a) { return (double)a; }
 static inline float narrow_early(double a) { return (float)a; }
+static inline float sin_early(float x) { return sin_approx(x); }
+static inline float cos_early(float x) { return cos_approx(x); }
 #define WIN_TRIG_AHEAD 1
 '''
 
