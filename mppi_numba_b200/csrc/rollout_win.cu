@@ -254,13 +254,26 @@ __device__ __forceinline__ float narrow_early(double a) {
   float r; asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(a)); return r;
 }
 // [emu:begin win_kernel]
+#ifndef WIN_ROUND_FP64
+#define WIN_ROUND_FP64 1
+#endif
 // float64 value rounded to float32 precision (round-to-nearest-even at bit 29), kept as float64:
-// == widen(narrow(a)) for every |a| in the float32 normal range, but on the integer pipe instead of a
-// second XU-pipe conversion (f64 conversions issue at half the MUFU rate on sm_100).
+// == widen(narrow(a)) for every |a| in the float32 normal range, without a second XU-pipe conversion.
+// WIN_ROUND_FP64 = 1 (default): Veltkamp's splitting on the FP64 pipe -- g = RN(a * (2^29 + 1)), hi = RN(g + RN(a - g))
+// is a rounded to 53 - 29 = 24 significant bits, ties to even (three round-to-nearest operations that must not be
+// contracted into an FMA: hence the intrinsics; pinned against the float32 conversion on 10^7 near-tie values in
+// tests/test_rollout_win_emulated_cpu.py).  Three FP64-pipe instructions (that pipe is ~10 % busy) instead of the five
+// integer instructions of the bit-level version below (ncu: the integer pipe is where this kernel's warps queue).
+// A zero loses its sign (-0 -> +0), which no later operation of the step can see.
 __device__ __forceinline__ double round_to_f32_precision(double a) {
+#if WIN_ROUND_FP64
+  const double g = __dmul_rn(a, 536870913.0);
+  return __dadd_rn(g, __dsub_rn(a, g));
+#else
   uint64_t b = ((uint64_t)(uint32_t)__double2hiint(a) << 32) | (uint32_t)__double2loint(a);
   b += 0x0FFFFFFFull + ((b >> 29) & 1ull);          // 64-bit add: the carry into the high word is the add's own
   return __hiloint2double((int)(uint32_t)(b >> 32), (int)((uint32_t)b & 0xE0000000u));
+#endif
 }
 
 // obstacle / unknown penalties (mppi.py:700-701); out of line: taken for ~2 % of the steps, and as

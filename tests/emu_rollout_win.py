@@ -107,6 +107,9 @@ static inline int lds_s8(uint32_t addr, int imm_plane) { return (int)(int8_t)sme
 static inline double lds_f64(uint32_t addr) { double v; std::memcpy(&v, smem + addr, 8); return v; }
 static inline double widen(float a) { return (double)a; }
 static inline float narrow(double a) { return (float)a; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double widen_early(float a) { return (double)a; }
 static inline float narrow_early(double a) { return (float)a; }
 static inline float sin_early(float x) { return sin_approx(x); }

@@ -217,3 +217,27 @@ def test_fused_noise_and_controls_kernel_equals_the_two_kernels(emu, N, T):
     assert (st_out == want_states).all()
     assert (noiseT[:, :N, 0] == np.clip(u_cur[:, None, 0] + noise[:, :, 0].T, 0, 3).astype(np.float64)).all()
     assert (noiseT[:, :N, 1] == np.clip(u_cur[:, None, 1] + noise[:, :, 1].T, F32(-np.pi), F32(np.pi)).astype(np.float64)).all()
+
+
+def test_veltkamp_split_equals_float32_rounding_including_ties():
+    """round_to_f32_precision (csrc/rollout_win.cu, WIN_ROUND_FP64): g = RN(a * (2^29 + 1)), hi = RN(g + RN(a - g)) must be
+    the float64 value of float32(a) -- round to nearest, ties to EVEN -- for every magnitude the state can take.  numpy
+    float64 arithmetic is the same IEEE arithmetic as the kernel's __dmul_rn / __dsub_rn / __dadd_rn.  10^7 values within
+    a few float64 ulps of a 24-bit tie (both parities, binade ends included), exact ties, and random mantissas."""
+    rng = np.random.default_rng(2)
+
+    def split_hi(a):
+        g = a * np.float64(2 ** 29 + 1)
+        return g + (a - g)
+
+    for _ in range(20):
+        m = rng.integers(2 ** 23, 2 ** 24, 500000).astype(np.float64)
+        m[:1000] = 2 ** 24 - 1
+        m[1000:2000] = 2 ** 23
+        e = rng.integers(-60, 60, 500000)
+        off = rng.integers(-3, 4, 500000).astype(np.float64)            # float64 ulps around the tie (2^-29 at this scale)
+        a = (m + 0.5 + off * 2.0 ** -29) * 2.0 ** e * rng.choice([-1.0, 1.0], 500000)
+        assert (split_hi(a) == a.astype(np.float32).astype(np.float64)).all()
+    a = rng.integers(2 ** 52, 2 ** 53, 2000000).astype(np.float64) * 2.0 ** rng.integers(-80, 20, 2000000)
+    assert (split_hi(a) == a.astype(np.float32).astype(np.float64)).all()
+    assert split_hi(np.float64(0.0)) == 0.0 and split_hi(np.float64(-0.0)) == 0.0
