@@ -239,20 +239,6 @@ __device__ __forceinline__ double widen(float a) {
 __device__ __forceinline__ float narrow(double a) {
   float r; asm("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(a)); return r;
 }
-// the same operations as `asm volatile`: kept where the source puts them (the step's sine / cosine are issued one step
-// ahead, right after the heading is known -- see the loop)
-__device__ __forceinline__ float sin_early(float x) {
-  float r; asm volatile("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
-}
-__device__ __forceinline__ float cos_early(float x) {
-  float r; asm volatile("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
-}
-__device__ __forceinline__ double widen_early(float a) {
-  double r; asm volatile("cvt.f64.f32 %0, %1;" : "=d"(r) : "f"(a)); return r;
-}
-__device__ __forceinline__ float narrow_early(double a) {
-  float r; asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(a)); return r;
-}
 // [emu:begin win_kernel]
 #ifndef WIN_ROUND_FP64
 #define WIN_ROUND_FP64 1
@@ -337,9 +323,6 @@ constexpr int WIN_WW = 240;       // window width in cells (inner TMA box extent
 // rollouts reached the goal early simply take the next chunk.
 // per-CTA timing / counting hook (tools/rollout_cta_times.py): compiled in only with -DB200MPPI_WIN_DEBUG_HOOK
 // (B200MPPI_NVCC_FLAGS of build.py) -- the hot loop's register allocation is tight enough for a dead branch to show
-#ifndef WIN_TRIG_AHEAD
-#define WIN_TRIG_AHEAD 1
-#endif
 #ifdef B200MPPI_WIN_DEBUG_HOOK
 #define WIN_DBG(a) ((a).dbg != nullptr)
 #else
@@ -477,19 +460,9 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     double rx = widen(x), ry = widen(y), rt = widen(th);
     float cost = 0.0f, d2 = 1e9f;
     double2 c2 = __ldg(ep);                                 // controls of step t (loaded during step t-1, see below)
-#if WIN_TRIG_AHEAD
-    // sine / cosine of the heading are computed ONE STEP AHEAD: as soon as a step knows its new heading it issues the two
-    // MUFU operations of the next step (and the next step widens them first thing), so that their latency runs under
-    // the cost terms and the next cell lookup instead of sitting between the traction lookup and the position update
-    // (a warp issues in order: the step's dependent chain bounds its rate when the other warps do not fill the gaps)
-    float cs = cos_early(th), sn = sin_early(th);
-#endif
     int t = 0;
     for (; t < Tn; ++t) {
       ep += a.npad;
-#if WIN_TRIG_AHEAD
-      const double wcs = widen_early(cs), wsn = widen_early(sn);
-#endif
       // ---- cell index of both axes: floor(a/res) by round-down magic-number addition on the FP32 pipe, taken
       //      at BOTH ends of an interval that contains the exact quotient a/res (relative half-width 2.4e-7,
       //      1.34x the worst accumulated rounding error, see inv_lo / inv_hi; the +-1e-30 covers a == 0 and flushed
@@ -523,35 +496,20 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       // ---- unicycle step (mppi.py:692-694): float64 FMA, one rounding to float32 per component.  The
       //      float64 copies hold the float32-rounded state, so the reference's f2d(x) costs nothing.
       const double dv = lds_f64(sb_lutL + (uint32_t)(ql * 8)) * c2.x;
-#if !WIN_TRIG_AHEAD
       const float cs = cos_approx(th);
       const float sn = sin_approx(th);
-      const double wcs = widen(cs), wsn = widen(sn);
-#endif
       // float64 copies of the float32-rounded state: XR of the three through the XU pipe (a second conversion,
       // widen(narrow(.))), the others on the integer pipe -- the same values either way
       const double x64 = (XR >= 3) ? widen(x) : round_to_f32_precision(rx);
       const double y64 = (XR >= 2) ? widen(y) : round_to_f32_precision(ry);
       const double th64 = (XR >= 1) ? widen(th) : round_to_f32_precision(rt);
-#if WIN_TRIG_AHEAD
+      rx = fma(dv, widen(cs), x64);
+      ry = fma(dv, widen(sn), y64);
       rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), c2.y, th64);
-      th = narrow_early(rt);
-      cs = cos_early(th); sn = sin_early(th);               // for the NEXT step
-      rx = fma(dv, wcs, x64);
-      ry = fma(dv, wsn, y64);
-#else
-      rx = fma(dv, wcs, x64);
-      ry = fma(dv, wsn, y64);
-      rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), c2.y, th64);
-#endif
       // `c2` is dead from here on: fetch the next step's controls straight into it -- the rest of this step and the
       // cell lookup of the next one (~70 instructions per warp, 32 warps per SM) cover the L2 latency
       c2 = __ldg(ep);                                       // (row T exists: the buffer has T + 1 rows, no guard needed)
-#if WIN_TRIG_AHEAD
-      x = narrow_early(rx); y = narrow_early(ry);
-#else
       x = narrow(rx); y = narrow(ry); th = narrow(rt);
-#endif
       // ---- stage cost (mppi.py:696-701)
       const float dx = fsub(gx, x), dy = fsub(gy, y);
       d2 = ffma(dx, dx, fmul(dy, dy));
@@ -572,6 +530,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     if (live) *cost_ptr(a.dst, m, n) = cost;                // map-major: the warp's 32 lanes store one 128-byte line
     }
   }
+  if (WIN_DBG(a)) __syncthreads();                          // the CTA's end, not the end of thread 0's warp
   if (WIN_DBG(a) && tid == 0) {                                // per-CTA wall time (tools/rollout_cta_times.py)
     a.dbg[6 * blockIdx.x + 0] = dbg_t0;
     a.dbg[6 * blockIdx.x + 1] = (long long)globaltimer_ns();
@@ -668,16 +627,6 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
        rollout_win_kernel<WIN_THREADS, 232, 2>, rollout_win_kernel<WIN_THREADS, 232, 3>},
       {rollout_win_kernel<WIN_THREADS, 224, 0>, rollout_win_kernel<WIN_THREADS, 224, 1>,
        rollout_win_kernel<WIN_THREADS, 224, 2>, rollout_win_kernel<WIN_THREADS, 224, 3>}};
-  // A/B hook: B200MPPI_WIN_THREADS = 512 | 640 | 768 | 896 (fewer resident warps per SM; WH = 232, XR = 0 only)
-  static const WinKernel alt_kernels[4] = {rollout_win_kernel<512, 232, 0>, rollout_win_kernel<640, 232, 0>,
-                                           rollout_win_kernel<768, 232, 0>, rollout_win_kernel<896, 232, 0>};
-  static int alt_threads = 0;
-  static bool alt_read = false;
-  if (!alt_read) {
-    if (const char* e = getenv("B200MPPI_WIN_THREADS")) alt_threads = atoi(e);
-    if (alt_threads != 512 && alt_threads != 640 && alt_threads != 768 && alt_threads != 896) alt_threads = 0;
-    alt_read = true;
-  }
   {
     // the opt-in is per device (per-context function): a process may run planners on several GPUs
     static bool attr_set[64] = {};
@@ -689,7 +638,6 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
           const cudaError_t e = cudaFuncSetAttribute(kernels[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_MAX_SMEM);
           if (e != cudaSuccess) return e;
         }
-      for (int i = 0; i < 4; ++i) cudaFuncSetAttribute(alt_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_MAX_SMEM);
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
@@ -743,10 +691,7 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
   const CUtensorMap& t1 = *reinterpret_cast<const CUtensorMap*>(tm_ang);
   const CUtensorMap& t2 = *reinterpret_cast<const CUtensorMap*>(tm_obs);
   const CUtensorMap& t3 = *reinterpret_cast<const CUtensorMap*>(tm_unk);
-  if (alt_threads && a.WH == 232)
-    alt_kernels[(alt_threads - 512) / 128]<<<grid, alt_threads, L.total, st>>>(b, t0, t1, t2, t3);
-  else
-    kernels[a.WH == 232 ? 0 : 1][xr]<<<grid, WIN_THREADS, L.total, st>>>(b, t0, t1, t2, t3);
+  kernels[a.WH == 232 ? 0 : 1][xr]<<<grid, WIN_THREADS, L.total, st>>>(b, t0, t1, t2, t3);
   return cudaGetLastError();
 }
 

@@ -110,11 +110,7 @@ static inline float narrow(double a) { return (float)a; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
-static inline double widen_early(float a) { return (double)a; }
-static inline float narrow_early(double a) { return (float)a; }
-static inline float sin_early(float x) { return sin_approx(x); }
-static inline float cos_early(float x) { return cos_approx(x); }
-#define WIN_TRIG_AHEAD 1
+
 '''
 
 HARNESS = r'''

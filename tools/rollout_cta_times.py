@@ -1,4 +1,6 @@
 """Per-CTA wall times of the persistent rollout kernel for one rank of a G-rank solve (run alone on one GPU).
+Needs a library built with the hook:  B200MPPI_NVCC_FLAGS=-DB200MPPI_WIN_DEBUG_HOOK python mppi_numba_b200/build.py --force
+(the default build leaves it out: the dead branches cost the hot loop 16 %).
     python tools/rollout_cta_times.py c5 8"""
 import contextlib, ctypes as C, io, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -25,6 +27,9 @@ out = np.zeros((148, 6), np.int64)
 check(lib.b200mppi_debug_rollout_cta_times(1, None, 0))
 solve()
 check(lib.b200mppi_debug_rollout_cta_times(0, out.ctypes.data_as(C.c_void_p), 148))
+if not out[:, 1].any():
+    sys.exit("no data: build the library with -DB200MPPI_WIN_DEBUG_HOOK (see the docstring)")
+out = out[out[:, 1] > 0]                      # the CTAs that ran (B200MPPI_WIN_GRID < 148)
 smid = out[:, 2] >> 40
 out[:, 2] &= (1 << 40) - 1
 wsteps = out[:, 5] >> 40
