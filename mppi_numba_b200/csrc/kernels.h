@@ -129,6 +129,7 @@ struct RolloutWinArgs {
   int unit;                 // share granularity in chunks (set by launch_rollout_win)
   int sync_passes;          // 1: chunks dealt pass by pass with a CTA barrier in between (short shares), 0: shared counter
   long long* dbg;           // per-CTA timing record or null (debug hook)
+  int rotate;               // debug: share of CTA b is the one of (b + rotate) % CTAs (B200MPPI_WIN_ROTATE; which SM runs which work)
   int stagger;              // cycles by which the warps of a scheduler are spread after a window barrier (0: none)
   const int8_t* lin_grid; const int8_t* ang_grid; const int8_t* obstacle; const int8_t* unknown;
   const float* noiseT;      // [T][npad] double2: clipped noisy controls (v, w), already widened to f64

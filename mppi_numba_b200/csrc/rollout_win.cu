@@ -262,11 +262,17 @@ __device__ __forceinline__ double round_to_f32_precision(double a) {
 #endif
 }
 
-// obstacle / unknown penalties (mppi.py:700-701); out of line: taken for ~2 % of the steps, and as
-// predicated inline code its six instructions would be issued on every step
-static __device__ __noinline__ float add_penalties(float cost, int ob, int un, float obs_cost, float unk_cost) {
-  cost = ffma((float)ob, obs_cost, cost);
-  return ffma((float)un, unk_cost, cost);
+// obstacle / unknown penalties (mppi.py:700-701), inside a branch taken when either mask byte is non-zero (a tenth of the
+// warp-steps at BASELINE config 5, up to half for the control sequences that graze obstacles).  Inline and off the XU
+// pipe: float(v) of the int8 mask value by the magic-number trick (exact for |v| < 2^22) instead of I2F -- as an
+// out-of-line call with two conversions queued behind the other warps' MUFU / F2F work the branch cost ~700 cycles per
+// visit (measured with the per-CTA debug hook), which made the CTAs whose rollouts cross obstacles the stragglers of
+// the grid.
+static __device__ __forceinline__ float add_penalties(float cost, int ob, int un, float obs_cost, float unk_cost) {
+  const float fo = fsub(__int_as_float(0x4B400000 + ob), 12582912.0f);
+  const float fu = fsub(__int_as_float(0x4B400000 + un), 12582912.0f);
+  cost = ffma(fo, obs_cost, cost);
+  return ffma(fu, unk_cost, cost);
 }
 
 // everything that is not "cell proven by the magic-number floors and staged in the window" (~0.1 % of the steps near
@@ -358,7 +364,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   // at 32 maps on 148 CTAs, such CTAs took 81-145 us against 57 us for the others.
   long long w_lo, w_hi;
   if (a.unit == 0) {
-    const int G = (int)gridDim.x, b = (int)blockIdx.x, q = G / p.M, r = G - q * p.M;    // the first r maps get q + 1 CTAs
+    const int G = (int)gridDim.x, b = ((int)blockIdx.x + a.rotate) % (int)gridDim.x, q = G / p.M, r = G - q * p.M;    // the first r maps get q + 1 CTAs
     int m, j, k;
     if (b < r * (q + 1)) { m = b / (q + 1); j = b - m * (q + 1); k = q + 1; }
     else { const int b2 = b - r * (q + 1); m = r + b2 / q; j = b2 - (m - r) * q; k = q; }
@@ -481,16 +487,28 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
                         ((unsigned)wx < uww) & ((unsigned)wy < uwh);
       if (__builtin_expect(fast, 1)) {
         const uint32_t ad = sb_win + (uint32_t)(wy * WW + wx);
+#ifdef WIN_DIAG_ONE_LDS
+        ql = lds_s8(ad, 0); qa = ql; ob = 0; un = 0;          // DIAG: timing only (wrong results)
+#else
         ql = lds_s8(ad, 0); qa = lds_s8(ad, PLANE); ob = lds_s8(ad, 2 * PLANE); un = lds_s8(ad, 3 * PLANE);
+#endif
       } else {
         if (WIN_DBG(a)) {                                   // debug hook: lane-steps on the slow path / outside the window
           atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 6 * blockIdx.x + 4, 1ull);
           if (!(((unsigned)wx < uww) & ((unsigned)wy < uwh)))
             atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 6 * blockIdx.x + 5, 1ull);
         }
+        long long dbg_c0 = 0;
+        bool dbg_first = false;
+        if (WIN_DBG(a)) {                                   // per-warp: calls and cycles (first active lane)
+          dbg_first = (int)(threadIdx.x & 31) == __ffs(__activemask()) - 1;
+          if (dbg_first) { atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 1536 + 4 * blockIdx.x + 0, 1ull); dbg_c0 = clock64(); }
+        }
         const int pk = lookup_slow(ax, ay, res, sb_win, uww, uwh, WW, PLANE, a.wx0, a.wy0, p.g.rows, p.g.cols, p.g.grid_rows,
                                    p.g.grid_cols, p.g.grid_pitch, p.g.mask_pitch, g_lin, g_ang, a.obstacle, a.unknown);
         ql = (int)(int8_t)pk; qa = (int)(int8_t)(pk >> 8); ob = (int)(int8_t)(pk >> 16); un = pk >> 24;
+        if (WIN_DBG(a) && dbg_first)
+          atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 1536 + 4 * blockIdx.x + 2, (unsigned long long)(clock64() - dbg_c0));
       }
       // ---- noisy clipped control (mppi.py:686-689): `c2`, precomputed per (n, t) by the prepare kernel
       // ---- unicycle step (mppi.py:692-694): float64 FMA, one rounding to float32 per component.  The
@@ -514,7 +532,17 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const float dx = fsub(gx, x), dy = fsub(gy, y);
       d2 = ffma(dx, dx, fmul(dy, dy));
       cost = fadd(cost, ffma(sqrt_approx(d2), p.dist_weight, p.dt));
-      if (__builtin_expect((ob | un) != 0, 0)) cost = add_penalties(cost, ob, un, p.obs_cost, p.unk_cost);
+      if (__builtin_expect((ob | un) != 0, 0)) {
+        long long dbg_c1 = 0;
+        bool dbg_f1 = false;
+        if (WIN_DBG(a)) {
+          dbg_f1 = (int)(threadIdx.x & 31) == __ffs(__activemask()) - 1;
+          if (dbg_f1) { atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 1536 + 4 * blockIdx.x + 1, 1ull); dbg_c1 = clock64(); }
+        }
+        cost = add_penalties(cost, ob, un, p.obs_cost, p.unk_cost);
+        if (WIN_DBG(a) && dbg_f1)
+          atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 1536 + 4 * blockIdx.x + 3, (unsigned long long)(clock64() - dbg_c1));
+      }
       if (d2 <= p.tol2) break;                              // goal reached (mppi.py:703-706)
     }
     // the loop is left early exactly when d2 <= tol2 and otherwise ends with d2 > tol2 (d2 = 1e9 for T = 0), so the
@@ -667,6 +695,9 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
     stagger_read = true;
   }
   b.stagger = stagger;
+  static int rotate = -1;
+  if (rotate < 0) { const char* e = getenv("B200MPPI_WIN_ROTATE"); rotate = e ? atoi(e) : 0; if (rotate < 0) rotate = 0; }
+  b.rotate = rotate;
   b.dbg = win_debug_buffer;
   static int sync_mode = -1;                                // B200MPPI_WIN_SYNC = 0 | 1 (A/B hook), default: by share length
   static bool sync_read = false;

@@ -22,6 +22,7 @@ struct CUtensorMap { const unsigned char* base; int cols, rows, maps, pitch, WW,
 struct double2 { double x, y; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline int __double2loint(double d) { uint64_t u; std::memcpy(&u, &d, 8); return (int)(uint32_t)u; }
 static inline int __double2hiint(double d) { uint64_t u; std::memcpy(&u, &d, 8); return (int)(uint32_t)(u >> 32); }
 static inline double __hiloint2double(int hi, int lo) {
@@ -75,6 +76,8 @@ static inline int __reduce_max_sync(unsigned, int v) {
 static inline long long clock64() { return 0; }
 static inline unsigned long long globaltimer_ns() { return 0; }
 static inline unsigned sm_id() { return 0; }
+static inline unsigned __activemask() { return 0xffffffffu; }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

@@ -23,13 +23,17 @@ def solve():
     else:
         check(lib.b200mppi_planner_solve_local(pl._handle, 1)); check(lib.b200mppi_planner_synchronize(pl._handle))
 for _ in range(6): solve()
-out = np.zeros((148, 6), np.int64)
+raw = np.zeros((256 + 99, 6), np.int64)        # 148 x 6 per-CTA slots, then (from word 1536) 148 x 4 extra counters
 check(lib.b200mppi_debug_rollout_cta_times(1, None, 0))
 solve()
-check(lib.b200mppi_debug_rollout_cta_times(0, out.ctypes.data_as(C.c_void_p), 148))
+check(lib.b200mppi_debug_rollout_cta_times(0, raw.ctypes.data_as(C.c_void_p), 256 + 99))
+out = raw[:148].copy()
+extra = raw.reshape(-1)[1536:1536 + 148 * 4].reshape(148, 4)
 if not out[:, 1].any():
     sys.exit("no data: build the library with -DB200MPPI_WIN_DEBUG_HOOK (see the docstring)")
-out = out[out[:, 1] > 0]                      # the CTAs that ran (B200MPPI_WIN_GRID < 148)
+ran = out[:, 1] > 0
+extra = extra[ran]
+out = out[ran]                                # the CTAs that ran (B200MPPI_WIN_GRID < 148)
 smid = out[:, 2] >> 40
 out[:, 2] &= (1 << 40) - 1
 wsteps = out[:, 5] >> 40
@@ -59,6 +63,12 @@ print("all CTAs: slow path %.4f of lane-steps, outside the window %.4f; corr(dur
 
 print("warp-steps per CTA min/median/max %d / %d / %d; corr(duration, warp-steps) = %.3f; ns per warp-step min/median/max %.1f / %.1f / %.1f" % (
     wsteps.min(), np.median(wsteps), wsteps.max(), np.corrcoef(dur, wsteps)[0, 1], (dur * 1e3 / wsteps).min(), np.median(dur * 1e3 / wsteps), (dur * 1e3 / wsteps).max()))
+print("slow-path calls per CTA (warp level) min/median/max %d / %d / %d, cycles per call %.0f; penalty calls %d / %d / %d, cycles per call %.0f" % (
+    extra[:, 0].min(), np.median(extra[:, 0]), extra[:, 0].max(), extra[:, 2].sum() / max(extra[:, 0].sum(), 1),
+    extra[:, 1].min(), np.median(extra[:, 1]), extra[:, 1].max(), extra[:, 3].sum() / max(extra[:, 1].sum(), 1)))
+print("corr(duration, slow calls) = %.3f, corr(duration, penalty calls) = %.3f" % (np.corrcoef(dur, extra[:, 0])[0, 1], np.corrcoef(dur, extra[:, 1])[0, 1]))
+print("by block (duration us / slow calls / penalty calls):")
+print(" ".join("%d:%.0f/%d/%d" % (b, dur[b], extra[b, 0], extra[b, 1]) for b in range(len(dur))))
 print("by block (duration us / warp-steps):")
 print(" ".join("%d:%.0f/%d" % (b, dur[b], wsteps[b]) for b in range(len(dur))))
 print("by SM id (duration us):")
