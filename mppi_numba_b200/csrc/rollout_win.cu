@@ -531,25 +531,31 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     if (live) *cost_ptr(a.dst, m, n) = cost;                // map-major: the warp's 32 lanes store one 128-byte line
     }
     // ---- this map has no unclaimed chunk left: warp 0 picks the CTA's next map while the other warps finish theirs
-    // (one thread, plain code: a warp-wide pick -- shuffles, a reduction, or an out-of-line call -- in this outer loop made
-    // the compiler reload six kernel parameters per step inside the hot loop)
-    if (tid == 0) {
+    if (tid < 32) {
+      int f = 0;
+      if (lane == 0) f = atomicAdd(a.queue + p.M, 1);
+      f = __shfl_sync(0xffffffffu, f, 0);
       int next = -1;
-      const int f = atomicAdd(a.queue + p.M, 1);
       if (f < p.M - first_fresh) {
         next = first_fresh + f;                             // a map nobody has started
       } else {
-        // the started map with the most unclaimed chunks; ties go to the first one after this CTA's own rotation, so
-        // that CTAs that look at the same moment spread out.  Failed claims overshoot cpm, hence the test.
-        int best = 0;
-        const int rot = (int)((blockIdx.x * 7u) % (unsigned)p.M);
-        for (int k = 0; k < p.M; ++k) {
-          const int i = (k + rot < p.M) ? k + rot : k + rot - p.M;
+        // the started map with the most unclaimed chunks (ties: a different favourite per CTA); claims by failed pulls
+        // overshoot cpm, hence the max with 0.  key = unclaimed * 2^14 + priority, M <= 2^14
+        unsigned best = 0;
+        for (int i = lane; i < p.M; i += 32) {
           const int left = cpm - *reinterpret_cast<volatile int*>(a.queue + i);
-          if (left > best) { best = left; next = i; }
+          const unsigned prio = (unsigned)(i + (int)blockIdx.x * 7) % (unsigned)p.M;
+          const unsigned key = left > 0 ? ((unsigned)min(left, 0x1ffff) << 14) | ((unsigned)p.M - 1u - prio) : 0u;
+          if (key > best) best = key;                       // (the map index is recovered from the priority below)
+        }
+        best = __reduce_max_sync(0xffffffffu, best);
+        if (best != 0u) {
+          const unsigned prio = (unsigned)p.M - 1u - (best & 0x3fffu);
+          // invert prio = (i + 7 b) mod M
+          next = (int)((prio + (unsigned)p.M - ((unsigned)blockIdx.x * 7u) % (unsigned)p.M) % (unsigned)p.M);
         }
       }
-      *s_map = next;
+      if (lane == 0) *s_map = next;
     }
     __syncthreads();
     m = *s_map;
