@@ -649,7 +649,6 @@ struct b200mppi_planner {
   float* cta_partials = nullptr; float* rank_partial = nullptr; float* state_rollout = nullptr;
   uint64_t* states = nullptr;
   float* noiseT = nullptr; float* ctrl = nullptr; int npad = 0;   // windowed rollout kernel inputs
-  int* win_queue = nullptr;                                         // its work queue (WIN_QUEUE_INTS, zero between launches)
   alignas(64) unsigned char tmaps[4][128];
   const void* tmap_key[6] = {};  // what the cached tensor maps were encoded for (grids, masks, geometry)
   bool use_win = true;
@@ -770,8 +769,6 @@ static int planner_init(b200mppi_planner* p, const b200mppi_config* cfg) {
   CU(cudaMalloc(&p->noiseT, (size_t)(p->T + 1) * p->npad * 2 * sizeof(double)));      // + 1 row: unguarded prefetch
   CU(cudaMemsetAsync(p->noiseT, 0, (size_t)(p->T + 1) * p->npad * 2 * sizeof(double), p->stream));
   CU(cudaMalloc(&p->ctrl, (size_t)p->npad * sizeof(float)));
-  CU(cudaMalloc(&p->win_queue, (size_t)WIN_QUEUE_INTS * sizeof(int)));
-  CU(cudaMemsetAsync(p->win_queue, 0, (size_t)WIN_QUEUE_INTS * sizeof(int), p->stream));
   p->use_win = getenv("B200MPPI_NO_WINDOW") == nullptr;
   CU(cudaMalloc(&p->reach_d, 256));
   CU(cudaMemsetAsync(p->reach_d, 0, 256, p->stream));
@@ -834,7 +831,7 @@ extern "C" int b200mppi_planner_destroy(b200mppi_planner* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   cudaFree(p->noise); cudaFree(p->u_cur); cudaFree(p->u_prev); cudaFree(p->costs); cudaFree(p->weights);
   cudaFree(p->w_raw); cudaFree(p->costs_nm); cudaFree(p->cta_partials); cudaFree(p->rank_partial);
-  cudaFree(p->state_rollout); cudaFree(p->states); cudaFree(p->noiseT); cudaFree(p->ctrl); cudaFree(p->win_queue); cudaFree(p->costs_x);
+  cudaFree(p->state_rollout); cudaFree(p->states); cudaFree(p->noiseT); cudaFree(p->ctrl); cudaFree(p->costs_x);
   cudaFree(p->obstacles); cudaFree(p->reach_d); cudaFree(p->upd_counter_d);
   for (int s = 0; s < P2P_MAX_PEERS; ++s)
     if (p->peer_ipc[s] && p->peer_x[s]) cudaIpcCloseMemHandle(p->peer_x[s]);
@@ -1014,13 +1011,13 @@ static int stage_rollout(b200mppi_planner* p) {
       w.npad = p->npad;
       w.lin_grid = l->grid; w.ang_grid = g->grid; w.obstacle = l->obstacle; w.unknown = l->unknown;
       w.noiseT = p->noiseT; w.ctrl = p->ctrl; w.u_cur = p->u_cur;
-      w.queue = p->win_queue;
       // sharded + peers connected: the all-to-all is this kernel's epilogue (stores into the peers, then the flags)
       const bool direct = p->shard_maps && p->p2p_ready;
       fill_cost_dst(p, w.dst, direct);
       if (direct) {
         const int ws = p->cfg.world_size;
         w.sig.ws = ws; w.sig.rank = p->cfg.rank;
+        w.sig.counter = (unsigned*)(p->xbuf + p->x_counter);
         w.sig.epoch = ++p->epoch_cost;
         for (int r = 0; r < ws; ++r) w.sig.peer_flags[r] = (uint32_t*)(p->peer_x[r] + p->x_flags_cost);
       }

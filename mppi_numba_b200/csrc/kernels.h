@@ -126,9 +126,11 @@ struct RolloutWinArgs {
   int WW, WH, wx0, wy0;     // window size / origin in cells (origin inside the map, wx0 a multiple of 16)
   int ww, wh;               // the part of the window that lies inside the map: staged cells [0, ww) x [0, wh)
   int npad;                 // row length of noiseT
-  int* queue;               // work queue in global memory, M + 2 ints, all zero between launches: [m] = next unclaimed
-                            // chunk of map m, [M] = fresh-map cursor, [M + 1] = CTAs finished (the last one clears it)
+  int unit;                 // share granularity in chunks (set by launch_rollout_win)
+  int sync_passes;          // 1: chunks dealt pass by pass with a CTA barrier in between (short shares), 0: shared counter
   long long* dbg;           // per-CTA timing record or null (debug hook)
+  int rotate;               // debug: share of CTA b is the one of (b + rotate) % CTAs (B200MPPI_WIN_ROTATE; which SM runs which work)
+  int stagger;              // cycles by which the warps of a scheduler are spread after a window barrier (0: none)
   const int8_t* lin_grid; const int8_t* ang_grid; const int8_t* obstacle; const int8_t* unknown;
   const float* noiseT;      // [T][npad] double2: clipped noisy controls (v, w), already widened to f64
   const float* ctrl;        // [npad]
@@ -149,8 +151,7 @@ void launch_noise_prepare(uint64_t* states, float* noise, const float* u_cur, fl
 bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int rows, int maps, int pitch,
                         int WW, int WH);
 void rollout_win_geometry(int T, int* WW, int* WH, size_t* smem);
-void rollout_win_set_debug(long long* dev);    // device buffer of 6 int64 per CTA (<= 256 CTAs) + counters from word 1536, or null
-constexpr int WIN_QUEUE_INTS = 16384 + 2;      // RolloutWinArgs.queue: one counter per map (M <= 16384) + cursor + finished CTAs
+void rollout_win_set_debug(long long* dev);    // device buffer of 4 int64 per CTA (<= 1024 CTAs) or null
 cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, const void* tm_ang, const void* tm_obs,
                                const void* tm_unk, cudaStream_t st);
 // CVaR over M (mppi.py:718-755): costs[n] = mean of the ceil(M*alpha) largest of costs_mn[:, n]

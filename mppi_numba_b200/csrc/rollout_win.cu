@@ -279,19 +279,12 @@ static __device__ __forceinline__ float add_penalties(float cost, int ob, int un
 // cell edges, plus the steps of rollouts that left the window): exact reference cell index, then the staged window
 // if the cell is in it, else global memory with the generic kernel's wrap + clamp.  Out of line: one call site, one
 // reconvergence region in the hot loop.
-static __device__ __noinline__ int lookup_slow(float ax, float ay, float res, float inv_lo, float inv_hi, uint32_t sb_win,
-                                               unsigned uww, unsigned uwh,
+static __device__ __noinline__ int lookup_slow(float ax, float ay, float res, uint32_t sb_win, unsigned uww, unsigned uwh,
                                                int WW, int PLANE, int wx0, int wy0, int rows, int cols, int grid_rows,
                                                int grid_cols, int grid_pitch, int mask_pitch,
                                                const int8_t* __restrict__ g_lin, const int8_t* __restrict__ g_ang,
                                                const int8_t* __restrict__ obstacle, const int8_t* __restrict__ unknown) {
-  // the exact sequence (three divisions) only for the axis whose interval holds an integer: the other axis' cell is
-  // proven by its equal floors (the caller's test, repeated here rather than passed in registers)
-  const float MAGIC = 12582912.0f;
-  const float kx = __fadd_rd(fmaf(ax, inv_lo, -1e-30f), MAGIC), kx2 = __fadd_rd(fmaf(ax, inv_hi, 1e-30f), MAGIC);
-  const float ky = __fadd_rd(fmaf(ay, inv_lo, -1e-30f), MAGIC), ky2 = __fadd_rd(fmaf(ay, inv_hi, 1e-30f), MAGIC);
-  const int xi = (__float_as_int(kx) == __float_as_int(kx2)) ? __float_as_int(kx) - 0x4B400000 : cell_index_exact(ax, res);
-  const int yi = (__float_as_int(ky) == __float_as_int(ky2)) ? __float_as_int(ky) - 0x4B400000 : cell_index_exact(ay, res);
+  const int xi = cell_index_exact(ax, res), yi = cell_index_exact(ay, res);
   const int wx = xi - wx0, wy = yi - wy0;
   int ql, qa, ob, un;
   if ((unsigned)wx < uww && (unsigned)wy < uwh) {
@@ -327,20 +320,13 @@ __host__ __device__ inline WinSmem win_smem_layout(int WW, int WH, int T) {
 
 constexpr int WIN_WW = 240;       // window width in cells (inner TMA box extent: 240 B, multiple of 16)
 
-// Work distribution: PERSISTENT grid, one CTA per SM, work pulled from a queue in global memory.  The work items are
-// 32-rollout chunks (map m, control sequences [32c, 32c + 32)); queue[m] is the next unclaimed chunk of map m.  A CTA
-// works on ONE map at a time: it stages that map's window once (thread 0 issues the TMA loads after the CTA has left
-// the previous window) and its warps claim chunks of that map -- one atomic per chunk, a warp that is done takes the
-// next one -- until the map has none left.  Then the CTA moves on: to a map nobody has started (the fresh-map cursor
-// queue[M]; CTA b starts on map b % M, so the cursor hands out maps from min(CTAs, M) on), else to the started map
-// with the most unclaimed chunks (it helps the CTAs already there: a map may be shared by any number of CTAs, each
-// with its own copy of the window), else it is done.  Why not static shares (rounds 1-2a: contiguous shares of the
-// map-major chunk list): equal chunk counts are not equal times.  Measured with the per-CTA debug hook at BASELINE
-// config 5, the same number of warp-steps took 105-224 us depending on WHICH control sequences and maps a CTA drew
-// (rollouts that graze obstacles or sit on cell edges run the rare paths; re-assigning the shares to other SMs moved
-// the slow CTAs with the work, r = 0.98), so the kernel ended 17 % (one GPU) to 60 % (one rank of eight) after its
-// average CTA.  With the queue an SM that finishes early takes work from the others down to single chunks.
-// The last CTA to finish (ticket queue[M + 1]) zeroes the queue for the next launch.
+// Work distribution: PERSISTENT grid, one CTA per SM.  The work list is the map-major sequence of 32-rollout chunks
+// (map m, control sequences [32c, 32c + 32)); CTA b owns the contiguous share [b*total/G, (b+1)*total/G) of it --
+// every SM gets the same number of chunks whatever M and N are (a (tiles, M) grid of one-tile CTAs quantises: 256
+// tile units on 148 SMs at 8 GPUs = two rounds where 1.73 would do).  A share spans one to a few maps: per map the
+// CTA stages that map's window once (thread 0 issues the TMA loads after the CTA has left the previous window), then
+// its warps pull chunks from a shared-memory counter until the map's part of the share is done -- warps whose
+// rollouts reached the goal early simply take the next chunk.
 // per-CTA timing / counting hook (tools/rollout_cta_times.py): compiled in only with -DB200MPPI_WIN_DEBUG_HOOK
 // (B200MPPI_NVCC_FLAGS of build.py) -- the hot loop's register allocation is tight enough for a dead branch to show
 #ifdef B200MPPI_WIN_DEBUG_HOOK
@@ -367,6 +353,28 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int cpm = a.npad >> 5;                               // chunks per map
+  const long long total = (long long)p.M * cpm;
+  // share boundaries are multiples of a.unit chunks (32 = one chunk per warp of the CTA when the shares are long
+  // enough: every map segment is then a whole number of passes and all warps reach the end-of-segment barrier
+  // together -- ncu showed 0.8 of 7.8 warps parked there with chunk-granular shares; 1 for short shares)
+  //
+  // a.unit == 0 (short shares and at least one CTA per map: the 8-GPU regime): shares never cross a map.  Map m gets q
+  // or q + 1 of the CTAs (q = CTAs / maps) and its chunks are split evenly among them.  A share that crosses a map
+  // boundary costs a second window and, worse, two partial passes (a handful of warps running alone twice): measured
+  // at 32 maps on 148 CTAs, such CTAs took 81-145 us against 57 us for the others.
+  long long w_lo, w_hi;
+  if (a.unit == 0) {
+    const int G = (int)gridDim.x, b = ((int)blockIdx.x + a.rotate) % (int)gridDim.x, q = G / p.M, r = G - q * p.M;    // the first r maps get q + 1 CTAs
+    int m, j, k;
+    if (b < r * (q + 1)) { m = b / (q + 1); j = b - m * (q + 1); k = q + 1; }
+    else { const int b2 = b - r * (q + 1); m = r + b2 / q; j = b2 - (m - r) * q; k = q; }
+    w_lo = (long long)m * cpm + (long long)cpm * j / k;
+    w_hi = (long long)m * cpm + (long long)cpm * (j + 1) / k;
+  } else {
+    const long long units = (total + a.unit - 1) / a.unit;
+    w_lo = min(total, units * blockIdx.x / gridDim.x * a.unit);
+    w_hi = min(total, units * (blockIdx.x + 1) / gridDim.x * a.unit);
+  }
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -400,12 +408,14 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
 
   const long long dbg_t0 = WIN_DBG(a) ? (long long)globaltimer_ns() : 0;
   uint32_t phase = 0;
-  int* s_map = s_next + 1;                                   // next map of this CTA (written by warp 0 between two maps)
-  const int first_fresh = min((int)gridDim.x, p.M);          // maps [0, first_fresh) are the CTAs' starting maps
-  int dbg_chunks = 0;
-  for (int m = (int)(blockIdx.x % (unsigned)p.M); m >= 0;) {
+  for (long long w = w_lo; w < w_hi;) {
+    const int m = (int)(w / cpm);
+    const int c_lo = (int)(w - (long long)m * cpm);
+    const int c_hi = (int)min((long long)cpm, w_hi - (long long)m * cpm);       // this map's part of the share
+    w += c_hi - c_lo;
     __syncthreads();                                        // every warp has left the previous window (and the tables are written)
     if (tid == 0) {
+      *s_next = c_lo;
       // order the CTA's generic-proxy reads of the previous window before the async-proxy writes of the next one
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(bar, 4u * (uint32_t)PLANE);
@@ -414,22 +424,39 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       tma_load_2d(smem + 2 * PLANE, &tm_obs, bar, a.wx0, a.wy0);
       tma_load_2d(smem + 3 * PLANE, &tm_unk, bar, a.wx0, a.wy0);
     }
-    __syncthreads();                                        // the loads are issued (the barrier's transaction count is armed)
+    __syncthreads();                                        // s_next visible
     mbar_wait(bar, phase);
     phase ^= 1u;
+    // the barrier above releases all 32 warps in lockstep: they would hit the XU / LSU / FP64 sections of the step
+    // together, pass after pass.  Spread the warps of a scheduler over one step period (a.stagger cycles per slot)
+    if (a.stagger > 0) {
+      const long long t0 = clock64();
+      const long long wait = (long long)(tid >> 7) * a.stagger;
+      while (clock64() - t0 < wait) { }
+    }
     const int8_t* __restrict__ g_lin = a.lin_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
     const int8_t* __restrict__ g_ang = a.ang_grid + (size_t)m * p.g.grid_rows * p.g.grid_pitch;
 
-    // a warp claims one chunk of this map at a time (the hardware favours some warps of a scheduler: they simply run
-    // more chunks and the issue slots stay full)
-    for (;;) {
-      int c = 0;
-      if (lane == 0) c = atomicAdd(a.queue + m, 1);
-      c = __shfl_sync(0xffffffffu, c, 0);
-      if (c >= cpm) break;
-      if (WIN_DBG(a) && lane == 0) ++dbg_chunks;
-      const int n = (c << 5) + lane;
-      const bool live = n < p.N;                     // ragged last chunk (n is padded to whole warps): such lanes
+    // How the warps get their chunks: from the shared counter (a warp that is done takes the next chunk; the hardware
+    // favours some warps of a scheduler, they simply run more chunks and the issue slots stay full).  The alternative
+    // kept for A/B timing (a.sync_passes, B200MPPI_WIN_SYNC=1): pass by pass -- warp w takes chunk c_lo + 32*pass + w and
+    // the CTA meets at a barrier after every pass.  It is slower even for two-pass shares: a pass started in lockstep
+    // ends with its low-priority warps running alone at a fraction of the issue rate.
+    for (int pass = 0;; ++pass) {
+      int c;
+      if (a.sync_passes) {
+        if (c_lo + pass * (THREADS / 32) >= c_hi) break;    // CTA-uniform
+        if (pass > 0) __syncthreads();
+        c = c_lo + pass * (THREADS / 32) + (tid >> 5);
+      } else {
+        c = 0;
+        if (lane == 0) c = atomicAdd(s_next, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= c_hi) break;
+      }
+      const bool has = c < c_hi;                            // pass mode: no chunk left for this warp in the last pass
+      const int n = has ? (c << 5) + lane : lane;
+      const bool live = has && n < p.N;                     // ragged last chunk (n is padded to whole warps): such lanes
       const int Tn = live ? p.T : 0;                        // run zero steps and store nothing, but stay with their warp
     const double2* __restrict__ ep = reinterpret_cast<const double2*>(a.noiseT) + n;
     float x = p.x0[0], y = p.x0[1], th = p.x0[2];
@@ -477,7 +504,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
           dbg_first = (int)(threadIdx.x & 31) == __ffs(__activemask()) - 1;
           if (dbg_first) { atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 1536 + 4 * blockIdx.x + 0, 1ull); dbg_c0 = clock64(); }
         }
-        const int pk = lookup_slow(ax, ay, res, inv_lo, inv_hi, sb_win, uww, uwh, WW, PLANE, a.wx0, a.wy0, p.g.rows, p.g.cols, p.g.grid_rows,
+        const int pk = lookup_slow(ax, ay, res, sb_win, uww, uwh, WW, PLANE, a.wx0, a.wy0, p.g.rows, p.g.cols, p.g.grid_rows,
                                    p.g.grid_cols, p.g.grid_pitch, p.g.mask_pitch, g_lin, g_ang, a.obstacle, a.unknown);
         ql = (int)(int8_t)pk; qa = (int)(int8_t)(pk >> 8); ob = (int)(int8_t)(pk >> 16); un = pk >> 24;
         if (WIN_DBG(a) && dbg_first)
@@ -530,55 +557,23 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
     cost = fadd(cost, d2f(num / (f2d(p.v_post) + 1e-6)));
     if (live) *cost_ptr(a.dst, m, n) = cost;                // map-major: the warp's 32 lanes store one 128-byte line
     }
-    // ---- this map has no unclaimed chunk left: warp 0 picks the CTA's next map while the other warps finish theirs
-    if (tid < 32) {
-      int f = 0;
-      if (lane == 0) f = atomicAdd(a.queue + p.M, 1);
-      f = __shfl_sync(0xffffffffu, f, 0);
-      int next = -1;
-      if (f < p.M - first_fresh) {
-        next = first_fresh + f;                             // a map nobody has started
-      } else {
-        // the started map with the most unclaimed chunks (ties: a different favourite per CTA); claims by failed pulls
-        // overshoot cpm, hence the max with 0.  key = unclaimed * 2^14 + priority, M <= 2^14
-        unsigned best = 0;
-        for (int i = lane; i < p.M; i += 32) {
-          const int left = cpm - *reinterpret_cast<volatile int*>(a.queue + i);
-          const unsigned prio = (unsigned)(i + (int)blockIdx.x * 7) % (unsigned)p.M;
-          const unsigned key = left > 0 ? ((unsigned)min(left, 0x1ffff) << 14) | ((unsigned)p.M - 1u - prio) : 0u;
-          if (key > best) best = key;                       // (the map index is recovered from the priority below)
-        }
-        best = __reduce_max_sync(0xffffffffu, best);
-        if (best != 0u) {
-          const unsigned prio = (unsigned)p.M - 1u - (best & 0x3fffu);
-          // invert prio = (i + 7 b) mod M
-          next = (int)((prio + (unsigned)p.M - ((unsigned)blockIdx.x * 7u) % (unsigned)p.M) % (unsigned)p.M);
-        }
-      }
-      if (lane == 0) *s_map = next;
-    }
-    __syncthreads();
-    m = *s_map;
   }
-  if (WIN_DBG(a)) {                                         // per-CTA wall time and chunk count (tools/rollout_cta_times.py)
-    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 6 * blockIdx.x + 3, (unsigned long long)dbg_chunks);
+  if (WIN_DBG(a)) __syncthreads();                          // the CTA's end, not the end of thread 0's warp
+  if (WIN_DBG(a) && tid == 0) {                                // per-CTA wall time (tools/rollout_cta_times.py)
+    a.dbg[6 * blockIdx.x + 0] = dbg_t0;
+    a.dbg[6 * blockIdx.x + 1] = (long long)globaltimer_ns();
+    a.dbg[6 * blockIdx.x + 2] = w_lo | ((long long)sm_id() << 40);           // SM id in the upper bits
+    a.dbg[6 * blockIdx.x + 3] = w_hi;
+  }
+  // sharded solve, peer-memory exchange: the costs above went straight into the receive buffers of the ranks that
+  // reduce them; the LAST CTA to get here raises this rank's epoch flag in every peer (p2p.cu has the protocol)
+  if (a.sig.ws > 0) {
+    __threadfence_system();
     __syncthreads();
     if (tid == 0) {
-      a.dbg[6 * blockIdx.x + 0] = dbg_t0;
-      a.dbg[6 * blockIdx.x + 1] = (long long)globaltimer_ns();
-      a.dbg[6 * blockIdx.x + 2] = (long long)sm_id() << 40;                  // SM id in the upper bits
-    }
-  }
-  // the LAST CTA to get here (ticket queue[M + 1]) zeroes the queue for the next launch and, in a sharded solve with the
-  // peer-memory exchange -- the costs above went straight into the receive buffers of the ranks that reduce them --
-  // raises this rank's epoch flag in every peer (p2p.cu has the protocol)
-  if (a.sig.ws > 0) __threadfence_system();
-  __syncthreads();
-  if (tid == 0) {
-    const int prev = atomicAdd(a.queue + p.M + 1, 1);
-    if (prev == (int)gridDim.x - 1) {
-      for (int i = 0; i < p.M + 2; ++i) a.queue[i] = 0;     // every CTA has made its last read of the queue
-      if (a.sig.ws > 0) {
+      const unsigned prev = atomicAdd(a.sig.counter, 1u);
+      if (prev == gridDim.x - 1) {
+        *a.sig.counter = 0;
         __threadfence_system();
         for (int q = 0; q < a.sig.ws; ++q) st_flag_sys(a.sig.peer_flags[q] + a.sig.rank, a.sig.epoch);
       }
@@ -622,9 +617,14 @@ bool make_u8_tensor_map(void* out_map, const void* base, int rank, int cols, int
 }
 
 constexpr int WIN_THREADS = 1024;
-static long long* win_debug_buffer = nullptr;   // b200mppi_debug_rollout_cta_times: 6 x int64 per CTA (start ns, end ns, SM id << 40,
-                                                // chunks run, lane-steps on the slow path, of which outside the window | warp-steps << 40)
+static long long* win_debug_buffer = nullptr;   // b200mppi_debug_rollout_cta_times: 6 x int64 per CTA (start ns, end ns, share lo / hi,
+                                                // lane-steps on the slow path, of which outside the window)
 void rollout_win_set_debug(long long* dev) { win_debug_buffer = dev; }
+constexpr int WIN_SYNC_MAX_PASSES = 0;    // shares of at most this many passes are run pass by pass (see the kernel);
+                                          // 0 = never: measured on a rank of an 8-GPU solve (2 passes per CTA) 0.207 ms
+                                          // against 0.186 ms with the shared counter -- a pass started in lockstep ends
+                                          // with its low-priority warps alone, the counter keeps the favoured warps busy
+constexpr int WIN_STAGGER_DEFAULT = 0;    // cycles between the warps of a scheduler after a window barrier (B200MPPI_WIN_STAGGER)
 constexpr int WIN_XR_DEFAULT = 0;         // measured on B200: see profiles/ (B200MPPI_WIN_XR sweeps it)
 static int win_grid_override = 0;         // B200MPPI_WIN_GRID (tuning / test hook): number of persistent CTAs
 constexpr int WIN_MAX_SMEM = 232448;      // 227 KB: per-block opt-in limit on sm_100
@@ -687,9 +687,37 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
   const long long total = (long long)a.p.M * (a.npad / 32);
   const int ctas = (int)std::min<long long>(std::max<long long>(total / 8, 1), sms);
   const dim3 grid(win_grid_override > 0 ? win_grid_override : ctas);
-  if (!a.queue || a.p.M > WIN_QUEUE_INTS - 2) return cudaErrorInvalidValue;
   RolloutWinArgs b = a;
+  static int stagger = WIN_STAGGER_DEFAULT;
+  static bool stagger_read = false;
+  if (!stagger_read) {
+    if (const char* e = getenv("B200MPPI_WIN_STAGGER")) stagger = atoi(e);
+    stagger_read = true;
+  }
+  b.stagger = stagger;
+  static int rotate = -1;
+  if (rotate < 0) { const char* e = getenv("B200MPPI_WIN_ROTATE"); rotate = e ? atoi(e) : 0; if (rotate < 0) rotate = 0; }
+  b.rotate = rotate;
   b.dbg = win_debug_buffer;
+  static int sync_mode = -1;                                // B200MPPI_WIN_SYNC = 0 | 1 (A/B hook), default: by share length
+  static bool sync_read = false;
+  if (!sync_read) {
+    if (const char* e = getenv("B200MPPI_WIN_SYNC")) sync_mode = atoi(e);
+    sync_read = true;
+  }
+  // whole passes (32 chunks) per share once a share is at least 4 passes long (no end-of-segment stragglers); shorter
+  // shares stay chunk-granular: rounding 3.46 passes per CTA (a rank of a 4-GPU solve) to 3 or 4 costs more than it
+  // saves (measured 0.387 against 0.308 ms)
+  b.unit = (total / (32LL * grid.x) >= 4) ? 32 : ((int)grid.x >= a.p.M ? 0 : 1);
+  static int unit_override = -1;                            // B200MPPI_WIN_UNIT = 0 | 1 | 32 (A/B hook)
+  static bool unit_read = false;
+  if (!unit_read) {
+    if (const char* e = getenv("B200MPPI_WIN_UNIT")) unit_override = atoi(e);
+    unit_read = true;
+  }
+  if (unit_override == 1 || unit_override == 32 || (unit_override == 0 && (int)grid.x >= a.p.M)) b.unit = unit_override;
+  const long long passes = (total + 32LL * grid.x - 1) / (32LL * grid.x);
+  b.sync_passes = sync_mode >= 0 ? (sync_mode != 0) : (passes <= WIN_SYNC_MAX_PASSES);
   const CUtensorMap& t0 = *reinterpret_cast<const CUtensorMap*>(tm_lin);
   const CUtensorMap& t1 = *reinterpret_cast<const CUtensorMap*>(tm_ang);
   const CUtensorMap& t2 = *reinterpret_cast<const CUtensorMap*>(tm_obs);

@@ -200,7 +200,7 @@ extern "C" int emu_noise_prepare(const uint64_t* states_in, const float* u_cur, 
 extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratios, const int8_t* lin, const int8_t* ang,
                                const int8_t* obs, const int8_t* unk, const float* noise, const float* u_cur,
                                float* costs_nm, int shift_x, int shift_y, int* origin_out, float* reach_out, int ctas,
-                               int dst_blocks) {
+                               int dst_blocks, int unit_override, int sync_passes) {
   using namespace b200;
   RolloutWinArgs w{};
   w.p = params(f, g, ratios);
@@ -246,14 +246,14 @@ extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratio
     const long long total = (long long)p.M * (npad / 32);
     ctas = (int)std::min<long long>(std::max<long long>(total / 8, 1), 148);
   }
-  std::vector<int> queue(p.M + 2, 0);                        // the work queue: zero before, zero again after the launch
-  w.queue = queue.data();
+  w.unit = ((long long)p.M * (npad / 32) / (32LL * ctas) >= 1) ? 32 : 1;     // launch_rollout_win
+  if (unit_override > 0) w.unit = unit_override;
+  if (unit_override < 0) w.unit = 0;                         // shares by map (needs ctas >= M)
+  w.sync_passes = sync_passes;
   run([&] { rollout_win_kernel<1024, 232, 0>(w, t_lin, t_ang, t_obs, t_unk); }, 1024, (unsigned)ctas, 1);
   for (int n = 0; n < p.N; ++n)
     for (int m = 0; m < p.M; ++m)
       costs_nm[(size_t)n * p.M + m] = recv[n / n_per][((size_t)rank * p.M + m) * n_per + n % n_per];
-  for (int v : queue)
-    if (v != 0) return 7;                                     // the last CTA clears the queue for the next launch
   if (ws > 1) {
     if (counter != 0) return 5;
     for (int d = 0; d < ws; ++d)
@@ -296,5 +296,5 @@ def build(out_dir):
     lib.emu_noise_prepare.restype = I
     lib.emu_noise_prepare.argtypes = [P, P, I, I, C.c_float, C.c_float, C.c_float, P, P, P, P, P, P, P]
     lib.emu_rollout_win.restype = I
-    lib.emu_rollout_win.argtypes = [P, P, P, P, P, P, P, P, P, P, I, I, P, P, I, I]
+    lib.emu_rollout_win.argtypes = [P, P, P, P, P, P, P, P, P, P, I, I, P, P, I, I, I, I]
     return lib

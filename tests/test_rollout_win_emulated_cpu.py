@@ -44,7 +44,7 @@ def test_windowed_kernel_matches_reference_and_generic_kernel(emu, gname):
         origin = np.zeros(2, np.int32)
         reach = np.zeros(1, F32)
         assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur),
-                                   _p(out), sx, sy, _p(origin), _p(reach), 0, 1) == 0
+                                   _p(out), sx, sy, _p(origin), _p(reach), 0, 1, 0, 0) == 0
         return out, origin
     inside, origin = run_win(0, 0)
     assert origin[0] % 16 == 0                                    # TMA: 16-byte aligned inner coordinate
@@ -126,7 +126,7 @@ def test_windowed_kernel_on_a_cell_edge_takes_the_exact_sequence(emu):
     geo = _c([R, Cc, R, Cc, Cc, Cc, T, N, M], np.int32)
     out = np.zeros((N, M), F32)
     assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur), _p(out),
-                               0, 0, None, None, 0, 1) == 0
+                               0, 0, None, None, 0, 1, 0, 1) == 0
     cnm, costs = np.zeros((N, M), F32), np.zeros(N, F32)
     gen.emu_rollout(0, _p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), None, _p(noise), _p(u_cur), _p(cnm),
                     _p(costs), None, 0)
@@ -134,17 +134,19 @@ def test_windowed_kernel_on_a_cell_edge_takes_the_exact_sequence(emu):
     assert (out > T * 1e5).all() and (out < (T + 1) * 1e5).all()          # the obstacle penalty of cell (5, 7), T times
 
 
-@pytest.mark.parametrize("ctas,blocks", [(0, 1), (1, 1), (2, 1), (3, 1), (7, 3), (5, 7), (2, 3)])
-def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_oracle(emu, ctas, blocks):
+@pytest.mark.parametrize("ctas,blocks,unit,sync", [(0, 1, 0, 0), (1, 1, 0, 0), (3, 1, 0, 1), (7, 3, 0, 0), (5, 7, 0, 1), (3, 1, 32, 0),
+                                                   (2, 1, 16, 1), (1, 1, 32, 1), (2, 1, -1, 0), (5, 3, -1, 0), (7, 1, -1, 1)])
+def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_oracle(emu, ctas, blocks, unit, sync):
     """N = 2100 control sequences (66 chunks of 32 per map, the last one ragged) x 2 maps on a persistent grid of
-    `ctas` CTAs (0: the launcher's own rule) pulling chunks from the global work queue: CTA b starts on map b % 2, a
-    CTA whose map is exhausted moves to a fresh one or helps on the map with the most unclaimed chunks (one window
-    after the other), the last CTA clears the queue (checked inside the harness); 200 x 200 cells of random traction,
-    obstacles and unknown cells, T = 40: windowed kernel == generic kernel (~1 ulp: pre-summed control cost) whatever
-    the grid, and both follow the oracle.  blocks > 1: the sharded destination layout -- every cost stored into the
-    "receive buffer" of the rank that reduces its control sequence, flags raised once by the last CTA (checked inside
-    the harness).  N = 2100 = 3 x 700 = 7 x 300.  (The harness runs the CTAs one after the other: the first one drains
-    the queue, the others find their starting map exhausted -- the claim protocol itself is one atomic per chunk.)"""
+    `ctas` CTAs (0: the launcher's own rule): shares of 132 chunks that start and end inside a map, CTAs that
+    stage two windows one after the other, warps pulling chunks from the shared counter; 200 x 200 cells of random
+    traction, obstacles and unknown cells, T = 40: windowed kernel == generic kernel (~1 ulp: pre-summed control
+    cost) whatever the grid, and both follow the oracle.  blocks > 1: the sharded destination layout -- every cost
+    stored into the "receive buffer" of the rank that reduces its control sequence, flags raised once by the last
+    CTA (checked inside the harness).  N = 2100 = 3 x 700 = 7 x 300.  unit > 0: share boundaries at multiples of
+    `unit` chunks (0 = the launcher's rule; -1 = shares that never cross a map: map m gets ctas/M or one more of the
+    CTAs, what the launcher picks for short shares when there are at least as many CTAs as maps); sync = 1: the chunks are dealt pass by pass with a CTA barrier in between
+    (what the launcher picks for short shares) instead of pulled from the shared counter."""
     from tests.scenarios import make_scenario, oracle_rollout_costs   # noqa: F401  (scenario generator only)
     from oracle import mppi_ref as MR
     win, gen = emu
@@ -165,7 +167,7 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
     out = np.zeros((N, M), F32)
     reach = np.zeros(1, F32)
     assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur), _p(out),
-                               0, 0, None, _p(reach), ctas, blocks) == 0
+                               0, 0, None, _p(reach), ctas, blocks, unit, sync) == 0
     # the reach statistic of the prepare kernel: max_n sum_t |clip(u_v + e_v)|, never below the exact sum
     vsum = np.abs(np.clip(u_cur[None, :, 0] + noise[:, :, 0], 0, 3).astype(np.float64)).sum(1).max()
     assert vsum <= float(reach[0]) <= vsum * (1 + 1e-5)
@@ -185,7 +187,7 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
         out2 = np.zeros((N, M), F32)
         origin = np.zeros(2, np.int32)
         assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur),
-                                   _p(out2), 110, 100, _p(origin), None, ctas, 1) == 0
+                                   _p(out2), 110, 100, _p(origin), None, ctas, 1, 0, sync) == 0
         assert origin[0] % 16 == 0 and origin[0] > 80 + 16 and origin[1] > 80
         assert (out2 == out).all()
 

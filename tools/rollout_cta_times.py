@@ -46,14 +46,20 @@ M = sc["M"] // G
 cpm = (sc["N"] + 31) // 32
 print("kernel span %.1f us; CTA duration min/median/max %.1f / %.1f / %.1f us; latest start %.1f us" % (end.max(), dur.min(), np.median(dur), dur.max(), start.max()))
 order = np.argsort(-dur)
-for b in list(order[:6]) + list(order[-4:]):
-    steps = max(out[b, 3], 1) * 32 * sc["T"]
-    print("cta %3d dur %6.1f us chunks %3d slow %.4f of lane-steps, outside window %.4f" % (
-        b, dur[b], out[b, 3], out[b, 4] / steps, out[b, 5] / steps), flush=True)
-print("chunks per CTA min/median/max %d / %d / %d" % (out[:, 3].min(), np.median(out[:, 3]), out[:, 3].max()))
-tot = (out[:, 3] * 32 * sc["T"]).sum()
+for b in list(order[:12]) + list(order[-4:]):
+    lo, hi = out[b, 2], out[b, 3]
+    segs = []
+    w = lo
+    while w < hi:
+        m = w // cpm
+        e = min(hi, (m + 1) * cpm)
+        segs.append(int(e - w)); w = e
+    steps = (hi - lo) * 32 * sc["T"]
+    print("cta %3d dur %6.1f us chunks %3d segments %s slow %.3f of lane-steps, outside window %.3f" % (
+        b, dur[b], hi - lo, segs, out[b, 4] / steps, out[b, 5] / steps), flush=True)
+tot = ((out[:, 3] - out[:, 2]) * 32 * sc["T"]).sum()
 print("all CTAs: slow path %.4f of lane-steps, outside the window %.4f; corr(duration, outside) = %.2f" % (
-    out[:, 4].sum() / tot, out[:, 5].sum() / tot, 0.0))
+    out[:, 4].sum() / tot, out[:, 5].sum() / tot, np.corrcoef(dur, out[:, 5] / ((out[:, 3] - out[:, 2]) * 32 * sc["T"]))[0, 1]))
 
 print("warp-steps per CTA min/median/max %d / %d / %d; corr(duration, warp-steps) = %.3f; ns per warp-step min/median/max %.1f / %.1f / %.1f" % (
     wsteps.min(), np.median(wsteps), wsteps.max(), np.corrcoef(dur, wsteps)[0, 1], (dur * 1e3 / wsteps).min(), np.median(dur * 1e3 / wsteps), (dur * 1e3 / wsteps).max()))
