@@ -279,12 +279,19 @@ static __device__ __forceinline__ float add_penalties(float cost, int ob, int un
 // cell edges, plus the steps of rollouts that left the window): exact reference cell index, then the staged window
 // if the cell is in it, else global memory with the generic kernel's wrap + clamp.  Out of line: one call site, one
 // reconvergence region in the hot loop.
-static __device__ __noinline__ int lookup_slow(float ax, float ay, float res, uint32_t sb_win, unsigned uww, unsigned uwh,
+static __device__ __noinline__ int lookup_slow(float ax, float ay, float res, float inv_lo, float inv_hi, uint32_t sb_win,
+                                               unsigned uww, unsigned uwh,
                                                int WW, int PLANE, int wx0, int wy0, int rows, int cols, int grid_rows,
                                                int grid_cols, int grid_pitch, int mask_pitch,
                                                const int8_t* __restrict__ g_lin, const int8_t* __restrict__ g_ang,
                                                const int8_t* __restrict__ obstacle, const int8_t* __restrict__ unknown) {
-  const int xi = cell_index_exact(ax, res), yi = cell_index_exact(ay, res);
+  // the exact sequence (three divisions) only for the axis whose interval holds an integer: the other axis' cell is
+  // proven by its equal floors (the caller's test, repeated here rather than passed in registers)
+  const float MAGIC = 12582912.0f;
+  const float kx = __fadd_rd(fmaf(ax, inv_lo, -1e-30f), MAGIC), kx2 = __fadd_rd(fmaf(ax, inv_hi, 1e-30f), MAGIC);
+  const float ky = __fadd_rd(fmaf(ay, inv_lo, -1e-30f), MAGIC), ky2 = __fadd_rd(fmaf(ay, inv_hi, 1e-30f), MAGIC);
+  const int xi = (__float_as_int(kx) == __float_as_int(kx2)) ? __float_as_int(kx) - 0x4B400000 : cell_index_exact(ax, res);
+  const int yi = (__float_as_int(ky) == __float_as_int(ky2)) ? __float_as_int(ky) - 0x4B400000 : cell_index_exact(ay, res);
   const int wx = xi - wx0, wy = yi - wy0;
   int ql, qa, ob, un;
   if ((unsigned)wx < uww && (unsigned)wy < uwh) {
@@ -498,17 +505,9 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
           if (!(((unsigned)wx < uww) & ((unsigned)wy < uwh)))
             atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 6 * blockIdx.x + 5, 1ull);
         }
-        long long dbg_c0 = 0;
-        bool dbg_first = false;
-        if (WIN_DBG(a)) {                                   // per-warp: calls and cycles (first active lane)
-          dbg_first = (int)(threadIdx.x & 31) == __ffs(__activemask()) - 1;
-          if (dbg_first) { atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 1536 + 4 * blockIdx.x + 0, 1ull); dbg_c0 = clock64(); }
-        }
-        const int pk = lookup_slow(ax, ay, res, sb_win, uww, uwh, WW, PLANE, a.wx0, a.wy0, p.g.rows, p.g.cols, p.g.grid_rows,
+        const int pk = lookup_slow(ax, ay, res, inv_lo, inv_hi, sb_win, uww, uwh, WW, PLANE, a.wx0, a.wy0, p.g.rows, p.g.cols, p.g.grid_rows,
                                    p.g.grid_cols, p.g.grid_pitch, p.g.mask_pitch, g_lin, g_ang, a.obstacle, a.unknown);
         ql = (int)(int8_t)pk; qa = (int)(int8_t)(pk >> 8); ob = (int)(int8_t)(pk >> 16); un = pk >> 24;
-        if (WIN_DBG(a) && dbg_first)
-          atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 1536 + 4 * blockIdx.x + 2, (unsigned long long)(clock64() - dbg_c0));
       }
       // ---- noisy clipped control (mppi.py:686-689): `c2`, precomputed per (n, t) by the prepare kernel
       // ---- unicycle step (mppi.py:692-694): float64 FMA, one rounding to float32 per component.  The
@@ -532,17 +531,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const float dx = fsub(gx, x), dy = fsub(gy, y);
       d2 = ffma(dx, dx, fmul(dy, dy));
       cost = fadd(cost, ffma(sqrt_approx(d2), p.dist_weight, p.dt));
-      if (__builtin_expect((ob | un) != 0, 0)) {
-        long long dbg_c1 = 0;
-        bool dbg_f1 = false;
-        if (WIN_DBG(a)) {
-          dbg_f1 = (int)(threadIdx.x & 31) == __ffs(__activemask()) - 1;
-          if (dbg_f1) { atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 1536 + 4 * blockIdx.x + 1, 1ull); dbg_c1 = clock64(); }
-        }
-        cost = add_penalties(cost, ob, un, p.obs_cost, p.unk_cost);
-        if (WIN_DBG(a) && dbg_f1)
-          atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 1536 + 4 * blockIdx.x + 3, (unsigned long long)(clock64() - dbg_c1));
-      }
+      if (__builtin_expect((ob | un) != 0, 0)) cost = add_penalties(cost, ob, un, p.obs_cost, p.unk_cost);
       if (d2 <= p.tol2) break;                              // goal reached (mppi.py:703-706)
     }
     // the loop is left early exactly when d2 <= tol2 and otherwise ends with d2 > tol2 (d2 = 1e9 for T = 0), so the

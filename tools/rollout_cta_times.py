@@ -1,4 +1,6 @@
-"""Per-CTA wall times of the persistent rollout kernel for one rank of a G-rank solve (run alone on one GPU).
+"""Per-CTA wall times of the persistent rollout kernel (CAUTION: the hook itself slows the kernel by ~16 %, and its
+slow-path counters are global atomics per slow lane-step -- they stretch exactly the CTAs whose rollouts take the rare
+paths; use it for which-CTA-does-what questions, not for how much the production kernel's CTAs differ) for one rank of a G-rank solve (run alone on one GPU).
 Needs a library built with the hook:  B200MPPI_NVCC_FLAGS=-DB200MPPI_WIN_DEBUG_HOOK python mppi_numba_b200/build.py --force
 (the default build leaves it out: the dead branches cost the hot loop 16 %).
     python tools/rollout_cta_times.py c5 8"""
@@ -63,12 +65,6 @@ print("all CTAs: slow path %.4f of lane-steps, outside the window %.4f; corr(dur
 
 print("warp-steps per CTA min/median/max %d / %d / %d; corr(duration, warp-steps) = %.3f; ns per warp-step min/median/max %.1f / %.1f / %.1f" % (
     wsteps.min(), np.median(wsteps), wsteps.max(), np.corrcoef(dur, wsteps)[0, 1], (dur * 1e3 / wsteps).min(), np.median(dur * 1e3 / wsteps), (dur * 1e3 / wsteps).max()))
-print("slow-path calls per CTA (warp level) min/median/max %d / %d / %d, cycles per call %.0f; penalty calls %d / %d / %d, cycles per call %.0f" % (
-    extra[:, 0].min(), np.median(extra[:, 0]), extra[:, 0].max(), extra[:, 2].sum() / max(extra[:, 0].sum(), 1),
-    extra[:, 1].min(), np.median(extra[:, 1]), extra[:, 1].max(), extra[:, 3].sum() / max(extra[:, 1].sum(), 1)))
-print("corr(duration, slow calls) = %.3f, corr(duration, penalty calls) = %.3f" % (np.corrcoef(dur, extra[:, 0])[0, 1], np.corrcoef(dur, extra[:, 1])[0, 1]))
-print("by block (duration us / slow calls / penalty calls):")
-print(" ".join("%d:%.0f/%d/%d" % (b, dur[b], extra[b, 0], extra[b, 1]) for b in range(len(dur))))
 print("by block (duration us / warp-steps):")
 print(" ".join("%d:%.0f/%d" % (b, dur[b], wsteps[b]) for b in range(len(dur))))
 print("by SM id (duration us):")
