@@ -711,19 +711,7 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
   const CUtensorMap& t1 = *reinterpret_cast<const CUtensorMap*>(tm_ang);
   const CUtensorMap& t2 = *reinterpret_cast<const CUtensorMap*>(tm_obs);
   const CUtensorMap& t3 = *reinterpret_cast<const CUtensorMap*>(tm_unk);
-  // B200MPPI_WIN_THREADS=896 | 768 (A/B hook): fewer resident warps per SM (WH = 232, XR = 0 only)
-  static const WinKernel alt_kernels[2] = {rollout_win_kernel<896, 232, 0>, rollout_win_kernel<768, 232, 0>};
-  static int alt_threads = -1;
-  if (alt_threads < 0) {
-    const char* e = getenv("B200MPPI_WIN_THREADS");
-    alt_threads = e ? atoi(e) : 0;
-    if (alt_threads != 896 && alt_threads != 768) alt_threads = 0;
-    for (int i = 0; i < 2; ++i) cudaFuncSetAttribute(alt_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_MAX_SMEM);
-  }
-  if (alt_threads && a.WH == 232 && b.unit == 0)
-    alt_kernels[alt_threads == 896 ? 0 : 1]<<<grid, alt_threads, L.total, st>>>(b, t0, t1, t2, t3);
-  else
-    kernels[a.WH == 232 ? 0 : 1][xr]<<<grid, WIN_THREADS, L.total, st>>>(b, t0, t1, t2, t3);
+  kernels[a.WH == 232 ? 0 : 1][xr]<<<grid, WIN_THREADS, L.total, st>>>(b, t0, t1, t2, t3);
   return cudaGetLastError();
 }
 
