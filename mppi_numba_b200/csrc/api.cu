@@ -66,6 +66,7 @@ struct b200mppi_tdm {
   float bounds[2] = {0, 1};
   float res = 1, pxl[2] = {0, 0}, pyl[2] = {0, 0};
   int8_t* obstacle = nullptr; int8_t* unknown = nullptr; int8_t* risk = nullptr;
+  bool masks01 = true;            // every obstacle / unknown byte is 0 or 1 (b200mppi_tdm_set_masks checks the host arrays)
   size_t mask_cap = 0, risk_cap = 0;
   int mask_rows = 0, mask_cols = 0, mask_pitch = 0;
   int64_t launches = 0;
@@ -543,6 +544,18 @@ extern "C" int b200mppi_tdm_set_masks(b200mppi_tdm* t, const int8_t* obs, const 
   rc = upload_plane(t, &t->unknown, &cap2, unk, rows, cols, pitch);
   if (rc) return rc;
   CU(cudaStreamSynchronize(t->stream));
+  bool b01 = true;
+  for (const int8_t* m : {obs, unk})
+    if (m)
+    {
+      const size_t n = (size_t)rows * cols;
+      uint64_t bad = 0;                                       // bits other than bit 0 of any byte, eight bytes at a time
+      size_t i = 0;
+      for (; i + 8 <= n; i += 8) { uint64_t w; std::memcpy(&w, m + i, 8); bad |= w & 0xFEFEFEFEFEFEFEFEull; }
+      for (; i < n; ++i) bad |= (uint64_t)(uint8_t)m[i] & 0xFEull;
+      b01 = b01 && bad == 0;
+    }
+  t->masks01 = b01;
   t->mask_rows = rows; t->mask_cols = cols; t->mask_pitch = pitch; t->masks_set = true;
   return B200MPPI_OK;
 }
@@ -1009,6 +1022,7 @@ static int stage_rollout(b200mppi_planner* p) {
       w.ww = std::min(WW, l->cols - w.wx0);
       w.wh = std::min(WH, l->rows - w.wy0);
       w.npad = p->npad;
+      w.masks01 = l->masks01 ? 1 : 0;
       w.lin_grid = l->grid; w.ang_grid = g->grid; w.obstacle = l->obstacle; w.unknown = l->unknown;
       w.noiseT = p->noiseT; w.ctrl = p->ctrl; w.u_cur = p->u_cur;
       // sharded + peers connected: the all-to-all is this kernel's epilogue (stores into the peers, then the flags)

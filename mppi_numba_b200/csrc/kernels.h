@@ -126,6 +126,7 @@ struct RolloutWinArgs {
   int WW, WH, wx0, wy0;     // window size / origin in cells (origin inside the map, wx0 a multiple of 16)
   int ww, wh;               // the part of the window that lies inside the map: staged cells [0, ww) x [0, wh)
   int npad;                 // row length of noiseT
+  int masks01;              // every obstacle / unknown byte is 0 or 1 (selects the kernel variant with the cheap penalties)
   int unit;                 // share granularity in chunks (set by launch_rollout_win)
   int sync_passes;          // 1: chunks dealt pass by pass with a CTA barrier in between (short shares), 0: shared counter
   long long* dbg;           // per-CTA timing record or null (debug hook)

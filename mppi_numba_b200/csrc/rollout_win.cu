@@ -341,7 +341,9 @@ constexpr int WIN_WW = 240;       // window width in cells (inner TMA box extent
 #else
 #define WIN_DBG(a) false
 #endif
-template <int THREADS, int WH, int XR>
+// MASK01: every byte of the obstacle / unknown masks is 0 or 1 (checked on the host when they are set): the penalty of a
+// step is then two predicated additions instead of the general multiply-adds
+template <int THREADS, int WH, bool MASK01>
 __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWinArgs a,
                                                                  const __grid_constant__ CUtensorMap tm_lin,
                                                                  const __grid_constant__ CUtensorMap tm_ang,
@@ -515,11 +517,11 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const double dv = lds_f64(sb_lutL + (uint32_t)(ql * 8)) * c2.x;
       const float cs = cos_approx(th);
       const float sn = sin_approx(th);
-      // float64 copies of the float32-rounded state: XR of the three through the XU pipe (a second conversion,
-      // widen(narrow(.))), the others on the integer pipe -- the same values either way
-      const double x64 = (XR >= 3) ? widen(x) : round_to_f32_precision(rx);
-      const double y64 = (XR >= 2) ? widen(y) : round_to_f32_precision(ry);
-      const double th64 = (XR >= 1) ? widen(th) : round_to_f32_precision(rt);
+      // float64 copies of the float32-rounded state, without a second XU-pipe conversion (widen(narrow(.)) measured
+      // slower: the XU pipe is this kernel's busiest)
+      const double x64 = round_to_f32_precision(rx);
+      const double y64 = round_to_f32_precision(ry);
+      const double th64 = round_to_f32_precision(rt);
       rx = fma(dv, widen(cs), x64);
       ry = fma(dv, widen(sn), y64);
       rt = fma(lds_f64(sb_lutA + (uint32_t)(qa * 8)), c2.y, th64);
@@ -531,7 +533,14 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
       const float dx = fsub(gx, x), dy = fsub(gy, y);
       d2 = ffma(dx, dx, fmul(dy, dy));
       cost = fadd(cost, ffma(sqrt_approx(d2), p.dist_weight, p.dt));
-      if (__builtin_expect((ob | un) != 0, 0)) cost = add_penalties(cost, ob, un, p.obs_cost, p.unk_cost);
+      if (MASK01) {
+        // ffma(1, c, cost) == cost + c and ffma(0, c, cost) == cost == cost + 0: add c or +0.0, selected by an integer
+        // multiply of c's bit pattern with the mask byte (no predicate, no branch, no conversion)
+        cost = fadd(cost, __int_as_float(ob * __float_as_int(p.obs_cost)));
+        cost = fadd(cost, __int_as_float(un * __float_as_int(p.unk_cost)));
+      } else if ((ob | un) != 0) {
+        cost = add_penalties(cost, ob, un, p.obs_cost, p.unk_cost);
+      }
       if (d2 <= p.tol2) break;                              // goal reached (mppi.py:703-706)
     }
     // the loop is left early exactly when d2 <= tol2 and otherwise ends with d2 > tol2 (d2 = 1e9 for T = 0), so the
@@ -614,7 +623,6 @@ constexpr int WIN_SYNC_MAX_PASSES = 0;    // shares of at most this many passes 
                                           // against 0.186 ms with the shared counter -- a pass started in lockstep ends
                                           // with its low-priority warps alone, the counter keeps the favoured warps busy
 constexpr int WIN_STAGGER_DEFAULT = 0;    // cycles between the warps of a scheduler after a window barrier (B200MPPI_WIN_STAGGER)
-constexpr int WIN_XR_DEFAULT = 0;         // measured on B200: see profiles/ (B200MPPI_WIN_XR sweeps it)
 static int win_grid_override = 0;         // B200MPPI_WIN_GRID (tuning / test hook): number of persistent CTAs
 constexpr int WIN_MAX_SMEM = 232448;      // 227 KB: per-block opt-in limit on sm_100
 
@@ -631,19 +639,10 @@ int rollout_win_threads() { return WIN_THREADS; }
 cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, const void* tm_ang, const void* tm_obs,
                                const void* tm_unk, cudaStream_t st) {
   const WinSmem L = win_smem_layout(a.WW, a.WH, a.p.T);
-  static int xr = WIN_XR_DEFAULT;
-  static bool xr_read = false;
-  if (!xr_read) {
-    if (const char* e = getenv("B200MPPI_WIN_XR")) xr = atoi(e);     // A/B hook: 0..3 state copies rounded on the XU pipe
-    if (xr < 0 || xr > 3) xr = WIN_XR_DEFAULT;
-    xr_read = true;
-  }
   typedef void (*WinKernel)(const RolloutWinArgs, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap);
-  static const WinKernel kernels[2][4] = {
-      {rollout_win_kernel<WIN_THREADS, 232, 0>, rollout_win_kernel<WIN_THREADS, 232, 1>,
-       rollout_win_kernel<WIN_THREADS, 232, 2>, rollout_win_kernel<WIN_THREADS, 232, 3>},
-      {rollout_win_kernel<WIN_THREADS, 224, 0>, rollout_win_kernel<WIN_THREADS, 224, 1>,
-       rollout_win_kernel<WIN_THREADS, 224, 2>, rollout_win_kernel<WIN_THREADS, 224, 3>}};
+  static const WinKernel kernels[2][2] = {
+      {rollout_win_kernel<WIN_THREADS, 232, false>, rollout_win_kernel<WIN_THREADS, 232, true>},
+      {rollout_win_kernel<WIN_THREADS, 224, false>, rollout_win_kernel<WIN_THREADS, 224, true>}};
   {
     // the opt-in is per device (per-context function): a process may run planners on several GPUs
     static bool attr_set[64] = {};
@@ -651,7 +650,7 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
       for (int i = 0; i < 2; ++i)
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
           const cudaError_t e = cudaFuncSetAttribute(kernels[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_MAX_SMEM);
           if (e != cudaSuccess) return e;
         }
@@ -711,7 +710,7 @@ cudaError_t launch_rollout_win(const RolloutWinArgs& a, const void* tm_lin, cons
   const CUtensorMap& t1 = *reinterpret_cast<const CUtensorMap*>(tm_ang);
   const CUtensorMap& t2 = *reinterpret_cast<const CUtensorMap*>(tm_obs);
   const CUtensorMap& t3 = *reinterpret_cast<const CUtensorMap*>(tm_unk);
-  kernels[a.WH == 232 ? 0 : 1][xr]<<<grid, WIN_THREADS, L.total, st>>>(b, t0, t1, t2, t3);
+  kernels[a.WH == 232 ? 0 : 1][a.masks01 ? 1 : 0]<<<grid, WIN_THREADS, L.total, st>>>(b, t0, t1, t2, t3);
   return cudaGetLastError();
 }
 

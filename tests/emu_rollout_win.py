@@ -200,7 +200,7 @@ extern "C" int emu_noise_prepare(const uint64_t* states_in, const float* u_cur, 
 extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratios, const int8_t* lin, const int8_t* ang,
                                const int8_t* obs, const int8_t* unk, const float* noise, const float* u_cur,
                                float* costs_nm, int shift_x, int shift_y, int* origin_out, float* reach_out, int ctas,
-                               int dst_blocks, int unit_override, int sync_passes) {
+                               int dst_blocks, int unit_override, int sync_passes, int masks01) {
   using namespace b200;
   RolloutWinArgs w{};
   w.p = params(f, g, ratios);
@@ -250,7 +250,9 @@ extern "C" int emu_rollout_win(const float* f, const int* g, const double* ratio
   if (unit_override > 0) w.unit = unit_override;
   if (unit_override < 0) w.unit = 0;                         // shares by map (needs ctas >= M)
   w.sync_passes = sync_passes;
-  run([&] { rollout_win_kernel<1024, 232, 0>(w, t_lin, t_ang, t_obs, t_unk); }, 1024, (unsigned)ctas, 1);
+  w.masks01 = masks01;
+  if (masks01) run([&] { rollout_win_kernel<1024, 232, true>(w, t_lin, t_ang, t_obs, t_unk); }, 1024, (unsigned)ctas, 1);
+  else run([&] { rollout_win_kernel<1024, 232, false>(w, t_lin, t_ang, t_obs, t_unk); }, 1024, (unsigned)ctas, 1);
   for (int n = 0; n < p.N; ++n)
     for (int m = 0; m < p.M; ++m)
       costs_nm[(size_t)n * p.M + m] = recv[n / n_per][((size_t)rank * p.M + m) * n_per + n % n_per];
@@ -296,5 +298,5 @@ def build(out_dir):
     lib.emu_noise_prepare.restype = I
     lib.emu_noise_prepare.argtypes = [P, P, I, I, C.c_float, C.c_float, C.c_float, P, P, P, P, P, P, P]
     lib.emu_rollout_win.restype = I
-    lib.emu_rollout_win.argtypes = [P, P, P, P, P, P, P, P, P, P, I, I, P, P, I, I, I, I]
+    lib.emu_rollout_win.argtypes = [P, P, P, P, P, P, P, P, P, P, I, I, P, P, I, I, I, I, I]
     return lib

@@ -39,12 +39,14 @@ def test_windowed_kernel_matches_reference_and_generic_kernel(emu, gname):
     geo = _c([Hp, Wp, R, Cc, Cc, Wp, T, N, M], np.int32)
     ref = g["sto_cnm_" + gname]
 
+    m01 = int(((obs & ~1) == 0).all() and ((unk & ~1) == 0).all())     # the kernel variant the launcher would pick
+
     def run_win(sx, sy):
         out = np.zeros((N, M), F32)
         origin = np.zeros(2, np.int32)
         reach = np.zeros(1, F32)
         assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur),
-                                   _p(out), sx, sy, _p(origin), _p(reach), 0, 1, 0, 0) == 0
+                                   _p(out), sx, sy, _p(origin), _p(reach), 0, 1, 0, 0, m01) == 0
         return out, origin
     inside, origin = run_win(0, 0)
     assert origin[0] % 16 == 0                                    # TMA: 16-byte aligned inner coordinate
@@ -126,7 +128,7 @@ def test_windowed_kernel_on_a_cell_edge_takes_the_exact_sequence(emu):
     geo = _c([R, Cc, R, Cc, Cc, Cc, T, N, M], np.int32)
     out = np.zeros((N, M), F32)
     assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur), _p(out),
-                               0, 0, None, None, 0, 1, 0, 1) == 0
+                               0, 0, None, None, 0, 1, 0, 1, 0) == 0
     cnm, costs = np.zeros((N, M), F32), np.zeros(N, F32)
     gen.emu_rollout(0, _p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), None, _p(noise), _p(u_cur), _p(cnm),
                     _p(costs), None, 0)
@@ -146,7 +148,8 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
     CTA (checked inside the harness).  N = 2100 = 3 x 700 = 7 x 300.  unit > 0: share boundaries at multiples of
     `unit` chunks (0 = the launcher's rule; -1 = shares that never cross a map: map m gets ctas/M or one more of the
     CTAs, what the launcher picks for short shares when there are at least as many CTAs as maps); sync = 1: the chunks are dealt pass by pass with a CTA barrier in between
-    (what the launcher picks for short shares) instead of pulled from the shared counter."""
+    (what the launcher picks for short shares) instead of pulled from the shared counter.  The masks hold only 0 / 1:
+    both penalty variants of the kernel (MASK01 and the general one) run, alternating over the parameter sets."""
     from tests.scenarios import make_scenario, oracle_rollout_costs   # noqa: F401  (scenario generator only)
     from oracle import mppi_ref as MR
     win, gen = emu
@@ -167,7 +170,7 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
     out = np.zeros((N, M), F32)
     reach = np.zeros(1, F32)
     assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur), _p(out),
-                               0, 0, None, _p(reach), ctas, blocks, unit, sync) == 0
+                               0, 0, None, _p(reach), ctas, blocks, unit, sync, (ctas + blocks) & 1) == 0
     # the reach statistic of the prepare kernel: max_n sum_t |clip(u_v + e_v)|, never below the exact sum
     vsum = np.abs(np.clip(u_cur[None, :, 0] + noise[:, :, 0], 0, 3).astype(np.float64)).sum(1).max()
     assert vsum <= float(reach[0]) <= vsum * (1 + 1e-5)
@@ -187,7 +190,7 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
         out2 = np.zeros((N, M), F32)
         origin = np.zeros(2, np.int32)
         assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur),
-                                   _p(out2), 110, 100, _p(origin), None, ctas, 1, 0, sync) == 0
+                                   _p(out2), 110, 100, _p(origin), None, ctas, 1, 0, sync, 1 - ((ctas + blocks) & 1)) == 0
         assert origin[0] % 16 == 0 and origin[0] > 80 + 16 and origin[1] > 80
         assert (out2 == out).all()
 
