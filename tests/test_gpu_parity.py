@@ -379,11 +379,17 @@ def test_rollout_costs_vs_oracle(eng, mode, N, M, T, H, res, B, near, warm):
         assert (got < 0.5 * np.median(got)).any(), "near-goal case should contain early exits"
 
 
-def test_window_kernel_equals_generic_kernel(eng, monkeypatch):
+@pytest.mark.parametrize("maskmax", [1, 3])
+def test_window_kernel_equals_generic_kernel(eng, monkeypatch, maskmax):
     """The TMA-window kernel and the generic global-memory kernel walk identical trajectories: per-(n,m)
     costs agree to the rounding of the pre-summed control cost (~1 ulp), including rollouts that leave
-    the window (res 0.05 m, T = 128)."""
+    the window (res 0.05 m, T = 128).  maskmax = 1: masks of 0 / 1 (the windowed kernel's MASK01 variant);
+    3: obstacle bytes 0 .. 3 (its general penalty arithmetic)."""
     sc = make_scenario("tdm", N=512, M=16, T=128, H=900, W=900, res=0.05, B=12, seed=8, warm_start=True)
+    if maskmax > 1:
+        rng = np.random.default_rng(3)
+        sc["obstacle"] = (sc["obstacle"].astype(np.int64) * rng.integers(1, maskmax + 1, sc["obstacle"].shape)).astype(sc["obstacle"].dtype)
+        assert sc["obstacle"].max() > 1
     L = eng._lib
     outs = []
     noise = grids = None

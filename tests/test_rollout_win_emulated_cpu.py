@@ -137,7 +137,8 @@ def test_windowed_kernel_on_a_cell_edge_takes_the_exact_sequence(emu):
 
 
 @pytest.mark.parametrize("ctas,blocks,unit,sync", [(0, 1, 0, 0), (1, 1, 0, 0), (3, 1, 0, 1), (7, 3, 0, 0), (5, 7, 0, 1), (3, 1, 32, 0),
-                                                   (2, 1, 16, 1), (1, 1, 32, 1), (2, 1, -1, 0), (5, 3, -1, 0), (7, 1, -1, 1)])
+                                                   (2, 1, 16, 1), (1, 1, 32, 1), (2, 1, -1, 0), (5, 3, -1, 0), (7, 1, -1, 1),
+                                                   (4, 1, 0, 0)])
 def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_oracle(emu, ctas, blocks, unit, sync):
     """N = 2100 control sequences (66 chunks of 32 per map, the last one ragged) x 2 maps on a persistent grid of
     `ctas` CTAs (0: the launcher's own rule): shares of 132 chunks that start and end inside a map, CTAs that
@@ -149,7 +150,8 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
     `unit` chunks (0 = the launcher's rule; -1 = shares that never cross a map: map m gets ctas/M or one more of the
     CTAs, what the launcher picks for short shares when there are at least as many CTAs as maps); sync = 1: the chunks are dealt pass by pass with a CTA barrier in between
     (what the launcher picks for short shares) instead of pulled from the shared counter.  The masks hold only 0 / 1:
-    both penalty variants of the kernel (MASK01 and the general one) run, alternating over the parameter sets."""
+    both penalty variants of the kernel (MASK01 and the general one) run, alternating over the parameter sets;
+    ctas = 4: obstacle bytes in -3 .. 3 through the general variant."""
     from tests.scenarios import make_scenario, oracle_rollout_costs   # noqa: F401  (scenario generator only)
     from oracle import mppi_ref as MR
     win, gen = emu
@@ -159,6 +161,8 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
     lin = rng.integers(0, 101, (M, R, Cc)).astype(np.int8)
     ang = rng.integers(0, 101, (M, R, Cc)).astype(np.int8)
     obs = (rng.random((R, Cc)) < 0.02).astype(np.int8)
+    if ctas == 4:                                            # mask bytes other than 0 / 1 (-3 .. 3): the general penalty variant only
+        obs = (obs * rng.integers(-3, 4, (R, Cc))).astype(np.int8)
     unk = (rng.random((R, Cc)) < 0.02).astype(np.int8)
     noise = (rng.standard_normal((N, T, 2)) * [2, 3]).astype(F32)
     u_cur = np.stack([rng.uniform(0, 2, T), rng.uniform(-1, 1, T)], 1).astype(F32)
@@ -170,7 +174,7 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
     out = np.zeros((N, M), F32)
     reach = np.zeros(1, F32)
     assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur), _p(out),
-                               0, 0, None, _p(reach), ctas, blocks, unit, sync, (ctas + blocks) & 1) == 0
+                               0, 0, None, _p(reach), ctas, blocks, unit, sync, 0 if ctas == 4 else (ctas + blocks) & 1) == 0
     # the reach statistic of the prepare kernel: max_n sum_t |clip(u_v + e_v)|, never below the exact sum
     vsum = np.abs(np.clip(u_cur[None, :, 0] + noise[:, :, 0], 0, 3).astype(np.float64)).sum(1).max()
     assert vsum <= float(reach[0]) <= vsum * (1 + 1e-5)
@@ -190,7 +194,7 @@ def test_windowed_kernel_multi_tile_random_scenario_matches_generic_kernel_and_o
         out2 = np.zeros((N, M), F32)
         origin = np.zeros(2, np.int32)
         assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur),
-                                   _p(out2), 110, 100, _p(origin), None, ctas, 1, 0, sync, 1 - ((ctas + blocks) & 1)) == 0
+                                   _p(out2), 110, 100, _p(origin), None, ctas, 1, 0, sync, 0 if ctas == 4 else 1 - ((ctas + blocks) & 1)) == 0
         assert origin[0] % 16 == 0 and origin[0] > 80 + 16 and origin[1] > 80
         assert (out2 == out).all()
 
