@@ -1,8 +1,8 @@
 // rollout_win.cu -- the stochastic ("CVaR-cost") rollout kernel as it is meant to run on a B200:
-// one CTA works on ONE sampled traction map; the window of that map around the robot (linear and
-// angular traction planes of map m, plus the obstacle / unknown planes shared by all maps) is staged
-// into shared memory with four TMA tensor loads (cp.async.bulk.tensor, zero-filled outside the map),
-// after which every per-step lookup of the 1024 rollouts of the CTA is a shared-memory byte load.
+// a persistent CTA per SM works on ONE sampled traction map at a time; the window of that map around the robot
+// (linear and angular traction planes of map m, plus the obstacle / unknown planes shared by all maps) is staged
+// into shared memory with four TMA tensor loads (cp.async.bulk.tensor), after which every per-step lookup of the
+// CTA's rollouts on that map is a shared-memory byte load.
 // Lanes of a warp share the map and differ in the control sequence n -- the opposite of the
 // reference (mppi_numba/mppi.py:613-755: block = n, thread = m, i.e. 32 different maps per warp-load).
 //
@@ -13,7 +13,7 @@
 //     256-entry float64 table per map type built with the same two operations;
 //   * the cell index uses round-down magic-number arithmetic on the FP32 pipe (no FRND / F2I on the
 //     XU pipe) and falls back to the exact reference sequence near cell edges;
-//   * obstacle / unknown penalties are skipped when the mask byte is 0 (x + 0*c == x exactly);
+//   * obstacle / unknown penalties without an integer-to-float conversion (masks of 0 / 1: cost + bits(c)*mask);
 //   * the control-cost sum over T, identical for all M maps of a control sequence, is computed once
 //     per n by the prepare kernel (rounding differs from the reference's running sum by ~1 ulp).
 // A rollout that leaves the window reads the maps from global memory instead (same values); the window never
@@ -333,7 +333,9 @@ constexpr int WIN_WW = 240;       // window width in cells (inner TMA box extent
 // tile units on 148 SMs at 8 GPUs = two rounds where 1.73 would do).  A share spans one to a few maps: per map the
 // CTA stages that map's window once (thread 0 issues the TMA loads after the CTA has left the previous window), then
 // its warps pull chunks from a shared-memory counter until the map's part of the share is done -- warps whose
-// rollouts reached the goal early simply take the next chunk.
+// rollouts reached the goal early simply take the next chunk.  Short shares (a rank of a 4- or 8-GPU solve): see
+// a.unit == 0 in the kernel.  A global work queue instead of static shares was measured and dropped.
+//
 // per-CTA timing / counting hook (tools/rollout_cta_times.py): compiled in only with -DB200MPPI_WIN_DEBUG_HOOK
 // (B200MPPI_NVCC_FLAGS of build.py) -- the hot loop's register allocation is tight enough for a dead branch to show
 #ifdef B200MPPI_WIN_DEBUG_HOOK
@@ -342,7 +344,7 @@ constexpr int WIN_WW = 240;       // window width in cells (inner TMA box extent
 #define WIN_DBG(a) false
 #endif
 // MASK01: every byte of the obstacle / unknown masks is 0 or 1 (checked on the host when they are set): the penalty of a
-// step is then two predicated additions instead of the general multiply-adds
+// step is then two additions of `c` or +0.0 (selected by an integer multiply) instead of the general multiply-adds
 template <int THREADS, int WH, bool MASK01>
 __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWinArgs a,
                                                                  const __grid_constant__ CUtensorMap tm_lin,
