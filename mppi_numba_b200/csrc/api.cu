@@ -55,6 +55,7 @@ struct b200mppi_tdm {
   // stale ones outside; states_alt still holds the pre-solve generator states, so the whole maps of that very
   // sampling call can be produced on demand (tdm_complete_grid) -- every reader of `grid` outside solve() does
   bool grid_partial = false;
+  bool advance_done = false;        // advance_states already launched for the coming boxed sampling (tdm_pair_advance_early)
   double partial_alpha = 1.0;
   float tr_abs_max = 0.0f;          // max |traction| a sampled byte can decode to: max_b |lo + 0.01*(hi-lo)*q_b|
   int64_t num_gen = 0;
@@ -236,6 +237,28 @@ static int tdm_sample_on(b200mppi_tdm* t, double alpha_dyn, cudaStream_t st, con
 
 // Both TDMs of a planner.  When their generator states are identical (same seed, same history: the
 // reference seeds both with cfg.seed) ONE pass draws each uniform once and samples both maps.
+// The state advance of a boxed pair sampling does not depend on the box: solve() launches it while the host still waits
+// for the reach read-back (the GPU would idle), tdm_sample_pair_on then skips its own.  If the sampling falls back to
+// whole maps after all, that launch stores the very same states again.
+static void tdm_pair_advance_early(b200mppi_tdm* l, b200mppi_tdm* g, double alpha_dyn, cudaStream_t st, int64_t* launches) {
+  if (!l->pmf_set || !g->pmf_set || l == g) return;
+  if (tdm_prepare_thresholds(l, alpha_dyn, st) || tdm_prepare_thresholds(g, alpha_dyn, st)) return;
+  const bool same_stream = l->sig == g->sig && l->rows == g->rows && l->cols == g->cols &&
+                           l->num_maps == g->num_maps && l->pitch == g->pitch &&
+                           l->cfg.tdm_thread_x == g->cfg.tdm_thread_x && l->cfg.tdm_thread_y == g->cfg.tdm_thread_y &&
+                           l->cfg.max_map_rows == g->cfg.max_map_rows;
+  if (!same_stream || !l->thr_ok || !g->thr_ok || tdm_prepare_jump(l, st)) return;
+  SampleGridsV2Args v2{};
+  fill_v2(l, v2, 0);
+  fill_v2(g, v2, 1);
+  if (!sample_grids_v2_fits(v2, 2)) return;
+  launch_advance_states(l->states, l->states_alt, g->states_alt, l->jump_tile_d, l->rows, l->cols, v2.tx, v2.ty,
+                        l->num_maps, st);
+  if (cudaGetLastError() != cudaSuccess) return;
+  l->advance_done = true;
+  *launches += 1;
+}
+
 static int tdm_sample_pair_on(b200mppi_tdm* l, b200mppi_tdm* g, double alpha_dyn, cudaStream_t st, int64_t* launches,
                               const SampleBox* box = nullptr) {
   if (!l->pmf_set || !g->pmf_set) return fail(B200MPPI_ESTATE, "sample_grids: PMF grid not set");
@@ -258,8 +281,10 @@ static int tdm_sample_pair_on(b200mppi_tdm* l, b200mppi_tdm* g, double alpha_dyn
       if (sample_grids_v2_fits(bx, 2)) { v2 = bx; boxed = true; }
     }
     launch_sample_grids_v2(v2, 2, st);
-    if (boxed) launch_advance_states(l->states, l->states_alt, g->states_alt, l->jump_tile_d, l->rows, l->cols, v2.tx,
-                                     v2.ty, l->num_maps, st);
+    const bool early = l->advance_done;
+    l->advance_done = false;
+    if (boxed && !early) launch_advance_states(l->states, l->states_alt, g->states_alt, l->jump_tile_d, l->rows, l->cols,
+                                               v2.tx, v2.ty, l->num_maps, st);
     CHECK_LAUNCH();
     std::swap(l->states, l->states_alt);
     std::swap(g->states, g->states_alt);
@@ -267,9 +292,10 @@ static int tdm_sample_pair_on(b200mppi_tdm* l, b200mppi_tdm* g, double alpha_dyn
     l->partial_alpha = g->partial_alpha = alpha_dyn;
     tdm_advance_sig(l);
     tdm_advance_sig(g);
-    *launches += boxed ? 2 : 1;
+    *launches += (boxed && !early) ? 2 : 1;
     return B200MPPI_OK;
   }
+  l->advance_done = false;
   if ((rc = tdm_sample_on(l, alpha_dyn, st, box))) return rc;
   if ((rc = tdm_sample_on(g, alpha_dyn, st, box))) return rc;
   *launches += (l->grid_partial ? 2 : 1) + (g->grid_partial ? 2 : 1);
@@ -693,6 +719,7 @@ struct b200mppi_planner {
   bool params_set = false;
   bool profiling = false;
   cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_reach = nullptr;   // after the reach read-back copy (planner_reach_box)
   float last_ms[B200MPPI_T_COUNT] = {};
   int64_t launches = 0;
 };
@@ -813,6 +840,7 @@ static int planner_init(b200mppi_planner* p, const b200mppi_config* cfg) {
   CU(cudaMalloc(&p->states, h.size() * sizeof(uint64_t)));
   CU(cudaMemcpyAsync(p->states, h.data(), h.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
   for (auto& e : p->ev) CU(cudaEventCreate(&e));
+  CU(cudaEventCreateWithFlags(&p->ev_reach, cudaEventDisableTiming));
   CU(cudaStreamSynchronize(p->stream));
   return B200MPPI_OK;
 }
@@ -851,6 +879,7 @@ extern "C" int b200mppi_planner_destroy(b200mppi_planner* p) {
   cudaFree(p->xbuf);
   if (p->h_u) cudaFreeHost(p->h_u);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+  if (p->ev_reach) cudaEventDestroy(p->ev_reach);
   if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
   delete p;
   return B200MPPI_OK;
@@ -1127,14 +1156,20 @@ extern "C" int b200mppi_planner_set_obstacles(b200mppi_planner* p, const float* 
 static bool planner_reach_box(b200mppi_planner* p, SampleBox* box, int* how, int* err) {
   *err = B200MPPI_OK;
   *how = 1;
+  if (p->lin) p->lin->advance_done = false;                // (set below, only for the sampling call that follows)
   if (p->box_mode == 0 || !planner_uses_window(p)) return false;
   const b200mppi_tdm* l = p->lin;
   const b200mppi_params& q = p->prm;
   double S = (double)p->T * std::fmax(std::fabs((double)q.vrange[0]), std::fabs((double)q.vrange[1]));
   if (p->box_mode == 2 && q.num_opt == 1 && p->prepared && p->reach_valid) {
     float* h = p->h_u + (size_t)p->T * 2 + 2;
-    if (cudaMemcpyAsync(h, p->reach_d + p->reach_slot, sizeof(float), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
-        cudaStreamSynchronize(p->stream) != cudaSuccess) {
+    // the host waits for the 4 bytes only (an event, not the stream): the state advance queued behind the copy runs
+    // while the host wakes up, sizes the box and launches the sampler
+    const double alpha = p->cfg.mode == B200MPPI_MODE_TDM ? q.alpha_dyn : 1.0;
+    bool ok = cudaMemcpyAsync(h, p->reach_d + p->reach_slot, sizeof(float), cudaMemcpyDeviceToHost, p->stream) == cudaSuccess &&
+              cudaEventRecord(p->ev_reach, p->stream) == cudaSuccess;
+    if (ok) tdm_pair_advance_early(p->lin, p->ang, alpha, p->stream, &p->launches);
+    if (!ok || cudaEventSynchronize(p->ev_reach) != cudaSuccess) {
       *err = fail(B200MPPI_ECUDA, std::string("reach read-back: ") + cudaGetErrorString(cudaGetLastError()));
       return false;
     }
