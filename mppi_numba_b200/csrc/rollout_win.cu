@@ -239,6 +239,11 @@ __device__ __forceinline__ double widen(float a) {
 __device__ __forceinline__ float narrow(double a) {
   float r; asm("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(a)); return r;
 }
+// opaque to the optimiser: the two values stay in their registers instead of being rematerialised at every use
+__device__ __forceinline__ void keep_in_registers(float& a, float& b) { asm volatile("" : "+f"(a), "+f"(b)); }
+// 2^29 + 1 in the constant bank: DMUL takes it as a c[][] operand (as a literal it costs two UMOV per step)
+__constant__ double k_veltkamp_c = 536870913.0;
+#define VELTKAMP_C k_veltkamp_c
 // [emu:begin win_kernel]
 #ifndef WIN_ROUND_FP64
 #define WIN_ROUND_FP64 1
@@ -253,7 +258,7 @@ __device__ __forceinline__ float narrow(double a) {
 // A zero loses its sign (-0 -> +0), which no later operation of the step can see.
 __device__ __forceinline__ double round_to_f32_precision(double a) {
 #if WIN_ROUND_FP64
-  const double g = __dmul_rn(a, 536870913.0);
+  const double g = __dmul_rn(a, VELTKAMP_C);
   return __dadd_rn(g, __dsub_rn(a, g));
 #else
   uint64_t b = ((uint64_t)(uint32_t)__double2hiint(a) << 32) | (uint32_t)__double2loint(a);
@@ -414,7 +419,8 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   // interval half-width 2.4e-7 (relative): the exact quotient q = a/res satisfies |fl(a*fl(inv*(1-+d))) - q(1-+d)| <=
   // 3 * 2^-24 |q| = 1.79e-7 |q| (roundings of 1/res, of the scaled reciprocal, of the FMA), so d = 2.4e-7 keeps q inside
   // [lower end, upper end] with a third to spare; a wider interval only sends more steps to the exact sequence
-  const float inv_lo = inv_res * (1.0f - 2.4e-7f), inv_hi = inv_res * (1.0f + 2.4e-7f);
+  float inv_lo = inv_res * (1.0f - 2.4e-7f), inv_hi = inv_res * (1.0f + 2.4e-7f);
+  keep_in_registers(inv_lo, inv_hi);                       // (else re-derived from inv_res on every step)
   const unsigned uww = (unsigned)a.ww, uwh = (unsigned)a.wh;     // staged AND inside the map (<= WW, WH)
 
   const long long dbg_t0 = WIN_DBG(a) ? (long long)globaltimer_ns() : 0;

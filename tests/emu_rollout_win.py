@@ -76,6 +76,8 @@ static inline int __reduce_max_sync(unsigned, int v) {
 static inline long long clock64() { return 0; }
 static inline unsigned long long globaltimer_ns() { return 0; }
 static inline unsigned sm_id() { return 0; }
+static inline void keep_in_registers(float&, float&) {}
+#define VELTKAMP_C 536870913.0
 static inline unsigned __activemask() { return 0xffffffffu; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
