@@ -574,9 +574,13 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
   // sharded solve, peer-memory exchange: the costs above went straight into the receive buffers of the ranks that
   // reduce them; the LAST CTA to get here raises this rank's epoch flag in every peer (p2p.cu has the protocol)
   if (a.sig.ws > 0) {
-    __threadfence_system();
+    // one fence per CTA: the barrier orders every thread's cost stores before thread 0, whose (cumulative) system-scope
+    // fence then orders them before its ticket -- the pattern of a cooperative grid barrier.  (A fence by each of the
+    // 1024 threads, as in the first version, costs the kernel ~10 us with stores in flight over NVLink.)
+    if (a.stagger == -1) __threadfence_system();            // A/B hook: the first version
     __syncthreads();
     if (tid == 0) {
+      __threadfence_system();
       const unsigned prev = atomicAdd(a.sig.counter, 1u);
       if (prev == gridDim.x - 1) {
         *a.sig.counter = 0;
