@@ -248,3 +248,34 @@ def test_veltkamp_split_equals_float32_rounding_including_ties():
     a = rng.integers(2 ** 52, 2 ** 53, 2000000).astype(np.float64) * 2.0 ** rng.integers(-80, 20, 2000000)
     assert (split_hi(a) == a.astype(np.float32).astype(np.float64)).all()
     assert split_hi(np.float64(0.0)) == 0.0 and split_hi(np.float64(-0.0)) == 0.0
+
+
+@pytest.mark.parametrize("ctas,M,N,unit", [(3, 3, 200, -1), (7, 3, 500, -1), (11, 5, 333, -1), (16, 5, 1000, -1), (5, 5, 64, -1),
+                                           (6, 4, 700, 1), (9, 7, 130, 32)])
+def test_share_arithmetic_covers_every_chunk_once(emu, ctas, M, N, unit):
+    """The share rules of the persistent grid (contiguous shares in units of 1 / 32 chunks, shares that never cross a map)
+    for CTA counts that do not divide the maps or the chunks: every (m, n) cost is written exactly once and equals the
+    generic kernel's (the destination starts as -1; an unwritten or doubly-claimed chunk would show)."""
+    win, gen = emu
+    rng = np.random.default_rng(ctas * 100 + M)
+    T, R, Cc = 6, 260, 250
+    res = F32(0.1)
+    lin = rng.integers(0, 101, (M, R, Cc)).astype(np.int8)
+    ang = rng.integers(0, 101, (M, R, Cc)).astype(np.int8)
+    obs = (rng.random((R, Cc)) < 0.02).astype(np.int8)
+    unk = (rng.random((R, Cc)) < 0.02).astype(np.int8)
+    noise = (rng.standard_normal((N, T, 2)) * [2, 3]).astype(F32)
+    u_cur = np.stack([rng.uniform(0, 2, T), rng.uniform(-1, 1, T)], 1).astype(F32)
+    x0, goal = [12.03, 12.97, 0.7], [20.0, 20.0]
+    f = _fparams(res, 0.0, 0.0, 0.1, x0, goal, 0.5, 0.01, 1.0, [2, 3], [0, 3], [-np.pi, np.pi], 1e5, 1e2, 1.0, 0.0, 0.0)
+    ratios = _ratios([0, 1], [0, 1])
+    geo = _c([R, Cc, R, Cc, Cc, Cc, T, N, M], np.int32)
+    out = np.full((N, M), -1.0, F32)
+    assert win.emu_rollout_win(_p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), _p(noise), _p(u_cur), _p(out),
+                               0, 0, None, None, ctas, 1, unit, 0, 1) == 0
+    cnm, costs = np.zeros((N, M), F32), np.zeros(N, F32)
+    gen.emu_rollout(0, _p(f), _p(geo), _p(ratios), _p(lin), _p(ang), _p(obs), _p(unk), None, _p(noise), _p(u_cur), _p(cnm),
+                    _p(costs), None, 0)
+    assert (out > 0).all()
+    rel = np.abs(out - cnm) / np.maximum(np.abs(cnm), 1e-6)
+    assert rel.max() < 2e-6, rel.max()
