@@ -504,11 +504,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_win_kernel(const RolloutWi
                         ((unsigned)wx < uww) & ((unsigned)wy < uwh);
       if (__builtin_expect(fast, 1)) {
         const uint32_t ad = sb_win + (uint32_t)(wy * WW + wx);
-#ifdef WIN_DIAG_ONE_LDS
-        ql = lds_s8(ad, 0); qa = ql; ob = 0; un = 0;          // DIAG: timing only (wrong results)
-#else
         ql = lds_s8(ad, 0); qa = lds_s8(ad, PLANE); ob = lds_s8(ad, 2 * PLANE); un = lds_s8(ad, 3 * PLANE);
-#endif
       } else {
         if (WIN_DBG(a)) {                                   // debug hook: lane-steps on the slow path / outside the window
           atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg) + 6 * blockIdx.x + 4, 1ull);
