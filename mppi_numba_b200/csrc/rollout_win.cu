@@ -280,6 +280,21 @@ static __device__ __forceinline__ float add_penalties(float cost, int ob, int un
   return ffma(fu, unk_cost, cost);
 }
 
+// floor(a / r) from the magic-number sums k, k2 of the two ends of the interval that contains the exact quotient (the
+// caller's): while both are integers in range (|index| < 2^21: the sums stay in the binade where one ulp is 1), the
+// floor is lo = k - MAGIC if the ends agree, and otherwise lo or hi = lo + 1 -- hi exactly when a >= hi * r, a product
+// of a 22-bit integer and a float32, exact in float64.  No division; what the reference's sequence (cell_index_exact:
+// three float32 divisions) returns is this same true floor.  Anything else (an interval wider than one integer,
+// indices beyond 2^21, NaN) runs that sequence.
+static __device__ __forceinline__ int cell_from_interval(float a, float r, float k, float k2) {
+  const int lo = __float_as_int(k) - 0x4B400000, hi = __float_as_int(k2) - 0x4B400000;
+  if (lo > -(1 << 21) && hi < (1 << 21) && r > 0.0f) {
+    if (hi == lo) return lo;
+    if (hi - lo == 1) return ((double)a >= (double)hi * (double)r) ? hi : lo;
+  }
+  return cell_index_exact(a, r);
+}
+
 // everything that is not "cell proven by the magic-number floors and staged in the window" (~0.1 % of the steps near
 // cell edges, plus the steps of rollouts that left the window): exact reference cell index, then the staged window
 // if the cell is in it, else global memory with the generic kernel's wrap + clamp.  Out of line: one call site, one
@@ -290,13 +305,12 @@ static __device__ __noinline__ int lookup_slow(float ax, float ay, float res, fl
                                                int grid_cols, int grid_pitch, int mask_pitch,
                                                const int8_t* __restrict__ g_lin, const int8_t* __restrict__ g_ang,
                                                const int8_t* __restrict__ obstacle, const int8_t* __restrict__ unknown) {
-  // the exact sequence (three divisions) only for the axis whose interval holds an integer: the other axis' cell is
-  // proven by its equal floors (the caller's test, repeated here rather than passed in registers)
+  // an exact decision only for the axis whose interval holds an integer: the other axis' cell is proven by its equal
+  // floors (the caller's test, repeated here rather than passed in registers)
   const float MAGIC = 12582912.0f;
   const float kx = __fadd_rd(fmaf(ax, inv_lo, -1e-30f), MAGIC), kx2 = __fadd_rd(fmaf(ax, inv_hi, 1e-30f), MAGIC);
   const float ky = __fadd_rd(fmaf(ay, inv_lo, -1e-30f), MAGIC), ky2 = __fadd_rd(fmaf(ay, inv_hi, 1e-30f), MAGIC);
-  const int xi = (__float_as_int(kx) == __float_as_int(kx2)) ? __float_as_int(kx) - 0x4B400000 : cell_index_exact(ax, res);
-  const int yi = (__float_as_int(ky) == __float_as_int(ky2)) ? __float_as_int(ky) - 0x4B400000 : cell_index_exact(ay, res);
+  const int xi = cell_from_interval(ax, res, kx, kx2), yi = cell_from_interval(ay, res, ky, ky2);
   const int wx = xi - wx0, wy = yi - wy0;
   int ql, qa, ob, un;
   if ((unsigned)wx < uww && (unsigned)wy < uwh) {

@@ -195,6 +195,22 @@ extern "C" int emu_noise_prepare(const uint64_t* states_in, const float* u_cur, 
   return 0;
 }
 
+// cell_from_interval (the division-free decision of the rare path) against the reference's exact sequence:
+// out_new[i] = the kernel's result for a[i] (magic-number floors of the interval's ends, then cell_from_interval),
+// out_ref[i] = cell_index_exact(a[i], res); differ[i] = 1 when the floors differed (the decision ran)
+extern "C" void emu_cell_between(const float* a, int n, float res, int* out_new, int* out_ref, int* differ) {
+  using namespace b200;
+  const float inv_res = 1.0f / res;
+  const float inv_lo = inv_res * (1.0f - 2.4e-7f), inv_hi = inv_res * (1.0f + 2.4e-7f);
+  const float MAGIC = 12582912.0f;
+  for (int i = 0; i < n; ++i) {
+    const float k = __fadd_rd(fmaf(a[i], inv_lo, -1e-30f), MAGIC), k2 = __fadd_rd(fmaf(a[i], inv_hi, 1e-30f), MAGIC);
+    differ[i] = __float_as_int(k) != __float_as_int(k2);
+    out_new[i] = cell_from_interval(a[i], res, k, k2);
+    out_ref[i] = cell_index_exact(a[i], res);
+  }
+}
+
 // ctas: number of persistent CTAs (0: launch_rollout_win's own rule for a 148-SM device).
 // dst_blocks: 1 = one map-major (M, N) destination; ws > 1 = the sharded layout, ws separate (ws*M, N/ws) "receive
 // buffers" written at the rows of "rank" 1 (fill_cost_dst with direct = true) plus the epoch flags of CostSignal --
@@ -300,5 +316,7 @@ def build(out_dir):
     lib.emu_noise_prepare.restype = I
     lib.emu_noise_prepare.argtypes = [P, P, I, I, C.c_float, C.c_float, C.c_float, P, P, P, P, P, P, P]
     lib.emu_rollout_win.restype = I
+    lib.emu_cell_between.argtypes = [P, I, C.c_float, P, P, P]
+    lib.emu_cell_between.restype = None
     lib.emu_rollout_win.argtypes = [P, P, P, P, P, P, P, P, P, P, I, I, P, P, I, I, I, I, I]
     return lib

@@ -279,3 +279,34 @@ def test_share_arithmetic_covers_every_chunk_once(emu, ctas, M, N, unit):
     assert (out > 0).all()
     rel = np.abs(out - cnm) / np.maximum(np.abs(cnm), 1e-6)
     assert rel.max() < 2e-6, rel.max()
+
+
+@pytest.mark.parametrize("res", [0.1, 0.05, 0.3, 1.0, 0.0625, 0.7])
+def test_division_free_cell_decision_equals_reference_sequence(emu, res):
+    """cell_from_interval (csrc/rollout_win.cu: floor(a / res) from the magic-number floors of the interval's ends, decided
+    by the exact float64 product hi * res when the interval holds an integer) returns what the reference's exact sequence (cell_index_exact: three
+    float32 divisions) returns -- on coordinates within a few float32 ulps of every kind of cell edge (both signs, indices
+    up to 2^20 and beyond the guarded range), where the decision actually runs, and on random coordinates."""
+    win, _ = emu
+    rng = np.random.default_rng(int(res * 1e4))
+    r32 = F32(res)
+    k = np.concatenate([rng.integers(-2000, 20000, 300000), rng.integers(-(1 << 20), 1 << 20, 200000),
+                        rng.integers(-(1 << 23), 1 << 23, 20000)])
+    edge = (k.astype(np.float64) * np.float64(r32)).astype(F32)                       # the float32 nearest the edge k * res
+    a = edge.copy()
+    for _ in range(3):                                                                # ... and up to 3 ulps either side
+        step = rng.integers(-1, 2, a.size)
+        a = np.where(step > 0, np.nextafter(a, F32(np.inf)), np.where(step < 0, np.nextafter(a, F32(-np.inf)), a)).astype(F32)
+    a = np.concatenate([a, edge, (rng.standard_normal(200000) * 300).astype(F32), np.zeros(4, F32)])
+    a = np.ascontiguousarray(a, F32)
+    new, ref, differ = np.zeros(a.size, np.int32), np.zeros(a.size, np.int32), np.zeros(a.size, np.int32)
+    win.emu_cell_between(_p(a), a.size, float(r32), _p(new), _p(ref), _p(differ))
+    assert differ.sum() > 10000                                                       # the decision ran often
+    bad = np.nonzero(new != ref)[0]
+    assert bad.size == 0, (a[bad[:5]], new[bad[:5]], ref[bad[:5]])
+    # and inside the range where the division-free decision is used (|index| < 2^21) both are the true floor of the exact
+    # quotient of the two float32 values (where float64 can tell); beyond 2^22 the reference's float32 sequence itself
+    # departs from it, which is why the kernel runs that sequence there
+    q = a.astype(np.float64) / np.float64(r32)
+    clear = (np.abs(q - np.round(q)) > 1e-6) & (np.abs(q) < 2 ** 21 - 2)
+    assert (ref[clear] == np.floor(q[clear])).all()
